@@ -1,0 +1,119 @@
+/*
+ * smx.h -- C-ABI of the B200 (sm_100a) alignment engine for SAVEMONEY's hot path.
+ *
+ * Drop-in boundary: these entry points are what the reference's bindings for the path would
+ * call instead of
+ *   parasail.nw_trace / sg_qe_de_trace / sg_qb_db_trace / sw_trace
+ *        (savemoney/modules/ref_query_alignment.py:35,58,68,82,343)          -> smx_align_*
+ *   af.k_mer_offset_analysis_2
+ *        (savemoney/modules/cython_functions/alignment_functions.pyx:46-64,
+ *         called at ref_query_alignment.py:385)                               -> smx_scan_*
+ *   multiprocessing.Pool fan-out over reads / plasmid pairs
+ *        (post_analysis/post_analysis_core.py:56-65, pre_survey/pre_survey_core.py:237-245)
+ *                                                                             -> one handle per GPU
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every HOST buffer is allocated by the caller;
+ *     the library owns only the device workspaces inside a handle.
+ *   - return value: 0 = success, negative = error (see smx_last_error); never throws, never
+ *     aborts, never falls back to a CPU path.
+ *   - a handle is bound to one CUDA device and must be used by one host thread at a time.
+ *   - sequences are upper-case ASCII bytes in one pool; s1 is the QUERY (read), s2 the
+ *     REFERENCE (plasmid), exactly parasail's argument order.  Bytes other than A,C,G,T score 0
+ *     against everything (parasail.matrix_create("ACGT", m, mm) wildcard row/column,
+ *     ref_query_alignment.py:32) but are printed '=' when the two characters are equal.
+ *   - CIGAR runs are uint32 `len << 4 | op` with BAM op codes ('I'=1, 'D'=2, '='=7, 'X'=8),
+ *     in forward order; 'I' consumes a query base, 'D' a reference base.
+ */
+#ifndef SMX_H
+#define SMX_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMX_MODE_NW 0        /* parasail.nw_trace          (global)                              */
+#define SMX_MODE_SG_QE_DE 1  /* parasail.sg_qe_de_trace    (free trailing gaps on both)          */
+#define SMX_MODE_SG_QB_DB 2  /* parasail.sg_qb_db_trace    (free leading gaps on both)           */
+#define SMX_MODE_SW 3        /* parasail.sw_trace          (local)                               */
+
+#define SMX_OP_I 1u
+#define SMX_OP_D 2u
+#define SMX_OP_EQ 7u
+#define SMX_OP_X 8u
+
+#define SMX_TOPOLOGY_CIRCULAR 0 /* param_dict["topology_of_dna"] == 0 (post_analysis.py:23) */
+#define SMX_TOPOLOGY_LINEAR 1
+
+typedef struct smx_handle smx_handle;
+
+int smx_version(void);
+
+/* Creates an engine bound to `device_ordinal`.  `stream` is a cudaStream_t passed as void*
+ * (e.g. torch.cuda.current_stream().cuda_stream) or NULL to let the engine create its own. */
+int smx_create(smx_handle **out, int device_ordinal, void *stream);
+void smx_destroy(smx_handle *h);
+/* message of the last failing call on this handle ("" if none); h may be NULL for create errors */
+const char *smx_last_error(const smx_handle *h);
+
+/* Upper bound for the device bytes of packed traceback kept in flight at once (default 24 GiB);
+ * larger batches are cut into chunks that are processed back to back. */
+int smx_set_trace_budget(smx_handle *h, int64_t bytes);
+
+/* ---- sequence pool -------------------------------------------------------------------------
+ * Copies `n` bytes of upper-case ASCII sequence data to the device; the offsets handed to the
+ * calls below index this pool.  Replaces any previous pool of the handle. */
+int smx_pool_upload(smx_handle *h, const uint8_t *seqs, int64_t n);
+
+/* ---- A8: batched affine-gap DP with traceback (replaces the parasail *_trace calls) ----------
+ * One call = three phases that can also be driven separately (bench.py times phase 2 alone):
+ *   smx_align_prepare : copy the n problem descriptors to the device, plan classes / chunks
+ *   smx_align_run     : forward DP (packed direction bits in HBM) + traceback kernels; results
+ *                       stay on the device.  *total_runs receives the number of CIGAR runs.
+ *   smx_align_fetch   : copy results to caller buffers.
+ * Gap of length L costs open + (L-1)*extend (open, extend > 0), as in parasail. */
+int smx_align_prepare(smx_handle *h,
+                      const int64_t *s1_off, const int32_t *s1_len,
+                      const int64_t *s2_off, const int32_t *s2_len,
+                      const uint8_t *mode, int32_t n,
+                      int32_t open, int32_t extend, int32_t match, int32_t mismatch);
+int smx_align_run(smx_handle *h, int64_t *total_runs);
+/* score/end_query/end_ref/beg_query/beg_ref: int32[n] (parasail Result.score, .end_query,
+ * .end_ref, .cigar.beg_query, .cigar.beg_ref); cigar_off: int64[n+1] (prefix offsets into
+ * cigar_rle, filled by the call); cigar_rle: uint32[total_runs] as returned by smx_align_run. */
+int smx_align_fetch(smx_handle *h, int32_t *score, int32_t *end_query, int32_t *end_ref,
+                    int32_t *beg_query, int32_t *beg_ref, int64_t *cigar_off, uint32_t *cigar_rle,
+                    int64_t cigar_capacity);
+/* device milliseconds (CUDA events on the engine's stream) of the last smx_align_run / smx_scan_run */
+float smx_last_run_ms(const smx_handle *h);
+/* DP cells (sum of s1_len*s2_len) of the prepared batch, and the number of kernel launches of the last run */
+int64_t smx_align_cells(const smx_handle *h);
+int32_t smx_last_run_launches(const smx_handle *h);
+
+/* diagnostic: raw copy of the first nbytes of the direction-bit arena of the last chunk */
+int smx_debug_copy_trace(smx_handle *h, uint8_t *dst, int64_t nbytes);
+
+/* ---- A3: diagonal match-count scan (replaces af.k_mer_offset_analysis_2) ---------------------
+ * For pair p with reference r = pool[ref_off[p] : +ref_len[p]] and query q = pool[qry_off[p] : +qry_len[p]]:
+ *   circular: counts[k] = #{ i < Nq : r[(k + i) mod Nr] == q[i] },          k in [0, Nr)
+ *   linear  : counts[k] = #{ i < Nq : 0 <= k+i-(Nq-1) < Nr and r[k+i-(Nq-1)] == q[i] },  k in [0, Nr+Nq-1)
+ * (ref_query_alignment.py:351-366 builds exactly these windows before calling the Cython scan.)
+ * Equality is on the raw bytes.  counts_off: int64[n+1] prefix offsets (filled by prepare). */
+int smx_scan_prepare(smx_handle *h,
+                     const int64_t *ref_off, const int32_t *ref_len,
+                     const int64_t *qry_off, const int32_t *qry_len,
+                     int32_t n, int32_t topology, int64_t *counts_off);
+int smx_scan_run(smx_handle *h);
+int smx_scan_fetch(smx_handle *h, int32_t *counts, int64_t counts_capacity);
+int64_t smx_scan_cells(const smx_handle *h);
+
+/* ---- measurement helper: dependency-free int32 / DPX issue-rate microbenchmark ---------------
+ * Runs `iters` rounds of independent VIADDMNMX / VIMNMX3 / IADD chains on every SM and returns
+ * achieved giga-ops/s (one op = one 32-bit lane instruction) in out_gops[3] = {viaddmax, vimax3, iadd}. */
+int smx_measure_int_peak(smx_handle *h, int32_t iters, double *out_gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMX_H */

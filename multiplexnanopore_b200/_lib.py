@@ -1,0 +1,56 @@
+"""ctypes binding of libsmx.so -- the only way the Python host reaches the CUDA engine.
+
+There is deliberately no fallback: if the shared library is missing or cannot be loaded the
+import of the product package fails loudly (north_star: "no CPU fallback").
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libsmx.so"
+
+# every symbol include/smx.h declares: (restype, argtypes)
+_SIGNATURES = {
+    "smx_version": (c_int, []),
+    "smx_create": (c_int, [POINTER(c_void_p), c_int, c_void_p]),
+    "smx_destroy": (None, [c_void_p]),
+    "smx_last_error": (c_char_p, [c_void_p]),
+    "smx_set_trace_budget": (c_int, [c_void_p, c_int64]),
+    "smx_pool_upload": (c_int, [c_void_p, c_void_p, c_int64]),
+    "smx_align_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                  c_int32, c_int32, c_int32, c_int32]),
+    "smx_align_run": (c_int, [c_void_p, POINTER(c_int64)]),
+    "smx_align_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
+    "smx_debug_copy_trace": (c_int, [c_void_p, c_void_p, c_int64]),
+    "smx_last_run_ms": (c_float, [c_void_p]),
+    "smx_align_cells": (c_int64, [c_void_p]),
+    "smx_last_run_launches": (c_int32, [c_void_p]),
+    "smx_scan_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "smx_scan_run": (c_int, [c_void_p]),
+    "smx_scan_fetch": (c_int, [c_void_p, c_void_p, c_int64]),
+    "smx_scan_cells": (c_int64, [c_void_p]),
+    "smx_measure_int_peak": (c_int, [c_void_p, c_int32, POINTER(c_double)]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m multiplexnanopore_b200.build` "
+                "(or __graft_entry__.build()). The engine has no CPU fallback.")
+        lib = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

@@ -1,0 +1,554 @@
+// C-ABI of the SMX engine (include/smx.h): handle, device workspaces, planning and launches.
+// Host-side C++ only orchestrates; all arithmetic of the path runs in the kernels included below.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/smx.h"
+#include "smx_common.cuh"
+#include "smx_dp.cuh"
+#include "smx_scan.cuh"
+#include "smx_traceback.cuh"
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Chunk {
+    int first = 0, count = 0;            // range in the size-sorted order
+    int cls_first[8] = {0}, cls_count[8] = {0};  // per kernel class (kshift*2 + local) ranges inside order_cls
+    size_t trace_bytes = 0;
+};
+
+}  // namespace
+
+struct smx_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 148;
+    std::string err;
+    int64_t trace_budget = (int64_t)24 << 30;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    int last_launches = 0;
+
+    DevBuf pool;
+    int64_t pool_len = 0;
+
+    // align state
+    int32_t n = 0;
+    SmxScoring sc{};
+    int64_t cells = 0;
+    std::vector<SmxProblem> probs;
+    std::vector<int32_t> order_cls;  // problem ids grouped by chunk then class, largest first
+    std::vector<int32_t> order_all;  // problem ids by chunk (for traceback)
+    std::vector<Chunk> chunks;
+    int32_t nmax = 0;
+    size_t max_chunk_trace = 0;
+    int64_t runs_scratch = 0;
+    int64_t total_runs = -1;
+    DevBuf d_probs, d_order_cls, d_order_all, d_results, d_trace, d_boundary, d_runs, d_dense, d_dense_off, d_tickets;
+    std::vector<SmxResult> h_results;
+    std::vector<int64_t> h_dense_off;
+
+    // scan state
+    int32_t scan_n = 0, scan_topology = 0;
+    int64_t scan_total = 0, scan_cells = 0;
+    int32_t scan_tiles = 0, scan_nq_max = 0;
+    DevBuf d_scan_pairs, d_scan_tile_pair, d_counts;
+};
+
+static thread_local std::string g_create_error;
+
+static int fail(smx_handle *h, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define SMX_CUDA(h, call)                                                                           \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail((h), -2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static int ensure(smx_handle *h, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return 0;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        want = bytes;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) { b.p = nullptr; return fail(h, -3, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e)); }
+    b.cap = want;
+    return 0;
+}
+
+static void release(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+}
+
+extern "C" int smx_version(void) { return 100; }
+
+extern "C" const char *smx_last_error(const smx_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int smx_create(smx_handle **out, int device_ordinal, void *stream)
+{
+    if (!out) return fail(nullptr, -1, "smx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(nullptr, -2, "smx_create: no CUDA device available (%s); this engine has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device_ordinal < 0 || device_ordinal >= ndev) return fail(nullptr, -1, "smx_create: bad device ordinal %d", device_ordinal);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device_ordinal)) != cudaSuccess)
+        return fail(nullptr, -2, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, -4, "smx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                    device_ordinal, prop.major, prop.minor);
+    smx_handle *h = new (std::nothrow) smx_handle();
+    if (!h) return fail(nullptr, -3, "out of host memory");
+    h->device = device_ordinal;
+    h->sm_count = prop.multiProcessorCount;
+    if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) { delete h; return fail(nullptr, -2, "cudaSetDevice: %s", cudaGetErrorString(e)); }
+    if (stream) { h->stream = (cudaStream_t)stream; h->owns_stream = false; }
+    else {
+        if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return fail(nullptr, -2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        h->owns_stream = true;
+    }
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+    *out = h;
+    return 0;
+}
+
+extern "C" void smx_destroy(smx_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf *bufs[] = {&h->pool, &h->d_probs, &h->d_order_cls, &h->d_order_all, &h->d_results, &h->d_trace, &h->d_boundary,
+                      &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts};
+    for (DevBuf *b : bufs) release(*b);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->owns_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int smx_set_trace_budget(smx_handle *h, int64_t bytes)
+{
+    if (!h) return -1;
+    if (bytes < (1 << 20)) return fail(h, -1, "trace budget must be at least 1 MiB");
+    h->trace_budget = bytes;
+    return 0;
+}
+
+extern "C" int smx_pool_upload(smx_handle *h, const uint8_t *seqs, int64_t n)
+{
+    if (!h) return -1;
+    if (!seqs || n <= 0) return fail(h, -1, "smx_pool_upload: empty pool");
+    SMX_CUDA(h, cudaSetDevice(h->device));
+    if (int rc = ensure(h, h->pool, (size_t)n + 64)) return rc;
+    SMX_CUDA(h, cudaMemcpyAsync(h->pool.p, seqs, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->pool_len = n;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A8: batched DP
+// ------------------------------------------------------------------------------------------------
+static int pick_kshift(int m)
+{
+    if (m > 128) return 3;
+    if (m > 64) return 2;
+    if (m > 32) return 1;
+    return 0;
+}
+
+extern "C" int smx_align_prepare(smx_handle *h, const int64_t *s1_off, const int32_t *s1_len, const int64_t *s2_off,
+                                 const int32_t *s2_len, const uint8_t *mode, int32_t n, int32_t open, int32_t extend,
+                                 int32_t match, int32_t mismatch)
+{
+    if (!h) return -1;
+    h->total_runs = -1;
+    h->n = 0;
+    if (n < 0 || (n > 0 && (!s1_off || !s1_len || !s2_off || !s2_len || !mode))) return fail(h, -1, "smx_align_prepare: NULL argument");
+    if (!h->pool.p) return fail(h, -1, "smx_align_prepare: no sequence pool uploaded");
+    if (open <= 0 || extend <= 0) return fail(h, -1, "gap penalties must be positive (my_classes.py:537-541)");
+    if (match > 127 || match < -128 || mismatch > 127 || mismatch < -128) return fail(h, -1, "match/mismatch must fit in int8");
+    SMX_CUDA(h, cudaSetDevice(h->device));
+    h->sc = SmxScoring{open, extend, match, mismatch};
+    h->probs.resize((size_t)n);
+    h->cells = 0;
+    h->nmax = 1;
+    int64_t runs_off = 0;
+    for (int p = 0; p < n; ++p) {
+        const int m = s1_len[p], nn = s2_len[p];
+        if (m <= 0 || nn <= 0) return fail(h, -1, "problem %d: empty sequence (callers never pass empty strings, ref_query_alignment.py:93-106,332-338)", p);
+        if (mode[p] > 3) return fail(h, -1, "problem %d: unknown mode %d", p, (int)mode[p]);
+        if (s1_off[p] < 0 || s2_off[p] < 0 || s1_off[p] + m > h->pool_len || s2_off[p] + nn > h->pool_len)
+            return fail(h, -1, "problem %d: sequence slice outside the uploaded pool", p);
+        // int32 score range: |H| <= open + extend*(m+n) + max(|match|,|mismatch|)*min(m,n)
+        const int64_t bound = (int64_t)open + (int64_t)extend * ((int64_t)m + nn) + 128LL * std::min(m, nn);
+        if (bound > (int64_t)(1 << 29)) return fail(h, -1, "problem %d: score range exceeds int32 headroom", p);
+        SmxProblem &q = h->probs[(size_t)p];
+        q.s1_off = s1_off[p]; q.s2_off = s2_off[p]; q.m = m; q.n = nn; q.mode = mode[p];
+        q.kshift = pick_kshift(m);
+        q.trace_off = 0;
+        q.cigar_off = runs_off;
+        runs_off += (int64_t)m + nn + 2;
+        h->cells += (int64_t)m * nn;
+        h->nmax = std::max(h->nmax, nn);
+    }
+    h->runs_scratch = runs_off;
+    // size-sorted order, then greedy chunking under the trace budget
+    std::vector<int32_t> order((size_t)n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
+        return (int64_t)h->probs[x].m * h->probs[x].n > (int64_t)h->probs[y].m * h->probs[y].n;
+    });
+    h->chunks.clear();
+    h->order_all = order;
+    h->order_cls.assign((size_t)n, 0);
+    h->max_chunk_trace = 0;
+    int pos = 0;
+    while (pos < n) {
+        Chunk c;
+        c.first = pos;
+        size_t bytes = 0;
+        while (pos < n) {
+            SmxProblem &q = h->probs[(size_t)order[pos]];
+            size_t tb = (size_t)smx_trace_bytes(q.m, q.n, 1 << q.kshift);
+            tb = (tb + 255) & ~(size_t)255;
+            if (c.count > 0 && bytes + tb > (size_t)h->trace_budget) break;
+            q.trace_off = (int64_t)bytes;
+            bytes += tb;
+            ++c.count; ++pos;
+        }
+        c.trace_bytes = bytes;
+        h->max_chunk_trace = std::max(h->max_chunk_trace, bytes);
+        // class lists (stable: keeps largest-first inside each class)
+        int w = c.first;
+        for (int cls = 7; cls >= 0; --cls) {
+            c.cls_first[cls] = w;
+            for (int x = c.first; x < c.first + c.count; ++x) {
+                const SmxProblem &q = h->probs[(size_t)order[x]];
+                const int qc = q.kshift * 2 + (q.mode == SMX_MODE_SW ? 1 : 0);
+                if (qc == cls) h->order_cls[(size_t)w++] = order[x];
+            }
+            c.cls_count[cls] = w - c.cls_first[cls];
+        }
+        h->chunks.push_back(c);
+    }
+    if (n == 0) { h->n = 0; return 0; }
+    if (int rc = ensure(h, h->d_probs, sizeof(SmxProblem) * (size_t)n)) return rc;
+    if (int rc = ensure(h, h->d_order_cls, sizeof(int32_t) * (size_t)n)) return rc;
+    if (int rc = ensure(h, h->d_order_all, sizeof(int32_t) * (size_t)n)) return rc;
+    if (int rc = ensure(h, h->d_results, sizeof(SmxResult) * (size_t)n)) return rc;
+    if (int rc = ensure(h, h->d_trace, h->max_chunk_trace + 256)) return rc;
+    if (int rc = ensure(h, h->d_runs, sizeof(uint32_t) * (size_t)h->runs_scratch)) return rc;
+    if (int rc = ensure(h, h->d_dense_off, sizeof(int64_t) * ((size_t)n + 1))) return rc;
+    if (int rc = ensure(h, h->d_tickets, sizeof(int32_t) * 8 * h->chunks.size())) return rc;
+    SMX_CUDA(h, cudaMemcpyAsync(h->d_probs.p, h->probs.data(), sizeof(SmxProblem) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    SMX_CUDA(h, cudaMemcpyAsync(h->d_order_cls.p, h->order_cls.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    SMX_CUDA(h, cudaMemcpyAsync(h->d_order_all.p, h->order_all.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->n = n;
+    return 0;
+}
+
+template <int K, bool LOCAL>
+static int launch_forward(smx_handle *h, const Chunk &c, int cls, int chunk_idx, int blocks_per_sm_hint)
+{
+    const int count = c.cls_count[cls];
+    if (count == 0) return 0;
+    int occ = 0;
+    SMX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, smx_dp_forward<K, LOCAL>, 128, 0));
+    if (occ < 1) occ = 1;
+    (void)blocks_per_sm_hint;
+    const int warps_per_block = 4;
+    int blocks = std::min(h->sm_count * occ, (count + warps_per_block - 1) / warps_per_block);
+    if (blocks < 1) blocks = 1;
+    const size_t line_bytes = sizeof(int2) * 2 * (size_t)h->nmax * (size_t)blocks * warps_per_block;
+    if (int rc = ensure(h, h->d_boundary, line_bytes)) return rc;
+    SmxFwdArgs a;
+    a.pool = (const uint8_t *)h->pool.p;
+    a.probs = (const SmxProblem *)h->d_probs.p;
+    a.order = (const int32_t *)h->d_order_cls.p + c.cls_first[cls];
+    a.n_order = count;
+    a.ticket = (int32_t *)h->d_tickets.p + chunk_idx * 8 + cls;
+    a.trace = (uint8_t *)h->d_trace.p;
+    a.boundary = (int2 *)h->d_boundary.p;
+    a.nmax = h->nmax;
+    a.results = (SmxResult *)h->d_results.p;
+    a.sc = h->sc;
+    smx_dp_forward<K, LOCAL><<<blocks, 128, 0, h->stream>>>(a);
+    SMX_CUDA(h, cudaGetLastError());
+    h->last_launches++;
+    return 0;
+}
+
+extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
+{
+    if (!h) return -1;
+    if (total_runs) *total_runs = 0;
+    h->last_launches = 0;
+    h->last_ms = 0.f;
+    if (h->n == 0) { h->total_runs = 0; return 0; }
+    SMX_CUDA(h, cudaSetDevice(h->device));
+    // boundary lines must be sized before the timed region (no allocation between launches)
+    {
+        const size_t line_bytes = sizeof(int2) * 2 * (size_t)h->nmax * (size_t)h->sm_count * 16 * 4;
+        if (int rc = ensure(h, h->d_boundary, line_bytes)) return rc;
+    }
+    SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    SMX_CUDA(h, cudaMemsetAsync(h->d_tickets.p, 0, sizeof(int32_t) * 8 * h->chunks.size(), h->stream));
+    for (size_t ci = 0; ci < h->chunks.size(); ++ci) {
+        const Chunk &c = h->chunks[ci];
+        int rc = 0;
+        if ((rc = launch_forward<8, false>(h, c, 6, (int)ci, 0))) return rc;
+        if ((rc = launch_forward<8, true>(h, c, 7, (int)ci, 0))) return rc;
+        if ((rc = launch_forward<4, false>(h, c, 4, (int)ci, 0))) return rc;
+        if ((rc = launch_forward<4, true>(h, c, 5, (int)ci, 0))) return rc;
+        if ((rc = launch_forward<2, false>(h, c, 2, (int)ci, 0))) return rc;
+        if ((rc = launch_forward<2, true>(h, c, 3, (int)ci, 0))) return rc;
+        if ((rc = launch_forward<1, false>(h, c, 0, (int)ci, 0))) return rc;
+        if ((rc = launch_forward<1, true>(h, c, 1, (int)ci, 0))) return rc;
+        SmxTbArgs t;
+        t.pool = (const uint8_t *)h->pool.p;
+        t.probs = (const SmxProblem *)h->d_probs.p;
+        t.order = (const int32_t *)h->d_order_all.p + c.first;
+        t.n_order = c.count;
+        t.trace = (const uint8_t *)h->d_trace.p;
+        t.results = (SmxResult *)h->d_results.p;
+        t.runs = (uint32_t *)h->d_runs.p;
+        smx_traceback<<<(c.count + 127) / 128, 128, 0, h->stream>>>(t);
+        SMX_CUDA(h, cudaGetLastError());
+        h->last_launches++;
+    }
+    SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    // results header to host: run counts -> dense offsets -> compaction
+    h->h_results.resize((size_t)h->n);
+    SMX_CUDA(h, cudaMemcpyAsync(h->h_results.data(), h->d_results.p, sizeof(SmxResult) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    SMX_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    h->h_dense_off.resize((size_t)h->n + 1);
+    int64_t acc = 0;
+    for (int p = 0; p < h->n; ++p) { h->h_dense_off[(size_t)p] = acc; acc += h->h_results[(size_t)p].n_runs; }
+    h->h_dense_off[(size_t)h->n] = acc;
+    h->total_runs = acc;
+    if (int rc = ensure(h, h->d_dense, sizeof(uint32_t) * (size_t)std::max<int64_t>(acc, 1))) return rc;
+    SMX_CUDA(h, cudaMemcpyAsync(h->d_dense_off.p, h->h_dense_off.data(), sizeof(int64_t) * ((size_t)h->n + 1), cudaMemcpyHostToDevice, h->stream));
+    const int threads = 256, wpb = threads / 32;
+    smx_compact_runs<<<(h->n + wpb - 1) / wpb, threads, 0, h->stream>>>((const SmxProblem *)h->d_probs.p, (const SmxResult *)h->d_results.p,
+                                                                        (const int64_t *)h->d_dense_off.p, (const uint32_t *)h->d_runs.p,
+                                                                        (uint32_t *)h->d_dense.p, h->n);
+    SMX_CUDA(h, cudaGetLastError());
+    h->last_launches++;
+    SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (total_runs) *total_runs = acc;
+    return 0;
+}
+
+extern "C" int smx_align_fetch(smx_handle *h, int32_t *score, int32_t *end_query, int32_t *end_ref, int32_t *beg_query,
+                               int32_t *beg_ref, int64_t *cigar_off, uint32_t *cigar_rle, int64_t cigar_capacity)
+{
+    if (!h) return -1;
+    if (h->total_runs < 0) return fail(h, -1, "smx_align_fetch: no completed smx_align_run");
+    if (cigar_capacity < h->total_runs) return fail(h, -1, "smx_align_fetch: cigar buffer too small (%lld < %lld)", (long long)cigar_capacity, (long long)h->total_runs);
+    for (int p = 0; p < h->n; ++p) {
+        const SmxResult &r = h->h_results[(size_t)p];
+        if (score) score[p] = r.score;
+        if (end_query) end_query[p] = r.end_q;
+        if (end_ref) end_ref[p] = r.end_r;
+        if (beg_query) beg_query[p] = r.beg_q;
+        if (beg_ref) beg_ref[p] = r.beg_r;
+    }
+    if (cigar_off) memcpy(cigar_off, h->h_dense_off.data(), sizeof(int64_t) * ((size_t)h->n + 1));
+    if (cigar_rle && h->total_runs > 0) {
+        SMX_CUDA(h, cudaSetDevice(h->device));
+        SMX_CUDA(h, cudaMemcpyAsync(cigar_rle, h->d_dense.p, sizeof(uint32_t) * (size_t)h->total_runs, cudaMemcpyDeviceToHost, h->stream));
+        SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+// diagnostic: raw copy of the packed direction-bit arena of the last chunk (layout: smx_dp.cuh)
+extern "C" int smx_debug_copy_trace(smx_handle *h, uint8_t *dst, int64_t nbytes)
+{
+    if (!h || !dst) return -1;
+    if ((size_t)nbytes > h->d_trace.cap) return fail(h, -1, "smx_debug_copy_trace: arena holds %zu bytes", h->d_trace.cap);
+    SMX_CUDA(h, cudaSetDevice(h->device));
+    SMX_CUDA(h, cudaMemcpy(dst, h->d_trace.p, (size_t)nbytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" float smx_last_run_ms(const smx_handle *h) { return h ? h->last_ms : 0.f; }
+extern "C" int64_t smx_align_cells(const smx_handle *h) { return h ? h->cells : 0; }
+extern "C" int32_t smx_last_run_launches(const smx_handle *h) { return h ? h->last_launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// A3: diagonal scan
+// ------------------------------------------------------------------------------------------------
+extern "C" int smx_scan_prepare(smx_handle *h, const int64_t *ref_off, const int32_t *ref_len, const int64_t *qry_off,
+                                const int32_t *qry_len, int32_t n, int32_t topology, int64_t *counts_off)
+{
+    if (!h) return -1;
+    h->scan_n = 0;
+    if (n < 0 || (n > 0 && (!ref_off || !ref_len || !qry_off || !qry_len)) || !counts_off) return fail(h, -1, "smx_scan_prepare: NULL argument");
+    if (topology != 0 && topology != 1) return fail(h, -1, "unknown topology_of_dna: %d (ref_query_alignment.py:368)", topology);
+    if (!h->pool.p) return fail(h, -1, "smx_scan_prepare: no sequence pool uploaded");
+    SMX_CUDA(h, cudaSetDevice(h->device));
+    std::vector<SmxScanPair> pairs((size_t)n);
+    std::vector<int32_t> tile_pair;
+    int64_t total = 0, cells = 0;
+    int32_t tiles = 0, nq_max = 1;
+    for (int p = 0; p < n; ++p) {
+        const int nr = ref_len[p], nq = qry_len[p];
+        if (nr <= 0 || nq <= 0) return fail(h, -1, "scan pair %d: empty sequence", p);
+        if (ref_off[p] < 0 || qry_off[p] < 0 || ref_off[p] + nr > h->pool_len || qry_off[p] + nq > h->pool_len)
+            return fail(h, -1, "scan pair %d: sequence slice outside the uploaded pool", p);
+        SmxScanPair &s = pairs[(size_t)p];
+        s.ref_off = ref_off[p]; s.qry_off = qry_off[p]; s.nr = nr; s.nq = nq;
+        s.max_k = topology == 0 ? nr : nr + nq - 1;
+        s.counts_off = total;
+        s.tile0 = tiles;
+        counts_off[p] = total;
+        total += s.max_k;
+        cells += (int64_t)s.max_k * nq;
+        const int t = (s.max_k + SMX_SCAN_TILE - 1) / SMX_SCAN_TILE;
+        for (int x = 0; x < t; ++x) tile_pair.push_back(p);
+        tiles += t;
+        nq_max = std::max(nq_max, nq);
+    }
+    counts_off[n] = total;
+    h->scan_total = total; h->scan_cells = cells; h->scan_tiles = tiles; h->scan_nq_max = nq_max; h->scan_topology = topology;
+    if (n == 0) return 0;
+    if (int rc = ensure(h, h->d_scan_pairs, sizeof(SmxScanPair) * (size_t)n)) return rc;
+    if (int rc = ensure(h, h->d_scan_tile_pair, sizeof(int32_t) * (size_t)tiles)) return rc;
+    if (int rc = ensure(h, h->d_counts, sizeof(int32_t) * (size_t)total)) return rc;
+    SMX_CUDA(h, cudaMemcpyAsync(h->d_scan_pairs.p, pairs.data(), sizeof(SmxScanPair) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    SMX_CUDA(h, cudaMemcpyAsync(h->d_scan_tile_pair.p, tile_pair.data(), sizeof(int32_t) * (size_t)tiles, cudaMemcpyHostToDevice, h->stream));
+    SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->scan_n = n;
+    return 0;
+}
+
+extern "C" int smx_scan_run(smx_handle *h)
+{
+    if (!h) return -1;
+    h->last_launches = 0;
+    h->last_ms = 0.f;
+    if (h->scan_n == 0) return 0;
+    SMX_CUDA(h, cudaSetDevice(h->device));
+    const int qwords = (h->scan_nq_max + 15) / 16;
+    const int rwords = (SMX_SCAN_TILE + h->scan_nq_max - 1 + 15) / 16 + 1;
+    const size_t smem = sizeof(uint32_t) * (size_t)(qwords + rwords + 4);
+    if (smem > 48 * 1024) SMX_CUDA(h, cudaFuncSetAttribute(smx_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SmxScanArgs a;
+    a.pool = (const uint8_t *)h->pool.p;
+    a.pairs = (const SmxScanPair *)h->d_scan_pairs.p;
+    a.tile_pair = (const int32_t *)h->d_scan_tile_pair.p;
+    a.counts = (int32_t *)h->d_counts.p;
+    a.topology = h->scan_topology;
+    a.smem_words_q = qwords;
+    SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    smx_scan_kernel<<<h->scan_tiles, SMX_SCAN_TILE, smem, h->stream>>>(a);
+    SMX_CUDA(h, cudaGetLastError());
+    h->last_launches = 1;
+    SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    SMX_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    return 0;
+}
+
+extern "C" int smx_scan_fetch(smx_handle *h, int32_t *counts, int64_t counts_capacity)
+{
+    if (!h) return -1;
+    if (!counts || counts_capacity < h->scan_total) return fail(h, -1, "smx_scan_fetch: counts buffer too small");
+    if (h->scan_n == 0) return 0;
+    SMX_CUDA(h, cudaSetDevice(h->device));
+    SMX_CUDA(h, cudaMemcpyAsync(counts, h->d_counts.p, sizeof(int32_t) * (size_t)h->scan_total, cudaMemcpyDeviceToHost, h->stream));
+    SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int64_t smx_scan_cells(const smx_handle *h) { return h ? h->scan_cells : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// int32 / DPX issue-rate microbenchmark (roofline denominator)
+// ------------------------------------------------------------------------------------------------
+template <int WHICH>
+__global__ void __launch_bounds__(256) smx_int_peak_kernel(int *out, int iters, int seed)
+{
+    // 8 independent chains per thread so that the ALU latency (4 cycles) is always covered
+    int v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = seed + threadIdx.x * 8 + c;
+    const int b = seed | 1, d = seed ^ 0x55;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (WHICH == 0) v[c] = __viaddmax_s32(v[c], b, d);
+                else if (WHICH == 1) v[c] = __vimax3_s32(v[c], b + u, d);
+                else v[c] = v[c] + (v[c] ^ b);  // IADD + LOP3 pair counted as 2 ops
+            }
+        }
+    }
+    int s = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s ^= v[c];
+    if (s == 0x7fffffff) out[0] = s;
+}
+
+extern "C" int smx_measure_int_peak(smx_handle *h, int32_t iters, double *out_gops)
+{
+    if (!h || !out_gops) return -1;
+    SMX_CUDA(h, cudaSetDevice(h->device));
+    if (int rc = ensure(h, h->d_tickets, 64)) return rc;
+    const int blocks = h->sm_count * 8, threads = 256;
+    for (int which = 0; which < 3; ++which) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {
+            SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+            if (which == 0) smx_int_peak_kernel<0><<<blocks, threads, 0, h->stream>>>((int *)h->d_tickets.p, iters, 12345 + rep);
+            else if (which == 1) smx_int_peak_kernel<1><<<blocks, threads, 0, h->stream>>>((int *)h->d_tickets.p, iters, 12345 + rep);
+            else smx_int_peak_kernel<2><<<blocks, threads, 0, h->stream>>>((int *)h->d_tickets.p, iters, 12345 + rep);
+            SMX_CUDA(h, cudaGetLastError());
+            SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+            SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+            float ms = 0.f;
+            SMX_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            best = std::min(best, ms);
+        }
+        const double ops = (double)blocks * threads * (double)iters * 16.0 * 8.0 * (which == 2 ? 2.0 : 1.0);
+        out_gops[which] = ops / (best * 1e-3) / 1e9;
+    }
+    return 0;
+}

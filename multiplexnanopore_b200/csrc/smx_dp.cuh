@@ -1,0 +1,255 @@
+// Forward affine-gap DP (Gotoh) with packed direction bits, one warp per problem.
+//
+// Replaces the arithmetic of parasail.{nw,sg_qe_de,sg_qb_db,sw}_trace as called from
+// savemoney/modules/ref_query_alignment.py:35,58,68,82,343 (semantics: SURVEY.md Appendix A).
+//
+// Parallelisation (B200: 148 SMs x 4 SMSPs, 32-wide warps):
+//   - inter-task: one warp owns one (query, reference) problem; warps pull problems from a
+//     size-sorted list through an atomic ticket (persistent grid = SMs x resident CTAs).
+//   - intra-task: systolic anti-diagonal wavefront.  Lane t owns K consecutive query rows of the
+//     current band of 32*K rows and, at step s, updates column j = s - t for those K rows.  The
+//     (H, F) pair of its last row and the reference base travel to lane t+1 by warp shuffles;
+//     between bands the bottom row goes through a small per-warp (H, F) line in global memory
+//     (L2 resident).
+//   - max-plus recurrence on the DPX path: VIMNMX / VIMNMX3 (__vimax3_s32), substitution score
+//     by one PRMT from a per-row 4-byte profile register.
+//   - direction bits: 4 bits per cell, the K nibbles of a lane's column are one 8/16/32-bit word;
+//     words are laid out [band][step][lane] so that every warp store is one contiguous line.
+#pragma once
+#include "smx_common.cuh"
+
+template <int K> struct SmxTraceWord;
+template <> struct SmxTraceWord<1> { typedef uint8_t type; };
+template <> struct SmxTraceWord<2> { typedef uint8_t type; };
+template <> struct SmxTraceWord<4> { typedef uint16_t type; };
+template <> struct SmxTraceWord<8> { typedef uint32_t type; };
+
+// bytes of packed direction bits a problem of m x n cells needs in class K
+__host__ __device__ inline int64_t smx_trace_bytes(int m, int n, int K)
+{
+    const int64_t bands = (m + 32 * K - 1) / (32 * K);
+    const int64_t w = K >= 2 ? K / 2 : 1;
+    return bands * (int64_t)(n + 31) * 32 * w;
+}
+
+// per-row substitution profile: byte c = score(query base, reference code c), c = 0..3; code 4 -> 0
+__device__ __forceinline__ uint32_t smx_profile(int qcode, int match, int mismatch)
+{
+    if (qcode > 3) return 0u;
+    const uint32_t mm = (uint32_t)(mismatch & 0xff), ma = (uint32_t)(match & 0xff);
+    uint32_t p = mm * 0x01010101u;
+    p &= ~(0xffu << (8 * qcode));
+    p |= ma << (8 * qcode);
+    return p;
+}
+
+// PRMT selector that picks byte `rcode` of the profile (or of the zero register for the
+// wildcard) and sign-extends it to 32 bits.
+__device__ __forceinline__ uint32_t smx_selector(int rcode)
+{
+    const uint32_t idx = (uint32_t)rcode;  // 0..3 -> profile bytes, 4 -> first byte of the zero register
+    return idx | ((idx | 8u) << 4) | ((idx | 8u) << 8) | ((idx | 8u) << 12);
+}
+
+// prmt.b32 in its default mode honours bit 3 of every selector nibble (replicate the sign of the
+// selected byte); the __byte_perm intrinsic masks that bit away, hence the inline PTX.
+__device__ __forceinline__ int smx_subst(uint32_t profile, uint32_t sel)
+{
+    int r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(profile), "r"(0u), "r"(sel));
+    return r;
+}
+
+struct SmxFwdArgs {
+    const uint8_t *pool;
+    const SmxProblem *probs;
+    const int32_t *order;  // problem indices of this class, largest first
+    int32_t n_order;
+    int32_t *ticket;
+    uint8_t *trace;
+    int2 *boundary;  // per warp: 2 lines of nmax (H, F) pairs
+    int32_t nmax;
+    SmxResult *results;
+    SmxScoring sc;
+};
+
+template <int K, bool LOCAL>
+__global__ void __launch_bounds__(128) smx_dp_forward(const SmxFwdArgs a)
+{
+    typedef typename SmxTraceWord<K>::type TW;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int2 *line0 = a.boundary + (size_t)gwarp * 2 * (size_t)a.nmax;
+    int2 *line1 = line0 + a.nmax;
+    const int go = a.sc.go, ge = a.sc.ge;
+
+    for (;;) {
+        int ticket = 0;
+        if (lane == 0) ticket = atomicAdd(a.ticket, 1);
+        ticket = __shfl_sync(SMX_FULL_MASK, ticket, 0);
+        if (ticket >= a.n_order) break;
+        const int pid = a.order[ticket];
+        const SmxProblem pr = a.probs[pid];
+        const int m = pr.m, n = pr.n, mode = pr.mode;
+        const bool free_beg = LOCAL || mode == 2;  // SMX_MODE_SG_QB_DB
+        const uint8_t *s1 = a.pool + pr.s1_off;
+        const uint8_t *s2 = a.pool + pr.s2_off;
+        TW *trace = reinterpret_cast<TW *>(a.trace + pr.trace_off);
+        const int nbands = (m + 32 * K - 1) / (32 * K);
+        const int steps = n + 31;
+
+        // end-cell candidates: last column (rows ascending) then last row (columns ascending)
+        int col_best = SMX_NEG_INF, col_best_i = 0;
+        int row_best = SMX_NEG_INF, row_best_j = 0;
+        int corner = 0;
+        int loc_best = 0, loc_i = m - 1, loc_j = n - 1;  // local mode: first maximum in row-major order
+        const int last_lane = ((m - 1) % (32 * K)) / K;
+        const int last_k = (m - 1) % K;
+
+        for (int band = 0; band < nbands; ++band) {
+            const int i0 = band * 32 * K + lane * K;
+            const int2 *top_line = (band & 1) ? line1 : line0;  // written by the previous band
+            int2 *bot_line = (band & 1) ? line0 : line1;
+            const bool last_band = band == nbands - 1;
+
+            uint32_t prof[K];
+            int Hl[K], Hlgo[K], El[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int i = i0 + k;
+                const int qc = i < m ? smx_code(s1[i]) : 4;
+                prof[k] = smx_profile(qc, a.sc.match, a.sc.mismatch);
+                Hl[k] = free_beg ? 0 : -(go + i * ge);  // H[i][-1]
+                Hlgo[k] = Hl[k] - go;
+                El[k] = SMX_NEG_INF;
+            }
+            int hd = (i0 == 0 || free_beg) ? 0 : -(go + (i0 - 1) * ge);  // H[i0-1][-1]
+            int out_h = 0, out_f = 0, rc_prev = 4;
+
+            for (int s0 = 0; s0 < steps; s0 += 32) {
+                // chunk prefetch for lane 0's inputs: top boundary (H, F) and reference codes of columns s0..s0+31
+                const int jc = s0 + lane;
+                int2 top = make_int2(0, SMX_NEG_INF);
+                int rch = 4;
+                if (jc < n) {
+                    if (band == 0) top.x = free_beg ? 0 : -(go + jc * ge);
+                    else top = __ldcg(&top_line[jc]);
+                    rch = smx_code(s2[jc]);
+                }
+                const int send = min(32, steps - s0);
+#pragma unroll 1
+                for (int ss = 0; ss < send; ++ss) {
+                    const int s = s0 + ss;
+                    int hu = __shfl_up_sync(SMX_FULL_MASK, out_h, 1);
+                    int fu = __shfl_up_sync(SMX_FULL_MASK, out_f, 1);
+                    int rc = __shfl_up_sync(SMX_FULL_MASK, rc_prev, 1);
+                    const int th = __shfl_sync(SMX_FULL_MASK, top.x, ss);
+                    const int tf = __shfl_sync(SMX_FULL_MASK, top.y, ss);
+                    const int tr = __shfl_sync(SMX_FULL_MASK, rch, ss);
+                    if (lane == 0) { hu = th; fu = tf; rc = tr; }
+                    rc_prev = rc;
+                    const int j = s - lane;
+                    if (j >= 0 && j < n) {
+                        const uint32_t sel = smx_selector(rc);
+                        const int hu_in = hu;
+                        int hugo = hu - go;
+                        uint32_t word = 0;
+                        int h = 0, f = 0;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const int e_ext = El[k] - ge;
+                            const int e_opn = Hlgo[k];
+                            const int e = max(e_ext, e_opn);
+                            const int f_ext = fu - ge;
+                            const int f_opn = hugo;
+                            f = max(f_ext, f_opn);
+                            const int hdiag = hd + smx_subst(prof[k], sel);
+                            // NOTE: the H source is decided on the unclamped maximum.  Writing it as
+                            // max(max3(..), 0) followed by `h == f` makes ptxas 12.9 fuse the clamp into
+                            // VIMNMX.RELU with a predicate output whose sense is inverted (observed on
+                            // sm_100a: INS/DEL swapped); for h > 0 both forms are equivalent.
+                            const int h3 = __vimax3_s32(hdiag, e, f);
+                            uint32_t nib = (h3 == hdiag) ? SMX_SRC_DIAG : ((h3 == f) ? SMX_SRC_DEL : SMX_SRC_INS);
+                            h = h3;
+                            if (LOCAL) {
+                                if (h3 <= 0) { h = 0; nib = SMX_SRC_ZERO; }
+                            }
+                            if (e_opn > e_ext) nib |= SMX_BIT_EOPEN;  // tie -> extend
+                            if (f_opn > f_ext) nib |= SMX_BIT_FOPEN;
+                            word |= nib << (4 * k);
+                            if (LOCAL) {
+                                const int i = i0 + k;
+                                if (i < m && (h > loc_best || (h == loc_best && h > 0 && (i < loc_i || (i == loc_i && j < loc_j))))) {
+                                    loc_best = h; loc_i = i; loc_j = j;
+                                }
+                            }
+                            hd = Hl[k];
+                            Hl[k] = h;
+                            hugo = h - go;
+                            Hlgo[k] = hugo;
+                            El[k] = e;
+                            fu = f;
+                        }
+                        hd = hu_in;  // H[i0-1][j] is the diagonal input of the next column
+                        out_h = h;
+                        out_f = f;
+                        trace[((size_t)band * steps + s) * 32 + lane] = (TW)word;
+                        if (lane == 31 && !last_band) __stcg(&bot_line[j], make_int2(h, f));
+                        if (!LOCAL) {
+                            if (j == n - 1) {
+#pragma unroll
+                                for (int k = 0; k < K; ++k) {
+                                    const int i = i0 + k;
+                                    if (i < m - 1 && Hl[k] > col_best) { col_best = Hl[k]; col_best_i = i; }
+                                    if (i == m - 1) corner = Hl[k];
+                                }
+                            }
+                            if (last_band && lane == last_lane) {
+                                int hv = Hl[0];
+#pragma unroll
+                                for (int k = 1; k < K; ++k) if (k == last_k) hv = Hl[k];
+                                if (hv > row_best) { row_best = hv; row_best_j = j; }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- end cell / score -------------------------------------------------------------
+        SmxResult r;
+        r.beg_q = 0; r.beg_r = 0; r.n_runs = 0; r.pad0 = 0; r.pad1 = 0;
+        if (LOCAL) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const int ob = __shfl_xor_sync(SMX_FULL_MASK, loc_best, off);
+                const int oi = __shfl_xor_sync(SMX_FULL_MASK, loc_i, off);
+                const int oj = __shfl_xor_sync(SMX_FULL_MASK, loc_j, off);
+                if (ob > loc_best || (ob == loc_best && ob > 0 && (oi < loc_i || (oi == loc_i && oj < loc_j)))) {
+                    loc_best = ob; loc_i = oi; loc_j = oj;
+                }
+            }
+            r.score = loc_best; r.end_q = loc_i; r.end_r = loc_j;
+        } else {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const int ob = __shfl_xor_sync(SMX_FULL_MASK, col_best, off);
+                const int oi = __shfl_xor_sync(SMX_FULL_MASK, col_best_i, off);
+                if (ob > col_best || (ob == col_best && oi < col_best_i)) { col_best = ob; col_best_i = oi; }
+            }
+            row_best = __shfl_sync(SMX_FULL_MASK, row_best, last_lane);
+            row_best_j = __shfl_sync(SMX_FULL_MASK, row_best_j, last_lane);
+            corner = __shfl_sync(SMX_FULL_MASK, corner, last_lane);
+            if (mode == 1) {  // SMX_MODE_SG_QE_DE
+                int best = SMX_NEG_INF, bi = m - 1, bj = n - 1;
+                if (col_best > best) { best = col_best; bi = col_best_i; bj = n - 1; }
+                if (row_best > best) { best = row_best; bi = m - 1; bj = row_best_j; }
+                r.score = best; r.end_q = bi; r.end_r = bj;
+            } else {
+                r.score = corner; r.end_q = m - 1; r.end_r = n - 1;
+            }
+        }
+        if (lane == 0) a.results[pid] = r;
+    }
+}

@@ -1,0 +1,188 @@
+"""Batched host API over the C-ABI (include/smx.h).  numpy in, numpy out; no torch types."""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+
+MODE_NW, MODE_SG_QE_DE, MODE_SG_QB_DB, MODE_SW = 0, 1, 2, 3
+TOPOLOGY_CIRCULAR, TOPOLOGY_LINEAR = 0, 1
+OP_CHARS = {1: "I", 2: "D", 7: "=", 8: "X"}
+_OP_LUT = np.zeros(16, dtype="S1")
+for _k, _v in OP_CHARS.items():
+    _OP_LUT[_k] = _v.encode()
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+@dataclass
+class AlignBatchResult:
+    """parasail Result fields for n problems in structure-of-arrays form."""
+    score: np.ndarray
+    end_query: np.ndarray
+    end_ref: np.ndarray
+    beg_query: np.ndarray
+    beg_ref: np.ndarray
+    cigar_off: np.ndarray  # int64[n+1]
+    cigar_rle: np.ndarray  # uint32[total], len << 4 | op (BAM op codes)
+
+    def runs(self, p: int) -> np.ndarray:
+        return self.cigar_rle[self.cigar_off[p]: self.cigar_off[p + 1]]
+
+    def cigar_string(self, p: int) -> str:
+        """'12=1X3I' -- the text parasail's `cigar.decode` carries."""
+        r = self.runs(p)
+        return "".join(f"{int(x) >> 4}{OP_CHARS[int(x) & 15]}" for x in r)
+
+    def expanded(self, p: int) -> str:
+        """one letter per alignment column (the reference's `my_cigar`, my_classes.py:428-429)."""
+        r = self.runs(p)
+        if r.size == 0:
+            return ""
+        return np.repeat(_OP_LUT[r & 15], r >> 4).tobytes().decode("ascii")
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Engine:
+    """One engine = one GPU (one `smx_handle`).  Not thread-safe; use one per host thread."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self._lib.smx_create(ctypes.byref(h), int(device), ctypes.c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise EngineError(f"smx_create failed ({rc}): {self._lib.smx_last_error(None).decode()}")
+        self._h = h
+        self.device = device
+        self._pool_len = 0
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.smx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise EngineError(f"{what} failed ({rc}): {self._lib.smx_last_error(self._h).decode()}")
+
+    def set_trace_budget(self, nbytes: int):
+        self._check(self._lib.smx_set_trace_budget(self._h, int(nbytes)), "smx_set_trace_budget")
+
+    @property
+    def last_run_ms(self) -> float:
+        return float(self._lib.smx_last_run_ms(self._h))
+
+    @property
+    def last_run_launches(self) -> int:
+        return int(self._lib.smx_last_run_launches(self._h))
+
+    # -- sequence pool ----------------------------------------------------------------------
+    def upload_pool(self, pool: bytes | np.ndarray):
+        arr = np.frombuffer(pool, dtype=np.uint8) if isinstance(pool, (bytes, bytearray)) else np.ascontiguousarray(pool, dtype=np.uint8)
+        self._check(self._lib.smx_pool_upload(self._h, _ptr(arr), arr.size), "smx_pool_upload")
+        self._pool_len = arr.size
+
+    def upload_sequences(self, seqs: Sequence[str]) -> tuple[np.ndarray, np.ndarray]:
+        """Uploads upper-cased sequences back to back; returns (offsets, lengths)."""
+        enc = [s.upper().encode("ascii") for s in seqs]
+        lens = np.array([len(e) for e in enc], dtype=np.int32)
+        offs = np.zeros(len(enc), dtype=np.int64)
+        if len(enc) > 1:
+            offs[1:] = np.cumsum(lens[:-1], dtype=np.int64)
+        self.upload_pool(b"".join(enc))
+        return offs, lens
+
+    # -- A8: batched DP + traceback ------------------------------------------------------------
+    def align_prepare(self, s1_off, s1_len, s2_off, s2_len, mode, open_: int, extend: int, match: int, mismatch: int):
+        s1_off = np.ascontiguousarray(s1_off, dtype=np.int64)
+        s2_off = np.ascontiguousarray(s2_off, dtype=np.int64)
+        s1_len = np.ascontiguousarray(s1_len, dtype=np.int32)
+        s2_len = np.ascontiguousarray(s2_len, dtype=np.int32)
+        mode = np.ascontiguousarray(mode, dtype=np.uint8)
+        n = s1_off.size
+        if not (s1_len.size == s2_off.size == s2_len.size == mode.size == n):
+            raise ValueError("descriptor arrays must have equal length")
+        self._n = n
+        self._check(self._lib.smx_align_prepare(self._h, _ptr(s1_off), _ptr(s1_len), _ptr(s2_off), _ptr(s2_len), _ptr(mode),
+                                                n, open_, extend, match, mismatch), "smx_align_prepare")
+
+    def align_run(self) -> int:
+        total = ctypes.c_int64(0)
+        self._check(self._lib.smx_align_run(self._h, ctypes.byref(total)), "smx_align_run")
+        self._total_runs = int(total.value)
+        return self._total_runs
+
+    def align_fetch(self) -> AlignBatchResult:
+        n = self._n
+        out = [np.empty(n, dtype=np.int32) for _ in range(5)]
+        off = np.zeros(n + 1, dtype=np.int64)
+        rle = np.empty(max(self._total_runs, 1), dtype=np.uint32)
+        self._check(self._lib.smx_align_fetch(self._h, *[_ptr(a) for a in out], _ptr(off), _ptr(rle), rle.size), "smx_align_fetch")
+        return AlignBatchResult(*out, off, rle[: self._total_runs])
+
+    def align_batch(self, s1_off, s1_len, s2_off, s2_len, mode, open_: int, extend: int, match: int, mismatch: int) -> AlignBatchResult:
+        self.align_prepare(s1_off, s1_len, s2_off, s2_len, mode, open_, extend, match, mismatch)
+        self.align_run()
+        return self.align_fetch()
+
+    @property
+    def align_cells(self) -> int:
+        return int(self._lib.smx_align_cells(self._h))
+
+    # -- A3: diagonal match-count scan ---------------------------------------------------------
+    def scan_prepare(self, ref_off, ref_len, qry_off, qry_len, topology: int) -> np.ndarray:
+        ref_off = np.ascontiguousarray(ref_off, dtype=np.int64)
+        qry_off = np.ascontiguousarray(qry_off, dtype=np.int64)
+        ref_len = np.ascontiguousarray(ref_len, dtype=np.int32)
+        qry_len = np.ascontiguousarray(qry_len, dtype=np.int32)
+        n = ref_off.size
+        counts_off = np.zeros(n + 1, dtype=np.int64)
+        self._check(self._lib.smx_scan_prepare(self._h, _ptr(ref_off), _ptr(ref_len), _ptr(qry_off), _ptr(qry_len), n,
+                                               int(topology), _ptr(counts_off)), "smx_scan_prepare")
+        self._scan_off = counts_off
+        return counts_off
+
+    def scan_run(self):
+        self._check(self._lib.smx_scan_run(self._h), "smx_scan_run")
+
+    def scan_fetch(self) -> np.ndarray:
+        counts = np.empty(max(int(self._scan_off[-1]), 1), dtype=np.int32)
+        self._check(self._lib.smx_scan_fetch(self._h, _ptr(counts), counts.size), "smx_scan_fetch")
+        return counts[: int(self._scan_off[-1])]
+
+    def scan_batch(self, ref_off, ref_len, qry_off, qry_len, topology: int) -> tuple[np.ndarray, np.ndarray]:
+        off = self.scan_prepare(ref_off, ref_len, qry_off, qry_len, topology)
+        self.scan_run()
+        return self.scan_fetch(), off
+
+    @property
+    def scan_cells(self) -> int:
+        return int(self._lib.smx_scan_cells(self._h))
+
+    # -- measurement --------------------------------------------------------------------------
+    def measure_int_peak(self, iters: int = 2000) -> dict:
+        out = (ctypes.c_double * 3)()
+        self._check(self._lib.smx_measure_int_peak(self._h, iters, out), "smx_measure_int_peak")
+        return {"viaddmax_gops": out[0], "vimax3_gops": out[1], "iadd_lop_gops": out[2]}
