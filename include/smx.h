@@ -40,6 +40,8 @@ extern "C" {
 
 #define SMX_OP_I 1u
 #define SMX_OP_D 2u
+#define SMX_OP_S 4u
+#define SMX_OP_H 5u
 #define SMX_OP_EQ 7u
 #define SMX_OP_X 8u
 
@@ -107,6 +109,38 @@ int smx_scan_prepare(smx_handle *h,
 int smx_scan_run(smx_handle *h);
 int smx_scan_fetch(smx_handle *h, int32_t *counts, int64_t counts_capacity);
 int64_t smx_scan_cells(const smx_handle *h);
+
+/* ---- A1: the whole alignment stage in one call ------------------------------------------------
+ * Replaces execute_alignment_core / execute_alignment_core_loop
+ * (savemoney/post_analysis/post_analysis_core.py:56-87) and RecommendedGrouping.set_distance_matrix /
+ * calc_distance (savemoney/pre_survey/pre_survey_core.py:237-271).  For every (query, reference)
+ * pair and both strands (forward, reverse complement -- Bio.Seq semantics, IUPAC aware):
+ *   A3 scan + A4 threshold/conserved runs (GPU) -> A5/A6 chain search (host threads) -> A7 plan ->
+ *   A8 batched DP + traceback (GPU) -> A9-A11 re-clipping, my_special_DP merge, rotation, score.
+ * Inputs are upper-case ASCII; ref_sigma[r] = scipy.stats.norm.ppf(1 - 0.1/len(ref r))
+ * (ref_query_alignment.py:200-201, computed by the Python host with scipy exactly like the reference).
+ * pair_ref/pair_qry: explicit pairs (pre_survey) or both NULL for all (query, reference)
+ * combinations in query-major order (post_analysis).  Pair-strand index = 2*pair + strand, which is
+ * the order of `result_list` in execute_alignment_core_loop (:85).
+ * omit_too_long: 1 for post_analysis (:72-73), 0 for pre_survey (pre_survey_core.py:255-256).
+ * n_threads <= 0: use every host core. */
+int smx_pipeline_run(smx_handle *h,
+                     const uint8_t *ref_seqs, const int64_t *ref_off, const int32_t *ref_len, int32_t n_refs,
+                     const double *ref_sigma,
+                     const uint8_t *qry_seqs, const int64_t *qry_off, const int32_t *qry_len, int32_t n_qrys,
+                     const int32_t *pair_ref, const int32_t *pair_qry, int32_t n_pairs,
+                     int32_t open, int32_t extend, int32_t match, int32_t mismatch,
+                     int32_t topology, int32_t omit_too_long, int32_t n_threads, int64_t *total_runs);
+/* Per pair-strand: score (MyResult.score, 0 for an empty result), new_query_seq_offset (INT32_MIN
+ * encodes None), status (0 = aligned, 1 = empty MyResult(), 2 = the reference would raise an
+ * assertion on this input), CIGAR runs `len << 4 | op` ('I'=1 'D'=2 'S'=4 'H'=5 '='=7 'X'=8) of
+ * MyResult.my_cigar with prefix offsets cigar_off[2*n_pairs + 1]. */
+int smx_pipeline_fetch(smx_handle *h, int32_t *score, int32_t *new_query_seq_offset, uint8_t *status,
+                       int64_t *cigar_off, uint32_t *cigar_rle, int64_t cigar_capacity);
+/* out[0..16]: t_total, t_pool, t_scan, t_select, t_chain, t_dp, t_stitch (host seconds), gpu_scan_ms,
+ * gpu_select_ms, gpu_dp_ms, scan_cells, dp_cells, n_dp_problems, n_host_redecisions, n_failed,
+ * kernel_launches, n_pair_strands */
+int smx_pipeline_stats(smx_handle *h, double *out, int32_t n);
 
 /* ---- measurement helper: dependency-free int32 / DPX issue-rate microbenchmark ---------------
  * Runs `iters` rounds of independent VIADDMNMX / VIMNMX3 / IADD chains on every SM and returns

@@ -32,6 +32,11 @@ _SIGNATURES = {
     "smx_scan_run": (c_int, [c_void_p]),
     "smx_scan_fetch": (c_int, [c_void_p, c_void_p, c_int64]),
     "smx_scan_cells": (c_int64, [c_void_p]),
+    "smx_pipeline_run": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32,
+                                 c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(c_int64)]),
+    "smx_pipeline_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
+    "smx_pipeline_stats": (c_int, [c_void_p, POINTER(c_double), c_int32]),
     "smx_measure_int_peak": (c_int, [c_void_p, c_int32, POINTER(c_double)]),
 }
 

@@ -65,6 +65,11 @@ struct smx_handle {
     int64_t scan_total = 0, scan_cells = 0;
     int32_t scan_tiles = 0, scan_nq_max = 0;
     DevBuf d_scan_pairs, d_scan_tile_pair, d_counts;
+
+    // pipeline state (smx_pipeline.cuh)
+    DevBuf d_sel_pairs, d_sel_out, d_regions;
+    std::vector<uint8_t> host_pool;
+    struct SmxPipelineState *pipe = nullptr;
 };
 
 static thread_local std::string g_create_error;
@@ -108,6 +113,8 @@ static void release(DevBuf &b)
     b.p = nullptr; b.cap = 0;
 }
 
+static void smx_pipeline_free(smx_handle *h);
+
 extern "C" int smx_version(void) { return 100; }
 
 extern "C" const char *smx_last_error(const smx_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -150,7 +157,9 @@ extern "C" void smx_destroy(smx_handle *h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     DevBuf *bufs[] = {&h->pool, &h->d_probs, &h->d_order_cls, &h->d_order_all, &h->d_results, &h->d_trace, &h->d_boundary,
-                      &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts};
+                      &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts,
+                      &h->d_sel_pairs, &h->d_sel_out, &h->d_regions};
+    smx_pipeline_free(h);
     for (DevBuf *b : bufs) release(*b);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -551,4 +560,398 @@ extern "C" int smx_measure_int_peak(smx_handle *h, int32_t iters, double *out_go
         out_gops[which] = ops / (best * 1e-3) / 1e9;
     }
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A1: the whole alignment stage (scan -> select -> chain -> DP -> stitch)
+// ------------------------------------------------------------------------------------------------
+#include "smx_pipeline.cuh"
+
+namespace {
+
+const int kRegionCap = 256;                 // device slots per pair-strand (overflow -> host re-decision)
+const int64_t kCountsBudget = 400ll << 20;  // int32 diagonal counts kept on the device per chunk
+
+uint8_t g_comp[256];
+bool g_comp_ready = false;
+void init_comp()
+{
+    if (g_comp_ready) return;
+    for (int i = 0; i < 256; ++i) g_comp[i] = (uint8_t)i;
+    // Bio.Seq.reverse_complement (my_classes.py:306-310): IUPAC-aware
+    const char *a = "ACGTMRWSYKVHDBN", *b = "TGCAKYWSRMBDHVN";
+    for (int i = 0; a[i]; ++i) g_comp[(uint8_t)a[i]] = (uint8_t)b[i];
+    g_comp_ready = true;
+}
+
+}  // namespace
+
+static SmxPipelineState *pipeline_state(smx_handle *h);
+
+extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const int64_t *ref_off, const int32_t *ref_len, int32_t n_refs,
+                                const double *ref_sigma, const uint8_t *qry_seqs, const int64_t *qry_off, const int32_t *qry_len,
+                                int32_t n_qrys, const int32_t *pair_ref, const int32_t *pair_qry, int32_t n_pairs, int32_t open,
+                                int32_t extend, int32_t match, int32_t mismatch, int32_t topology, int32_t omit_too_long,
+                                int32_t n_threads, int64_t *total_runs)
+{
+    using namespace smx;
+    if (!h) return -1;
+    SmxPipelineState &st = *pipeline_state(h);
+    st = SmxPipelineState();
+    if (!ref_seqs || !ref_off || !ref_len || !ref_sigma || !qry_seqs || !qry_off || !qry_len || n_refs <= 0 || n_qrys <= 0)
+        return fail(h, -1, "smx_pipeline_run: NULL or empty input");
+    if (topology != 0 && topology != 1) return fail(h, -1, "unknown topology_of_dna: %d (ref_query_alignment.py:215)", topology);
+    if ((pair_ref == nullptr) != (pair_qry == nullptr)) return fail(h, -1, "pair_ref and pair_qry must both be given or both be NULL");
+    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    init_comp();
+    const double t_begin = now_s();
+    SMX_CUDA(h, cudaSetDevice(h->device));
+    const Scoring sc{open, extend, match, mismatch};
+
+    // ---- pool: every sequence stored twice back to back so that rotated slices are contiguous ----
+    std::vector<int64_t> rpool((size_t)n_refs), qpool((size_t)n_qrys * 2);
+    int64_t total = 0;
+    for (int r = 0; r < n_refs; ++r) { if (ref_len[r] <= 0) return fail(h, -1, "reference %d is empty", r); rpool[(size_t)r] = total; total += 2ll * ref_len[r]; }
+    for (int q = 0; q < n_qrys; ++q) {
+        if (qry_len[q] <= 0) return fail(h, -1, "query %d is empty", q);
+        if (qry_len[q] > 65535) return fail(h, -1, "query %d: %d bases; this engine supports reads up to 65535 bases", q, qry_len[q]);
+        qpool[(size_t)q * 2] = total; total += 2ll * qry_len[q];
+        qpool[(size_t)q * 2 + 1] = total; total += 2ll * qry_len[q];
+    }
+    {
+        std::vector<uint8_t> pool((size_t)total);
+        for (int r = 0; r < n_refs; ++r) {
+            const uint8_t *s = ref_seqs + ref_off[r];
+            memcpy(&pool[(size_t)rpool[(size_t)r]], s, (size_t)ref_len[r]);
+            memcpy(&pool[(size_t)rpool[(size_t)r] + (size_t)ref_len[r]], s, (size_t)ref_len[r]);
+        }
+        parallel_for(n_qrys, n_threads, [&](int q, int) {
+            const uint8_t *s = qry_seqs + qry_off[q];
+            const int L = qry_len[q];
+            uint8_t *f = &pool[(size_t)qpool[(size_t)q * 2]], *c = &pool[(size_t)qpool[(size_t)q * 2 + 1]];
+            memcpy(f, s, (size_t)L); memcpy(f + L, s, (size_t)L);
+            for (int i = 0; i < L; ++i) c[i] = g_comp[s[L - 1 - i]];
+            memcpy(c + L, c, (size_t)L);
+        });
+        if (int rc = smx_pool_upload(h, pool.data(), total)) return rc;
+        // keep a host copy for the rare host re-decisions
+        h->host_pool.swap(pool);
+    }
+    st.t_pool = now_s() - t_begin;
+
+    // ---- pair-strand table ----
+    const int64_t np_ = pair_ref ? n_pairs : (int64_t)n_qrys * n_refs;
+    if (np_ * 2 > (int64_t)INT32_MAX) return fail(h, -1, "too many pair-strands");
+    st.ps.resize((size_t)np_ * 2);
+    for (int64_t p = 0; p < np_; ++p) {
+        const int r = pair_ref ? pair_ref[p] : (int)(p % n_refs);
+        const int q = pair_qry ? pair_qry[p] : (int)(p / n_refs);
+        if (r < 0 || r >= n_refs || q < 0 || q >= n_qrys) return fail(h, -1, "pair %lld: index out of range", (long long)p);
+        for (int s = 0; s < 2; ++s) {
+            PairStrand &x = st.ps[(size_t)p * 2 + s];
+            x.ref = r; x.qry = q; x.strand = s; x.nr = ref_len[r]; x.nq = qry_len[q];
+            x.ref_pool = rpool[(size_t)r]; x.qry_pool = qpool[(size_t)q * 2 + s];
+            // calc_conserved_region (:207): reads of >= 1.75 reference lengths are dropped (after the scan
+            // in the reference; the scan has no side effect, so it is skipped here)
+            x.skip = omit_too_long && ((double)x.nr * 1.75 <= (double)x.nq);
+        }
+    }
+
+    // ---- A3 + A4 on the device, chunked by the counts budget ----
+    std::vector<int> active;
+    for (size_t i = 0; i < st.ps.size(); ++i) if (!st.ps[i].skip) active.push_back((int)i);
+    size_t pos = 0;
+    std::vector<int64_t> s_roff, s_qoff, c_off;
+    std::vector<int32_t> s_rlen, s_qlen;
+    std::vector<SmxSelPair> sel_pairs;
+    std::vector<SmxSelOut> sel_out;
+    std::vector<SmxRegion> reg_host, redo;
+    std::vector<int32_t> counts_host;
+    while (pos < active.size()) {
+        size_t end = pos;
+        int64_t budget = 0;
+        while (end < active.size()) {
+            const PairStrand &x = st.ps[(size_t)active[end]];
+            const int64_t mk = topology == 0 ? x.nr : (int64_t)x.nr + x.nq - 1;
+            if (end > pos && budget + mk > kCountsBudget) break;
+            budget += mk; ++end;
+        }
+        const int n = (int)(end - pos);
+        s_roff.resize(n); s_qoff.resize(n); s_rlen.resize(n); s_qlen.resize(n); c_off.resize((size_t)n + 1);
+        for (int i = 0; i < n; ++i) {
+            const PairStrand &x = st.ps[(size_t)active[pos + i]];
+            s_roff[i] = x.ref_pool; s_qoff[i] = x.qry_pool; s_rlen[i] = x.nr; s_qlen[i] = x.nq;
+        }
+        double t0 = now_s();
+        if (int rc = smx_scan_prepare(h, s_roff.data(), s_rlen.data(), s_qoff.data(), s_qlen.data(), n, topology, c_off.data())) return rc;
+        if (int rc = smx_scan_run(h)) return rc;
+        st.gpu_scan_ms += h->last_ms; st.scan_cells += h->scan_cells; st.launches += 1;
+        st.t_scan += now_s() - t0;
+        t0 = now_s();
+        sel_pairs.resize(n); sel_out.resize(n);
+        for (int i = 0; i < n; ++i) {
+            const PairStrand &x = st.ps[(size_t)active[pos + i]];
+            SmxSelPair &s = sel_pairs[i];
+            s.ref_off = x.ref_pool; s.qry_off = x.qry_pool; s.counts_off = c_off[i]; s.region_off = (int64_t)i * kRegionCap;
+            s.sigma = ref_sigma[x.ref]; s.nr = x.nr; s.nq = x.nq;
+            s.max_k = (int32_t)(c_off[(size_t)i + 1] - c_off[i]);
+            if (topology == 0) { s.slice_lo = 0; s.slice_hi = x.nr; }
+            else if (x.nr > x.nq) { s.slice_lo = x.nq - 1; s.slice_hi = x.nr; }   // :363-366
+            else { s.slice_lo = x.nr - 1; s.slice_hi = x.nq; }
+            s.region_cap = kRegionCap;
+        }
+        if (int rc = ensure(h, h->d_sel_pairs, sizeof(SmxSelPair) * (size_t)n)) return rc;
+        if (int rc = ensure(h, h->d_sel_out, sizeof(SmxSelOut) * (size_t)n)) return rc;
+        if (int rc = ensure(h, h->d_regions, sizeof(SmxRegion) * (size_t)n * kRegionCap)) return rc;
+        SMX_CUDA(h, cudaMemcpyAsync(h->d_sel_pairs.p, sel_pairs.data(), sizeof(SmxSelPair) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+        SmxSelArgs sa;
+        sa.pool = (const uint8_t *)h->pool.p; sa.pairs = (const SmxSelPair *)h->d_sel_pairs.p; sa.counts = (const int32_t *)h->d_counts.p;
+        sa.regions = (SmxRegion *)h->d_regions.p; sa.out = (SmxSelOut *)h->d_sel_out.p; sa.topology = topology;
+        SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+        smx_select_kernel<<<n, SMX_SEL_THREADS, 0, h->stream>>>(sa);
+        SMX_CUDA(h, cudaGetLastError());
+        SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        st.launches += 1;
+        reg_host.resize((size_t)n * kRegionCap);
+        SMX_CUDA(h, cudaMemcpyAsync(sel_out.data(), h->d_sel_out.p, sizeof(SmxSelOut) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        SMX_CUDA(h, cudaMemcpyAsync(reg_host.data(), h->d_regions.p, sizeof(SmxRegion) * (size_t)n * kRegionCap, cudaMemcpyDeviceToHost, h->stream));
+        SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+        { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1); st.gpu_select_ms += ms; }
+        for (int i = 0; i < n; ++i) {
+            PairStrand &x = st.ps[(size_t)active[pos + i]];
+            const SmxSelOut &o = sel_out[i];
+            const SmxRegion *rg = &reg_host[(size_t)i * kRegionCap];
+            int nreg = o.n_regions;
+            if (o.flags) {  // ambiguous threshold or overflow: decide on the host from this pair-strand's counts
+                const SmxSelPair &s = sel_pairs[i];
+                counts_host.resize((size_t)s.max_k);
+                SMX_CUDA(h, cudaMemcpy(counts_host.data(), (const int32_t *)h->d_counts.p + s.counts_off, sizeof(int32_t) * (size_t)s.max_k, cudaMemcpyDeviceToHost));
+                host_regions(&h->host_pool[(size_t)x.ref_pool], &h->host_pool[(size_t)x.qry_pool], x.nr, x.nq, topology, counts_host.data(),
+                             s.max_k, s.slice_lo, s.slice_hi, s.sigma, redo);
+                rg = redo.data(); nreg = (int)redo.size();
+                ++st.n_host_redo;
+            }
+            if (nreg == 0) { x.skip = true; continue; }
+            std::vector<SmxRegion> tmp(rg, rg + nreg);
+            std::sort(tmp.begin(), tmp.end(), [](const SmxRegion &a, const SmxRegion &b) { return a.k != b.k ? a.k < b.k : a.qs < b.qs; });
+            x.regions.resize((size_t)nreg);
+            for (int t = 0; t < nreg; ++t) {
+                int64_t rs = (int64_t)tmp[t].k + tmp[t].qs, re = (int64_t)tmp[t].k + tmp[t].qe;
+                int32_t qs = tmp[t].qs, qe = tmp[t].qe;
+                if (topology == 0) {  // :411-417
+                    if (re - rs > x.nr - 1) { re = rs - 1; qe = qs + x.nr - 1; }
+                    rs %= x.nr; re %= x.nr;
+                    if (re < 0) re += x.nr;
+                } else {  // :418-420
+                    rs -= x.nq - 1; re -= x.nq - 1;
+                }
+                x.regions[(size_t)t] = Region{(int32_t)rs, (int32_t)re, qs, qe};
+            }
+        }
+        st.t_select += now_s() - t0;
+        pos = end;
+    }
+
+    // ---- A5/A6/A7: chain + plan on host threads ----
+    double t0 = now_s();
+    std::vector<int> todo;
+    for (size_t i = 0; i < st.ps.size(); ++i) if (!st.ps[i].skip) todo.push_back((int)i);
+    std::vector<std::vector<PlannedProblem>> local((size_t)todo.size());
+    std::vector<ChainSearch> searchers((size_t)std::max(1, n_threads));
+    parallel_for((int)todo.size(), n_threads, [&](int ti, int tid) {
+        PairStrand &x = st.ps[(size_t)todo[(size_t)ti]];
+        std::vector<PlannedProblem> &probs = local[(size_t)ti];
+        std::vector<int> trace;
+        const bool ok = topology == 0 ? searchers[(size_t)tid].circular(x.regions, x.nr, x.nq, trace) : searchers[(size_t)tid].linear(x.regions, trace);
+        if (!ok || trace.empty()) { x.failed = true; return; }
+        std::vector<Region> P(trace.size());
+        for (size_t t = 0; t < trace.size(); ++t) P[t] = x.regions[(size_t)trace[t]];
+        const int nr = x.nr, nq = x.nq;
+        auto add_problem = [&](uint8_t mode, int qs, int qlen, int rs, int rlen) -> int {
+            // slices are in rotated coordinates; the doubled pool makes them contiguous
+            PlannedProblem pp;
+            pp.s1_off = x.qry_pool + ((int64_t)x.q_off + qs) % nq; pp.m = qlen;
+            pp.s2_off = x.ref_pool + ((int64_t)x.ref_off + rs) % nr; pp.n = rlen;
+            pp.mode = mode;
+            probs.push_back(pp);
+            return (int)probs.size() - 1;
+        };
+        auto literal = [&](char c, int len) { if (len > 0) x.pieces.push_back(Piece{PIECE_LITERAL, c, len, {-1, -1}, 0, 0, 0}); };
+        auto fill_gap = [&](int rs, int re, int qs, int qe) -> bool {  // execute_alignment_using_conserved_regions_core (:330-345)
+            if (rs > re) { if (rs - 1 != re) return false; literal('I', qe - qs + 1); return true; }
+            if (qs > qe) { if (qs - 1 != qe) return false; literal('D', re - rs + 1); return true; }
+            const int id = add_problem(SMX_MODE_NW, qs, qe - qs + 1, rs, re - rs + 1);
+            x.pieces.push_back(Piece{PIECE_NW, 0, 0, {id, -1}, 0, 0, 0});
+            return true;
+        };
+        const size_t np2 = P.size();
+        if (topology == 0) {
+            // set_tidy_offset (:725-736): start the chain at the region with the smallest query start
+            if (!(P.back().qs < P.back().qe)) { x.failed = true; return; }
+            size_t amin = 0;
+            for (size_t t = 1; t < np2; ++t) if (P[t].qs < P[amin].qs) amin = t;
+            std::rotate(P.begin(), P.begin() + (long)amin, P.end());
+            x.ref_off = P[0].rs; x.q_off = P[0].qs;
+            for (Region &g : P) {
+                g.rs -= x.ref_off; g.re -= x.ref_off; g.qs -= x.q_off; g.qe -= x.q_off;
+                if (g.rs < 0) g.rs += nr;
+                if (g.re < 0) g.re += nr;
+                if (g.qs < 0) g.qs += nq;
+                if (g.qe < 0) g.qe += nq;
+            }
+            const int q_end = nq - x.q_off - 1;
+            for (size_t t = 0; t < np2; ++t) {  // iter_regions (:763-781)
+                const Region &g = P[t];
+                const Region &nx = P[(t + 1) % np2];
+                literal('=', g.re - g.rs + 1);
+                const int rs = g.re + 1, qs = g.qe + 1, re = nx.rs - 1, qe = nx.qs - 1;
+                if (re != -1) { if (!fill_gap(rs, re, qs, qe)) { x.failed = true; return; } continue; }
+                if (qe != -1) { x.failed = true; return; }  // assert at :285
+                if (rs == nr) literal('S', nq - qs);
+                else if (qs == nq) literal('H', nr - rs);
+                else {  // my_special_DP (:293-302)
+                    const int n1 = std::max(0, q_end + 1 - qs), n2 = nq - (q_end + 1), nrf = nr - rs;
+                    Piece pc{PIECE_SPECIAL, 0, 0, {-1, -1}, nrf, n1, n2};
+                    if (n1 > 0) pc.prob[0] = add_problem(SMX_MODE_SG_QE_DE, qs, n1, rs, nrf);
+                    if (n2 > 0) pc.prob[1] = add_problem(SMX_MODE_SG_QB_DB, q_end + 1, n2, rs, nrf);
+                    x.pieces.push_back(pc);
+                }
+            }
+        } else {
+            x.ref_off = 0; x.q_off = 0;
+            // execute_alignment_using_conserved_regions_linear (:226-268)
+            const int hre = P[0].rs - 1, hqe = P[0].qs - 1;
+            if (hre == -1) literal('S', hqe + 1);
+            else if (hqe == -1) literal('H', hre + 1);
+            else { const int id = add_problem(SMX_MODE_SG_QB_DB, 0, hqe + 1, 0, hre + 1); x.pieces.push_back(Piece{PIECE_SG_HEAD, 0, 0, {id, -1}, 0, 0, 0}); }
+            for (size_t t = 0; t + 1 < np2; ++t) {
+                literal('=', P[t].re - P[t].rs + 1);
+                if (!fill_gap(P[t].re + 1, P[t + 1].rs - 1, P[t].qe + 1, P[t + 1].qs - 1)) { x.failed = true; return; }
+            }
+            const Region &g = P.back();
+            literal('=', g.re - g.rs + 1);
+            const int rs = g.re + 1, qs = g.qe + 1;
+            if (rs == nr) literal('S', nq - qs);
+            else if (qs == nq) literal('H', nr - rs);
+            else { const int id = add_problem(SMX_MODE_SG_QE_DE, qs, nq - qs, rs, nr - rs); x.pieces.push_back(Piece{PIECE_SG_TAIL, 0, 0, {id, -1}, 0, 0, 0}); }
+        }
+    });
+    // global problem ids
+    std::vector<int64_t> p_s1, p_s2;
+    std::vector<int32_t> p_m, p_n;
+    std::vector<uint8_t> p_mode;
+    for (size_t ti = 0; ti < todo.size(); ++ti) {
+        PairStrand &x = st.ps[(size_t)todo[ti]];
+        if (x.failed) { ++st.n_failed; continue; }
+        const int base = (int)p_m.size();
+        for (const PlannedProblem &pp : local[ti]) {
+            if (pp.m <= 0 || pp.n <= 0) return fail(h, -5, "internal: empty DP slice planned");
+            p_s1.push_back(pp.s1_off); p_s2.push_back(pp.s2_off); p_m.push_back(pp.m); p_n.push_back(pp.n); p_mode.push_back(pp.mode);
+        }
+        for (Piece &pc : x.pieces) for (int z = 0; z < 2; ++z) if (pc.prob[z] >= 0) pc.prob[z] += base;
+    }
+    local.clear();
+    st.t_chain = now_s() - t0;
+
+    // ---- A8 on the device ----
+    t0 = now_s();
+    const int n_prob = (int)p_m.size();
+    std::vector<int64_t> cg_off((size_t)n_prob + 1, 0);
+    std::vector<uint32_t> cg;
+    st.n_dp = n_prob;
+    if (n_prob > 0) {
+        if (int rc = smx_align_prepare(h, p_s1.data(), p_m.data(), p_s2.data(), p_n.data(), p_mode.data(), n_prob, open, extend, match, mismatch)) return rc;
+        int64_t truns = 0;
+        if (int rc = smx_align_run(h, &truns)) return rc;
+        st.gpu_dp_ms = h->last_ms; st.dp_cells = h->cells; st.launches += h->last_launches;
+        cg.resize((size_t)std::max<int64_t>(truns, 1));
+        if (int rc = smx_align_fetch(h, nullptr, nullptr, nullptr, nullptr, nullptr, cg_off.data(), cg.data(), (int64_t)cg.size())) return rc;
+    }
+    st.t_dp = now_s() - t0;
+
+    // ---- A9-A11 on host threads ----
+    t0 = now_s();
+    std::atomic<int> n_bad(0);
+    parallel_for((int)todo.size(), n_threads, [&](int ti, int) {
+        PairStrand &x = st.ps[(size_t)todo[(size_t)ti]];
+        if (x.failed) return;
+        std::string cig, tmp;
+        auto expand = [&](int pid, std::string &dst) { expand_runs(&cg[(size_t)cg_off[(size_t)pid]], cg_off[(size_t)pid + 1] - cg_off[(size_t)pid], dst); };
+        for (const Piece &pc : x.pieces) {
+            switch (pc.kind) {
+            case PIECE_LITERAL: cig.append((size_t)pc.len, pc.letter); break;
+            case PIECE_NW: expand(pc.prob[0], cig); break;
+            case PIECE_SG_HEAD: { SgResult r; expand(pc.prob[0], r.cig); finish_qb_db(r, sc); cig += r.cig; break; }
+            case PIECE_SG_TAIL: { SgResult r; expand(pc.prob[0], r.cig); finish_qe_de(r, sc); cig += r.cig; break; }
+            case PIECE_SPECIAL: {
+                SgResult r1, r2;
+                if (pc.prob[0] >= 0) { expand(pc.prob[0], r1.cig); finish_qe_de(r1, sc); }
+                else { r1.cig.assign((size_t)pc.n_ref, 'H'); r1.beg_ref = -1; r1.end_ref = -1; }
+                if (pc.prob[1] >= 0) { expand(pc.prob[1], r2.cig); finish_qb_db(r2, sc); }
+                else { r2.cig.assign((size_t)pc.n_ref, 'H'); r2.beg_ref = pc.n_ref; r2.end_ref = pc.n_ref; }
+                if (!merge_special(r1, r2, (size_t)pc.n_ref, (size_t)pc.nq1, (size_t)pc.nq2, sc, tmp)) { x.failed = true; n_bad++; return; }
+                cig += tmp;
+                break;
+            }
+            }
+        }
+        int64_t new_off = 0;
+        if (topology == 0) new_off = rotate_to_ref0(cig, x.ref_off, x.q_off);
+        x.score = (int32_t)cigar_score(cig, sc);
+        x.new_q_off = (int32_t)new_off;
+        encode_runs(cig, x.runs);
+    });
+    st.n_failed += n_bad.load();
+    st.t_stitch = now_s() - t0;
+
+    st.out_off.assign(st.ps.size() + 1, 0);
+    for (size_t i = 0; i < st.ps.size(); ++i) st.out_off[i + 1] = st.out_off[i] + (int64_t)st.ps[i].runs.size();
+    st.total_runs = st.out_off.back();
+    st.t_total = now_s() - t_begin;
+    st.valid = true;
+    if (total_runs) *total_runs = st.total_runs;
+    return 0;
+}
+
+extern "C" int smx_pipeline_fetch(smx_handle *h, int32_t *score, int32_t *new_query_seq_offset, uint8_t *status, int64_t *cigar_off,
+                                  uint32_t *cigar_rle, int64_t cigar_capacity)
+{
+    if (!h) return -1;
+    SmxPipelineState &st = *pipeline_state(h);
+    if (!st.valid) return fail(h, -1, "smx_pipeline_fetch: no completed smx_pipeline_run");
+    if (cigar_capacity < st.total_runs) return fail(h, -1, "smx_pipeline_fetch: cigar buffer too small");
+    for (size_t i = 0; i < st.ps.size(); ++i) {
+        const smx::PairStrand &x = st.ps[i];
+        const bool empty = x.skip || x.failed;
+        if (score) score[i] = empty ? 0 : x.score;
+        if (new_query_seq_offset) new_query_seq_offset[i] = empty ? INT32_MIN : x.new_q_off;
+        if (status) status[i] = x.failed ? 2 : (x.skip ? 1 : 0);
+        if (cigar_rle && !x.runs.empty()) memcpy(cigar_rle + st.out_off[i], x.runs.data(), sizeof(uint32_t) * x.runs.size());
+    }
+    if (cigar_off) memcpy(cigar_off, st.out_off.data(), sizeof(int64_t) * st.out_off.size());
+    return 0;
+}
+
+extern "C" int smx_pipeline_stats(smx_handle *h, double *out, int32_t n)
+{
+    if (!h || !out) return -1;
+    const SmxPipelineState &st = *pipeline_state(h);
+    const double v[] = {st.t_total, st.t_pool, st.t_scan, st.t_select, st.t_chain, st.t_dp, st.t_stitch, st.gpu_scan_ms, st.gpu_select_ms,
+                        st.gpu_dp_ms, (double)st.scan_cells, (double)st.dp_cells, (double)st.n_dp, (double)st.n_host_redo, (double)st.n_failed,
+                        (double)st.launches, (double)st.ps.size()};
+    const int m = (int)(sizeof(v) / sizeof(v[0]));
+    for (int i = 0; i < n; ++i) out[i] = i < m ? v[i] : 0.0;
+    return 0;
+}
+
+static SmxPipelineState *pipeline_state(smx_handle *h)
+{
+    if (!h->pipe) h->pipe = new SmxPipelineState();
+    return h->pipe;
+}
+
+static void smx_pipeline_free(smx_handle *h)
+{
+    delete h->pipe;
+    h->pipe = nullptr;
 }

@@ -1,0 +1,190 @@
+// Row A4 on the device: threshold over the diagonal counts and conserved-run detection.
+// Restates calc_conserved_region_core's selection (ref_query_alignment.py:388) and
+// WindowAnalysis.exec (:966-984):
+//     selected k : counts[k] > median(counts[slice]) + sigma * std(counts[slice])
+//     regions    : maximal runs of ref_ext[k+i] == query[i] with length > 20 on every selected k
+// One CTA per pair-strand.  median by a two-level 256-bin histogram select (exact), mean/variance
+// from exact int64 sums; the float64 threshold differs from numpy's pairwise-summed value by a few
+// ulps at most, so pair-strands whose threshold lies within 1e-6 of an integer are flagged and
+// re-decided on the host with numpy's exact summation order (smx_pipeline.cuh).
+#pragma once
+#include "smx_common.cuh"
+
+#define SMX_SEL_THREADS 256
+#define SMX_SEL_MAX_K 2048   // selected diagonals kept per pair-strand (overflow -> host path)
+#define SMX_RUN_MIN 20       // WindowAnalysis.consecutive_true_threshold
+
+struct SmxSelPair {
+    int64_t ref_off, qry_off, counts_off, region_off;
+    double sigma;
+    int32_t nr, nq, max_k, slice_lo, slice_hi, region_cap;
+};
+
+struct SmxSelOut {
+    double thr;
+    int32_t n_regions;  // may exceed region_cap (then flagged)
+    int32_t n_selected;
+    int32_t flags;      // 1 = threshold ambiguous, 2 = selected overflow, 4 = region overflow
+    int32_t pad;
+};
+
+struct SmxRegion { int32_t k, qs, qe; };
+
+struct SmxSelArgs {
+    const uint8_t *pool;
+    const SmxSelPair *pairs;
+    const int32_t *counts;
+    SmxRegion *regions;
+    SmxSelOut *out;
+    int32_t topology;
+};
+
+// k-th smallest (0-based rank) of v[lo..hi) with values in [0, 65535]
+__device__ int smx_select_rank(const int32_t *v, int lo, int hi, int rank, int *hist /*256*/, int *bcast)
+{
+    const int tid = threadIdx.x;
+    hist[tid] = 0;
+    __syncthreads();
+    for (int x = lo + tid; x < hi; x += SMX_SEL_THREADS) atomicAdd(&hist[(v[x] >> 8) & 255], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0, b = 0;
+        for (; b < 256; ++b) { if (acc + hist[b] > rank) break; acc += hist[b]; }
+        bcast[0] = b; bcast[1] = rank - acc;
+    }
+    __syncthreads();
+    const int hb = bcast[0], r2 = bcast[1];
+    __syncthreads();
+    hist[tid] = 0;
+    __syncthreads();
+    for (int x = lo + tid; x < hi; x += SMX_SEL_THREADS) { const int c = v[x]; if (((c >> 8) & 255) == hb) atomicAdd(&hist[c & 255], 1); }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0, b = 0;
+        for (; b < 256; ++b) { if (acc + hist[b] > r2) break; acc += hist[b]; }
+        bcast[2] = (hb << 8) | b;
+    }
+    __syncthreads();
+    const int res = bcast[2];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(SMX_SEL_THREADS) smx_select_kernel(const SmxSelArgs a)
+{
+    __shared__ int hist[256];
+    __shared__ int bcast[4];
+    __shared__ long long red[2 * (SMX_SEL_THREADS / 32)];
+    __shared__ int sel[SMX_SEL_MAX_K];
+    __shared__ int n_sel, n_reg;
+    __shared__ double thr_s;
+
+    const SmxSelPair pr = a.pairs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t *cnt = a.counts + pr.counts_off;
+    const int lo = pr.slice_lo, hi = pr.slice_hi, n = hi - lo;
+    int flags = 0;
+
+    // exact sums
+    long long s1 = 0, s2 = 0;
+    for (int x = lo + tid; x < hi; x += SMX_SEL_THREADS) { const long long c = cnt[x]; s1 += c; s2 += c * c; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { s1 += __shfl_xor_sync(SMX_FULL_MASK, s1, off); s2 += __shfl_xor_sync(SMX_FULL_MASK, s2, off); }
+    if (lane == 0) { red[warp] = s1; red[SMX_SEL_THREADS / 32 + warp] = s2; }
+    if (tid == 0) { n_sel = 0; n_reg = 0; }
+    __syncthreads();
+    // median (np.median: mean of the two middle order statistics for even n)
+    const int m_lo = smx_select_rank(cnt, lo, hi, (n - 1) / 2, hist, bcast);
+    const int m_hi = (n & 1) ? m_lo : smx_select_rank(cnt, lo, hi, n / 2, hist, bcast);
+    if (tid == 0) {
+        long long t1 = 0, t2 = 0;
+        for (int w = 0; w < SMX_SEL_THREADS / 32; ++w) { t1 += red[w]; t2 += red[SMX_SEL_THREADS / 32 + w]; }
+        const double med = ((double)m_lo + (double)m_hi) * 0.5;
+        const double var = (double)(t2 * (long long)n - t1 * t1) / ((double)n * (double)n);
+        thr_s = med + pr.sigma * sqrt(var > 0.0 ? var : 0.0);
+    }
+    __syncthreads();
+    const double thr = thr_s;
+    if (fabs(thr - rint(thr)) < 1e-6) flags |= 1;
+
+    // selected diagonals, ascending k (ordered compaction, 256 candidates per round)
+    for (int base = 0; base < pr.max_k; base += SMX_SEL_THREADS) {
+        const int k = base + tid;
+        const bool hit = k < pr.max_k && (double)cnt[k] > thr;
+        const unsigned bal = __ballot_sync(SMX_FULL_MASK, hit);
+        if (lane == 0) hist[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < warp; ++w) before += hist[w];
+        int total = 0;
+        for (int w = 0; w < SMX_SEL_THREADS / 32; ++w) total += hist[w];
+        const int pos = n_sel + before + __popc(bal & ((1u << lane) - 1u));
+        if (hit && pos < SMX_SEL_MAX_K) sel[pos] = k;
+        __syncthreads();
+        if (tid == 0) n_sel += total;
+        __syncthreads();
+    }
+    int nsel = n_sel;
+    if (nsel > SMX_SEL_MAX_K) { flags |= 2; nsel = SMX_SEL_MAX_K; }
+
+    // conserved runs: one warp per selected diagonal
+    const uint8_t *ref = a.pool + pr.ref_off;
+    const uint8_t *qry = a.pool + pr.qry_off;
+    const int nr = pr.nr, nq = pr.nq;
+    const bool linear = a.topology == 1;
+    SmxRegion *out = a.regions + pr.region_off;
+    for (int si = warp; si < nsel; si += SMX_SEL_THREADS / 32) {
+        const int k = sel[si];
+        int start = -1;  // lane 0: start of the open run
+        for (int base = 0; base < nq; base += 32) {
+            const int i = base + lane;
+            bool eq = false;
+            if (i < nq) {
+                int p = linear ? (k - (nq - 1) + i) : ((k + i) % nr);
+                if (!linear || (p >= 0 && p < nr)) eq = ref[p] == qry[i];
+            }
+            unsigned m = __ballot_sync(SMX_FULL_MASK, eq);
+            if (lane == 0) {
+                int pos = 0;
+                while (pos < 32) {
+                    if (start >= 0) {
+                        const unsigned z = ~m >> pos;  // first mismatch at or after pos
+                        if (z == 0) break;
+                        const int off = __ffs(z) - 1;
+                        const int end = base + pos + off - 1;
+                        if (end - start + 1 > SMX_RUN_MIN) {
+                            const int idx = atomicAdd(&n_reg, 1);
+                            if (idx < pr.region_cap) out[idx] = SmxRegion{k, start, end};
+                        }
+                        start = -1;
+                        pos += off;
+                    } else {
+                        const unsigned o = m >> pos;
+                        if (o == 0) break;
+                        const int off = __ffs(o) - 1;
+                        start = base + pos + off;
+                        pos += off;
+                    }
+                }
+            }
+        }
+        if (lane == 0 && start >= 0) {
+            const int end = nq - 1;
+            if (end - start + 1 > SMX_RUN_MIN) {
+                const int idx = atomicAdd(&n_reg, 1);
+                if (idx < pr.region_cap) out[idx] = SmxRegion{k, start, end};
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        SmxSelOut o;
+        o.thr = thr;
+        o.n_regions = n_reg;
+        o.n_selected = n_sel;
+        if (n_reg > pr.region_cap) flags |= 4;
+        o.flags = flags;
+        o.pad = 0;
+        a.out[blockIdx.x] = o;
+    }
+}

@@ -1,0 +1,254 @@
+// Rows A7, A9, A10, A11 on the host (C++): CIGAR post-processing around the DP results.
+// Works on expanded column strings (one letter per alignment column, the reference's `my_cigar`,
+// savemoney/modules/my_classes.py:428-429) with the alphabet = X I D S H (+ N O inside the merge).
+// Restates, with file:line in savemoney/modules/ref_query_alignment.py unless noted:
+//   soft_clip()        MyResult.set_soft_clipping(_core)              :562-622
+//   merge_special()    MyAlignerBase.my_special_DP                    :89-163
+//   aligned_columns()  msa.MyMSA.generate_msa for two rows            modules/msa.py:882-982
+//   prefix_scores()    cumsum_my_cigar_scores                         :164-185
+//   rotate_to_ref0()   MyResult.set_ref_seq_offset_as_0 (+ helpers)   :465-511
+//   cigar_score()      MyResult.set_cigar_score                       :452-464
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace smx {
+
+struct Scoring { int go, ge, ma, mi; };
+
+inline char op_char(uint32_t code)
+{
+    switch (code) { case 1: return 'I'; case 2: return 'D'; case 4: return 'S'; case 5: return 'H'; case 7: return '='; case 8: return 'X'; default: return '?'; }
+}
+inline uint32_t op_code(char c)
+{
+    switch (c) { case 'I': return 1; case 'D': return 2; case 'S': return 4; case 'H': return 5; case '=': return 7; case 'X': return 8; default: return 15; }
+}
+
+inline void expand_runs(const uint32_t *runs, int64_t n, std::string &out)
+{
+    for (int64_t i = 0; i < n; ++i) out.append((size_t)(runs[i] >> 4), op_char(runs[i] & 15u));
+}
+
+inline void encode_runs(const std::string &cig, std::vector<uint32_t> &out)
+{
+    out.clear();
+    size_t i = 0;
+    while (i < cig.size()) {
+        size_t j = i;
+        while (j < cig.size() && cig[j] == cig[i]) ++j;
+        out.push_back((uint32_t)((j - i) << 4) | op_code(cig[i]));
+        i = j;
+    }
+}
+
+inline int64_t count_of(const std::string &s, size_t from, size_t to, const char *letters)
+{
+    int64_t n = 0;
+    for (size_t i = from; i < to; ++i)
+        for (const char *l = letters; *l; ++l) if (s[i] == *l) { ++n; break; }
+    return n;
+}
+
+// set_soft_clipping_core: keep the prefix up to the first maximum of the running affine score, turn
+// the rest into S (query columns) + H (reference columns). Returns the number of aligned reference bases.
+inline int64_t soft_clip(std::string &cig, const Scoring &sc)
+{
+    int64_t cur = 0, best = 0, best_i = -1;
+    char prev = 0;
+    for (size_t i = 0; i < cig.size(); ++i) {
+        const char L = cig[i];
+        if (L == '=') cur += sc.ma;
+        else if (L == 'X') cur += sc.mi;
+        else cur -= (prev == L) ? sc.ge : sc.go;  // I or D
+        if (best_i < 0 || cur > best) { best = cur; best_i = (int64_t)i; }
+        prev = L;
+    }
+    const size_t total = cig.size();
+    if (best < 0) {
+        const int64_t nq = (int64_t)total - count_of(cig, 0, total, "D");
+        const int64_t nr = (int64_t)total - count_of(cig, 0, total, "I");
+        cig.assign((size_t)nq, 'S');
+        cig.append((size_t)nr, 'H');
+        return 0;
+    }
+    const size_t keep = (size_t)best_i + 1;
+    const int64_t n_s = (int64_t)(total - keep) - count_of(cig, keep, total, "D");
+    const int64_t n_h = (int64_t)(total - keep) - count_of(cig, keep, total, "I");
+    const int64_t aligned_ref = (int64_t)keep - count_of(cig, 0, keep, "I");
+    cig.resize(keep);
+    cig.append((size_t)n_s, 'S');
+    cig.append((size_t)n_h, 'H');
+    return aligned_ref;
+}
+
+struct SgResult {
+    std::string cig;
+    int64_t beg_ref = 0, end_ref = 0;
+};
+
+// my_special_sg_qe_de (:60-73): clip from the front
+inline void finish_qe_de(SgResult &r, const Scoring &sc) { r.end_ref = soft_clip(r.cig, sc) - 1; }
+
+// my_special_sg_qb_db (:74-87): clip on the reversed string
+inline void finish_qb_db(SgResult &r, const Scoring &sc)
+{
+    std::string rev(r.cig.rbegin(), r.cig.rend());
+    soft_clip(rev, sc);
+    r.beg_ref = count_of(rev, 0, rev.size(), "H");
+    r.cig.assign(rev.rbegin(), rev.rend());
+}
+
+// generate_msa reduced to my_cigar_list_aligned for two rows
+inline bool aligned_columns(const std::string &c1, const std::string &c2, size_t n_ref, size_t nq1, size_t nq2,
+                            std::string &a1, std::string &a2)
+{
+    if (c1.empty() || c2.empty()) return false;
+    const std::string cg[2] = {c1 + "Z" + c1.back(), c2 + "Z" + c2.back()};
+    const size_t nq[2] = {nq1, nq2};
+    size_t ci[2] = {0, 0}, qi[2] = {0, 0}, ri = 0;
+    std::string *out[2] = {&a1, &a2};
+    a1.clear(); a2.clear();
+    auto filler = [&](int i) -> char {
+        const std::string &c = cg[i];
+        const size_t x = ci[i];
+        const char before = x == 0 ? c.back() : c[x - 1];  // Python index -1 wraps to the appended last letter
+        return (c[x] == 'H' || before == 'H' || (c[x] == 'Z' && c[0] == 'H')) ? 'O' : 'N';
+    };
+    for (;;) {
+        const char col[2] = {cg[0][ci[0]], cg[1][ci[1]]};
+        const bool has_i = col[0] == 'I' || col[1] == 'I', has_s = col[0] == 'S' || col[1] == 'S';
+        if (!has_i && !has_s) {
+            if (ri == n_ref) {  // the sentinel 'Z' of the reference
+                if (!(col[0] == 'Z' && col[1] == 'Z' && qi[0] == nq[0] && qi[1] == nq[1])) return false;
+                return true;
+            }
+            for (int i = 0; i < 2; ++i) {
+                const char L = col[i];
+                if (L == '=' || L == 'X') ++qi[i];
+                else if (L != 'D' && L != 'H') return false;
+                out[i]->push_back(L);
+                ++ci[i];
+            }
+            ++ri;
+        } else {
+            const char want = has_s ? 'S' : 'I';
+            for (int i = 0; i < 2; ++i) {
+                if (col[i] == want) { out[i]->push_back(want); ++ci[i]; ++qi[i]; }
+                else out[i]->push_back(filler(i));
+            }
+        }
+    }
+}
+
+// cumsum_my_cigar_scores: acc[0] = 0, acc[x+1] = score after column x; gap runs are maximal same-letter runs
+inline void prefix_scores(const std::string &cig, const Scoring &sc, std::vector<int64_t> &acc)
+{
+    acc.assign(cig.size() + 1, 0);
+    char prev = 0;
+    for (size_t i = 0; i < cig.size(); ++i) {
+        const char L = cig[i];
+        int64_t d = 0;
+        if (L == '=') d = sc.ma;
+        else if (L == 'X') d = sc.mi;
+        else if (L == 'D' || L == 'I') d = (prev == L) ? -sc.ge : -sc.go;
+        acc[i + 1] = acc[i] + d;
+        prev = L;
+    }
+}
+
+// my_special_DP: join the clipped sg_qe_de result of (q1, ref) with the clipped sg_qb_db result of (q2, ref)
+inline bool merge_special(const SgResult &r1, const SgResult &r2, size_t n_ref, size_t nq1, size_t nq2, const Scoring &sc, std::string &out)
+{
+    const int64_t gap = r2.beg_ref - r1.end_ref - 1;
+    if (gap > 0) {
+        const size_t h1 = (size_t)count_of(r1.cig, 0, r1.cig.size(), "H");
+        const size_t h2 = (size_t)count_of(r2.cig, 0, r2.cig.size(), "H");
+        out.assign(r1.cig, 0, r1.cig.size() - h1);
+        out.append((size_t)gap, 'H');
+        out.append(r2.cig, h2, std::string::npos);
+        return true;
+    }
+    std::string a1, a2;
+    if (!aligned_columns(r1.cig, r2.cig, n_ref, nq1, nq2, a1, a2)) return false;
+    std::vector<int64_t> left, right;
+    prefix_scores(a1, sc, left);
+    std::string a2r(a2.rbegin(), a2.rend());
+    prefix_scores(a2r, sc, right);  // right[x] = score of the last x columns of a2
+    const size_t L = a1.size();
+    if (a2.size() != L) return false;
+    size_t cut = 0;
+    int64_t best = 0;
+    for (size_t x = 0; x <= L; ++x) {
+        const int64_t v = left[x] + right[L - x];
+        if (x == 0 || v > best) { best = v; cut = x; }
+    }
+    const int64_t n_s1 = (int64_t)(L - cut) - count_of(a1, cut, L, "DNHO");
+    const int64_t n_s2 = (int64_t)cut - count_of(a2, 0, cut, "DNHO");
+    out.clear();
+    for (size_t x = 0; x < cut; ++x) if (a1[x] != 'N' && a1[x] != 'O') out.push_back(a1[x]);
+    out.append((size_t)(n_s1 + n_s2), 'S');
+    for (size_t x = cut; x < L; ++x) if (a2[x] != 'N' && a2[x] != 'O') out.push_back(a2[x]);
+    return true;
+}
+
+// get_aligned_ref_seq_offset / get_aligned_query_seq_offset: fixed-point on the tail of the column string
+inline int64_t aligned_offset(const std::string &cig, int64_t off, const char *letters)
+{
+    if (off == 0) return 0;
+    const int64_t n = (int64_t)cig.size();
+    auto tail_count = [&](int64_t a) { return count_of(cig, (size_t)(a >= n ? 0 : n - a), (size_t)n, letters); };
+    int64_t a = off, prev = 0, cnt = tail_count(a);
+    while (off != a - cnt) {
+        a += cnt - prev;
+        prev = cnt;
+        cnt = tail_count(a);
+    }
+    return a;
+}
+
+// Python slice cig[-a:-b] (b == 0 means "to the end"); negative starts clamp at 0
+inline int64_t count_dh_tail(const std::string &cig, int64_t a, int64_t b)
+{
+    const int64_t n = (int64_t)cig.size();
+    int64_t from = n - a, to = n - b;
+    if (from < 0) from = 0;
+    if (to < 0) to = 0;
+    if (to <= from) return 0;
+    return count_of(cig, (size_t)from, (size_t)to, "DH");
+}
+
+inline int64_t rotate_to_ref0(std::string &cig, int64_t ref_off, int64_t q_off)
+{
+    const int64_t a_r = aligned_offset(cig, ref_off, "IS");
+    const int64_t a_q = aligned_offset(cig, q_off, "DH");
+    const int64_t diff = a_q - a_r;
+    int64_t new_off;
+    if (a_q > a_r) new_off = diff - count_dh_tail(cig, a_q, a_r);
+    else if (a_q != 0) new_off = diff + count_dh_tail(cig, a_r, a_q);
+    else if (a_r != 0) new_off = diff + count_dh_tail(cig, a_r, 0);
+    else new_off = 0;
+    const int64_t n = (int64_t)cig.size();
+    if (a_r > 0) {
+        const size_t from = (size_t)(a_r >= n ? 0 : n - a_r);  // cig[-a_r:] + cig[:-a_r]
+        std::string rot = cig.substr(from) + cig.substr(0, from);
+        cig.swap(rot);
+    }
+    return new_off;
+}
+
+inline int64_t cigar_score(const std::string &cig, const Scoring &sc)
+{
+    int64_t s = 0;
+    char prev = 0;
+    for (char L : cig) {
+        if (L == '=') s += sc.ma;
+        else if (L == 'X') s += sc.mi;
+        else if (L == 'D' || L == 'I') s -= (prev == L) ? sc.ge : sc.go;
+        prev = L;
+    }
+    return s;
+}
+
+}  // namespace smx

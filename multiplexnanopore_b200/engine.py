@@ -186,3 +186,81 @@ class Engine:
         out = (ctypes.c_double * 3)()
         self._check(self._lib.smx_measure_int_peak(self._h, iters, out), "smx_measure_int_peak")
         return {"viaddmax_gops": out[0], "vimax3_gops": out[1], "iadd_lop_gops": out[2]}
+
+
+@dataclass
+class PipelineResult:
+    """Output of the alignment stage for P pairs x 2 strands, index = 2 * pair + strand."""
+    score: np.ndarray                  # int32[2P]   MyResult.score (0 for empty results)
+    new_query_seq_offset: np.ndarray   # int32[2P]   INT32_MIN encodes None
+    status: np.ndarray                 # uint8[2P]   0 aligned, 1 empty MyResult(), 2 reference would raise
+    cigar_off: np.ndarray              # int64[2P+1]
+    cigar_rle: np.ndarray              # uint32[total]
+    stats: dict
+
+    _OPS = {1: "I", 2: "D", 4: "S", 5: "H", 7: "=", 8: "X"}
+
+    def runs(self, i: int) -> np.ndarray:
+        return self.cigar_rle[self.cigar_off[i]: self.cigar_off[i + 1]]
+
+    def cigar_string(self, i: int) -> str:
+        """RLE text as MyResult.cigar renders it (ref_query_alignment.py:449-451)."""
+        return "".join(f"{int(x) >> 4}{self._OPS[int(x) & 15]}" for x in self.runs(i))
+
+    def my_cigar(self, i: int) -> str:
+        r = self.runs(i)
+        if r.size == 0:
+            return ""
+        lut = np.zeros(16, dtype="S1")
+        for k, v in self._OPS.items():
+            lut[k] = v.encode()
+        return np.repeat(lut[r & 15], r >> 4).tobytes().decode("ascii")
+
+    def offset(self, i: int):
+        v = int(self.new_query_seq_offset[i])
+        return None if v == -2147483648 else v
+
+
+_STAT_KEYS = ("t_total", "t_pool", "t_scan", "t_select", "t_chain", "t_dp", "t_stitch", "gpu_scan_ms", "gpu_select_ms",
+              "gpu_dp_ms", "scan_cells", "dp_cells", "n_dp_problems", "n_host_redecisions", "n_failed", "kernel_launches",
+              "n_pair_strands")
+
+
+def _pack(seqs):
+    enc = [s.encode("ascii") if isinstance(s, str) else bytes(s) for s in seqs]
+    lens = np.array([len(e) for e in enc], dtype=np.int32)
+    offs = np.zeros(len(enc), dtype=np.int64)
+    if len(enc) > 1:
+        offs[1:] = np.cumsum(lens[:-1], dtype=np.int64)
+    return np.frombuffer(b"".join(enc), dtype=np.uint8), offs, lens
+
+
+def pipeline_run(self, refs, queries, sigmas, open_: int, extend: int, match: int, mismatch: int, topology: int,
+                 omit_too_long: bool, pairs=None, n_threads: int = 0) -> PipelineResult:
+    """A1: scan -> select -> chain -> DP -> stitch for every (query, reference) pair and both strands.
+    refs/queries: upper-case str (or bytes); sigmas: float64 per reference; pairs: optional int array [P, 2]
+    of (ref_idx, query_idx); default = all combinations, query-major."""
+    rb, ro, rl = _pack(refs)
+    qb, qo, ql = _pack(queries)
+    sig = np.ascontiguousarray(sigmas, dtype=np.float64)
+    if sig.size != len(refs):
+        raise ValueError("one sigma per reference")
+    if pairs is not None:
+        pairs = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
+        pr = np.ascontiguousarray(pairs[:, 0]); pq = np.ascontiguousarray(pairs[:, 1]); n_pairs = pairs.shape[0]
+    else:
+        pr = pq = None; n_pairs = len(refs) * len(queries)
+    total = ctypes.c_int64(0)
+    self._check(self._lib.smx_pipeline_run(self._h, _ptr(rb), _ptr(ro), _ptr(rl), len(refs), _ptr(sig), _ptr(qb), _ptr(qo), _ptr(ql),
+                                           len(queries), _ptr(pr), _ptr(pq), n_pairs, open_, extend, match, mismatch, int(topology),
+                                           int(bool(omit_too_long)), int(n_threads), ctypes.byref(total)), "smx_pipeline_run")
+    n = 2 * n_pairs
+    score = np.empty(n, np.int32); off = np.empty(n, np.int32); status = np.empty(n, np.uint8)
+    coff = np.zeros(n + 1, np.int64); rle = np.empty(max(int(total.value), 1), np.uint32)
+    self._check(self._lib.smx_pipeline_fetch(self._h, _ptr(score), _ptr(off), _ptr(status), _ptr(coff), _ptr(rle), rle.size), "smx_pipeline_fetch")
+    st = (ctypes.c_double * len(_STAT_KEYS))()
+    self._check(self._lib.smx_pipeline_stats(self._h, st, len(_STAT_KEYS)), "smx_pipeline_stats")
+    return PipelineResult(score, off, status, coff, rle[: int(total.value)], dict(zip(_STAT_KEYS, list(st))))
+
+
+Engine.pipeline_run = pipeline_run

@@ -1,0 +1,156 @@
+"""Host-side mirror of the reference interface for the alignment path (same names, argument meaning
+and error behaviour), backed by the CUDA engine:
+
+  execute_alignment_core(ref_seq_list, my_fastq, param_dict)   post_analysis/post_analysis_core.py:56-65
+  set_distance_matrix(ref_seq_list, param_dict)                 pre_survey/pre_survey_core.py:237-245
+  calc_distance(ref_seq_1, ref_seq_2, param_dict)               pre_survey/pre_survey_core.py:251-271
+  MyResult                                                      modules/ref_query_alignment.py:425-529
+
+A maintainer switches the reference over by replacing the bodies of those two driver functions with
+calls into this module; kwargs, result_dict layout and output files stay unchanged.
+"""
+from __future__ import annotations
+
+import re
+from itertools import combinations
+
+import numpy as np
+from scipy import stats
+
+from .engine import Engine
+
+PERCENTILE_FACTOR = 0.1  # MyOptimizedAligner.percentile_factor (ref_query_alignment.py:189)
+_RUNS = re.compile(r"((.)\2*)")
+
+
+class MyResult:
+    """Same public fields as the reference's MyResult: my_cigar, score, new_query_seq_offset."""
+    __slots__ = ("_src", "_idx", "_my_cigar", "score", "new_query_seq_offset")
+
+    def __init__(self, src=None, idx=0):
+        self._src, self._idx, self._my_cigar = src, idx, None
+        if src is None:
+            self._my_cigar, self.score, self.new_query_seq_offset = "", 0, None
+        else:
+            self.score = int(src.score[idx])
+            self.new_query_seq_offset = src.offset(idx)
+
+    @property
+    def my_cigar(self) -> str:
+        if self._my_cigar is None:
+            self._my_cigar = self._src.my_cigar(self._idx)
+        return self._my_cigar
+
+    @my_cigar.setter
+    def my_cigar(self, v):
+        self._my_cigar = v
+
+    @property
+    def cigar(self) -> str:
+        if self._src is not None and self._my_cigar is None:
+            return self._src.cigar_string(self._idx)
+        return "".join(f"{len(run)}{L}" for run, L in _RUNS.findall(self.my_cigar))
+
+    def __len__(self):
+        return len(self.my_cigar)
+
+    def to_dict(self):
+        return {"cigar": self.cigar, "score": self.score, "new_query_seq_offset": self.new_query_seq_offset}
+
+    def calc_levenshtein_distance(self):
+        return len(self.my_cigar) - self.my_cigar.count("=")
+
+
+def _seq_of(x) -> str:
+    s = x if isinstance(x, str) else (getattr(x, "_seq", None) or str(x))
+    return s.upper()  # MySeq upper-cases on construction (my_classes.py:271-272)
+
+
+def _check_params(p):
+    for k in ("gap_open_penalty", "gap_extend_penalty", "match_score", "mismatch_score", "topology_of_dna"):
+        if k not in p:
+            raise Exception(f"missing key in `param_dict`: {k}")
+    if p["topology_of_dna"] not in (0, 1):
+        raise Exception(f"unknown topology_of_dna: {p['topology_of_dna']}")
+
+
+def sigma_for(n_ref: int) -> float:
+    return float(stats.norm.ppf(1 - 1 / n_ref * PERCENTILE_FACTOR, loc=0, scale=1))  # :200-201
+
+
+_default_engine = None
+
+
+def default_engine() -> Engine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(0)
+    return _default_engine
+
+
+def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None, n_threads=0):
+    _check_params(param_dict)
+    eng = engine or default_engine()
+    refs = [_seq_of(r) for r in refs]
+    queries = [_seq_of(q) for q in queries]
+    sig = [sigma_for(len(r)) for r in refs]
+    return eng.pipeline_run(refs, queries, sig, param_dict["gap_open_penalty"], param_dict["gap_extend_penalty"],
+                            param_dict["match_score"], param_dict["mismatch_score"], param_dict["topology_of_dna"],
+                            omit_too_long, pairs=pairs, n_threads=n_threads)
+
+
+def _raise_failed(res):
+    bad = np.where(res.status == 2)[0]
+    if bad.size:
+        raise AssertionError(f"alignment failed an internal assertion of the reference algorithm on pair-strand(s) {bad[:8].tolist()}")
+
+
+def execute_alignment_core(ref_seq_list, my_fastq, param_dict, engine=None):
+    """result_dict[query_id] = [MyResult] * (2 * N_ref), order [ref0, ref0_rc, ref1, ...] (:63-65, :85)."""
+    ids = list(my_fastq.keys())
+    reads = [my_fastq[i][0] for i in ids]
+    res = align_all(ref_seq_list, reads, param_dict, omit_too_long=True, engine=engine,
+                    n_threads=0)
+    _raise_failed(res)
+    n2 = 2 * len(ref_seq_list)
+    out = {}
+    for qi, qid in enumerate(ids):
+        row = []
+        for j in range(n2):
+            i = qi * n2 + j
+            row.append(MyResult(res, i) if res.status[i] == 0 else MyResult())
+        out[qid] = row
+    return out
+
+
+def calc_distance_from(res, p, len_i, len_j) -> int:
+    s0, s1 = int(res.score[2 * p]), int(res.score[2 * p + 1])
+    if s0 <= 0 and s1 <= 0:
+        return len_i + len_j
+    i = 2 * p if s0 >= s1 else 2 * p + 1
+    r = res.runs(i)
+    total = int((r >> 4).sum())
+    eq = int((r >> 4)[(r & 15) == 7].sum())
+    return total - eq
+
+
+def calc_distance(ref_seq_1, ref_seq_2, param_dict, engine=None) -> int:
+    res = align_all([ref_seq_1], [ref_seq_2], param_dict, omit_too_long=False, engine=engine)
+    _raise_failed(res)
+    return calc_distance_from(res, 0, len(_seq_of(ref_seq_1)), len(_seq_of(ref_seq_2)))
+
+
+def set_distance_matrix(ref_seq_list, param_dict, engine=None) -> np.ndarray:
+    """all i < j pairs: reference = plasmid i, query = plasmid j and its reverse complement."""
+    seqs = [_seq_of(r) for r in ref_seq_list]
+    n = len(seqs)
+    pairs = np.array(list(combinations(range(n), 2)), dtype=np.int32).reshape(-1, 2)
+    dm = np.zeros((n, n), dtype=int)
+    if len(pairs) == 0:
+        return dm
+    res = align_all(seqs, seqs, param_dict, omit_too_long=False, pairs=pairs, engine=engine)
+    _raise_failed(res)
+    for p, (i, j) in enumerate(pairs):
+        dm[i, j] = dm[j, i] = calc_distance_from(res, p, len(seqs[i]), len(seqs[j]))
+    assert (dm >= 0).all()
+    return dm

@@ -77,6 +77,14 @@ def main():
     reads, _ = synth.reads_for(rng, lin, 10, topology=1)
     cases.append(run_case(ns, "c4_small_linear", lin, reads, dict(base, topology_of_dna=1)))
 
+    # the seeds of tests/test_pipeline_parity.py::test_engine_matches_port_on_fresh_inputs: seed 31 holds a
+    # my_special_DP overlap merge whose arg-max is a tie (first maximum wins, ref_query_alignment.py:136)
+    for topo, seed in ((0, 31), (0, 32), (1, 33)):
+        rng = np.random.default_rng(seed)
+        pl = synth.plasmid_set(rng, 4, 1200, 2600, backbone=600)
+        rd, _ = synth.reads_for(rng, pl, 10, topology=topo, frac_full=0.6, frac_partial=0.25, homopolymer_rate=1.0)
+        cases.append(run_case(ns, f"fresh_{seed}_topology{topo}", pl, rd, dict(base, topology_of_dna=topo)))
+
     # pre_survey distances: demo maps (7 of the 15 pairs are the legacy known answers) + a synthetic family
     dist = {"demo_names": list(maps.keys()), "demo": {}, "family_maps": [], "family": {}}
     t0 = time.time()

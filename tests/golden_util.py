@@ -20,4 +20,5 @@ def case(name):
 
 
 CASE_NAMES = ["c1_demo_circular", "c2_small_circular", "c2_small_circular_scoring2",
-              "c2_small_circular_homopolymers", "c4_small_linear"]
+              "c2_small_circular_homopolymers", "c4_small_linear",
+              "fresh_31_topology0", "fresh_32_topology0", "fresh_33_topology1"]
