@@ -24,6 +24,7 @@ _SIGNATURES = {
                                   c_int32, c_int32, c_int32, c_int32]),
     "smx_align_run": (c_int, [c_void_p, POINTER(c_int64)]),
     "smx_align_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
+    "smx_align_kernel_ms": (c_int, [c_void_p, c_void_p, c_void_p]),
     "smx_debug_copy_trace": (c_int, [c_void_p, c_void_p, c_int64]),
     "smx_last_run_ms": (c_float, [c_void_p]),
     "smx_align_cells": (c_int64, [c_void_p]),

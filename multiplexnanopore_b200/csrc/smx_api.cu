@@ -40,6 +40,13 @@ struct smx_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
     int last_launches = 0;
+    // per-kernel timing of the last smx_align_run: [0..7] forward classes (kshift*2 + local), [8] traceback, [9] compaction
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_tag;
+    size_t ev_used = 0;
+    double kernel_ms[10] = {0};
+    int kernel_launches[10] = {0};
+    int64_t class_cells[8] = {0};
 
     DevBuf pool;
     int64_t pool_len = 0;
@@ -115,6 +122,22 @@ static void release(DevBuf &b)
 
 static void smx_pipeline_free(smx_handle *h);
 
+// records an event after the launch just issued and tags the interval that ends here
+static int mark(smx_handle *h, int tag)
+{
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return fail(h, -2, "cudaEventCreate failed");
+        h->ev_pool.push_back(e);
+        h->ev_tag.push_back(0);
+    }
+    h->ev_tag[h->ev_used] = tag;
+    cudaError_t e = cudaEventRecord(h->ev_pool[h->ev_used], h->stream);
+    if (e != cudaSuccess) return fail(h, -2, "cudaEventRecord failed: %s", cudaGetErrorString(e));
+    h->ev_used++;
+    return 0;
+}
+
 extern "C" int smx_version(void) { return 100; }
 
 extern "C" const char *smx_last_error(const smx_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -161,6 +184,7 @@ extern "C" void smx_destroy(smx_handle *h)
                       &h->d_sel_pairs, &h->d_sel_out, &h->d_regions};
     smx_pipeline_free(h);
     for (DevBuf *b : bufs) release(*b);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->owns_stream) cudaStreamDestroy(h->stream);
@@ -213,6 +237,7 @@ extern "C" int smx_align_prepare(smx_handle *h, const int64_t *s1_off, const int
     h->sc = SmxScoring{open, extend, match, mismatch};
     h->probs.resize((size_t)n);
     h->cells = 0;
+    for (int c = 0; c < 8; ++c) h->class_cells[c] = 0;
     h->nmax = 1;
     int64_t runs_off = 0;
     for (int p = 0; p < n; ++p) {
@@ -227,6 +252,7 @@ extern "C" int smx_align_prepare(smx_handle *h, const int64_t *s1_off, const int
         SmxProblem &q = h->probs[(size_t)p];
         q.s1_off = s1_off[p]; q.s2_off = s2_off[p]; q.m = m; q.n = nn; q.mode = mode[p];
         q.kshift = pick_kshift(m);
+        h->class_cells[q.kshift * 2 + (mode[p] == SMX_MODE_SW ? 1 : 0)] += (int64_t)m * nn;
         q.trace_off = 0;
         q.cigar_off = runs_off;
         runs_off += (int64_t)m + nn + 2;
@@ -318,7 +344,7 @@ static int launch_forward(smx_handle *h, const Chunk &c, int cls, int chunk_idx,
     smx_dp_forward<K, LOCAL><<<blocks, 128, 0, h->stream>>>(a);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
-    return 0;
+    return mark(h, cls);
 }
 
 extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
@@ -336,6 +362,9 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
     }
     SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     SMX_CUDA(h, cudaMemsetAsync(h->d_tickets.p, 0, sizeof(int32_t) * 8 * h->chunks.size(), h->stream));
+    h->ev_used = 0;
+    for (int c = 0; c < 10; ++c) { h->kernel_ms[c] = 0.0; h->kernel_launches[c] = 0; }
+    if (int rc = mark(h, -1)) return rc;
     for (size_t ci = 0; ci < h->chunks.size(); ++ci) {
         const Chunk &c = h->chunks[ci];
         int rc = 0;
@@ -358,6 +387,7 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
         smx_traceback<<<(c.count + 127) / 128, 128, 0, h->stream>>>(t);
         SMX_CUDA(h, cudaGetLastError());
         h->last_launches++;
+        if (int rc2 = mark(h, 8)) return rc2;
     }
     SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     // results header to host: run counts -> dense offsets -> compaction
@@ -378,7 +408,14 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
                                                                         (uint32_t *)h->d_dense.p, h->n);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
+    if (int rc = mark(h, 9)) return rc;
     SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (size_t i = 1; i < h->ev_used; ++i) {
+        if (h->ev_tag[i] < 0) continue;
+        float ms = 0.f;
+        // the compaction interval also spans the small header copy that precedes it
+        if (cudaEventElapsedTime(&ms, h->ev_pool[i - 1], h->ev_pool[i]) == cudaSuccess) { h->kernel_ms[h->ev_tag[i]] += ms; h->kernel_launches[h->ev_tag[i]]++; }
+    }
     if (total_runs) *total_runs = acc;
     return 0;
 }
@@ -413,6 +450,14 @@ extern "C" int smx_debug_copy_trace(smx_handle *h, uint8_t *dst, int64_t nbytes)
     if ((size_t)nbytes > h->d_trace.cap) return fail(h, -1, "smx_debug_copy_trace: arena holds %zu bytes", h->d_trace.cap);
     SMX_CUDA(h, cudaSetDevice(h->device));
     SMX_CUDA(h, cudaMemcpy(dst, h->d_trace.p, (size_t)nbytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int smx_align_kernel_ms(const smx_handle *h, double *ms10, int64_t *cells8)
+{
+    if (!h) return -1;
+    if (ms10) for (int c = 0; c < 10; ++c) ms10[c] = h->kernel_ms[c];
+    if (cells8) for (int c = 0; c < 8; ++c) cells8[c] = h->class_cells[c];
     return 0;
 }
 
@@ -864,6 +909,9 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         int64_t truns = 0;
         if (int rc = smx_align_run(h, &truns)) return rc;
         st.gpu_dp_ms = h->last_ms; st.dp_cells = h->cells; st.launches += h->last_launches;
+        for (int c = 0; c < 10; ++c) st.dp_kernel_ms[c] = h->kernel_ms[c];
+        for (int c = 0; c < 8; ++c) st.dp_class_cells[c] = h->class_cells[c];
+        for (int c = 0; c < 10; ++c) st.dp_kernel_launches[c] = h->kernel_launches[c];
         cg.resize((size_t)std::max<int64_t>(truns, 1));
         if (int rc = smx_align_fetch(h, nullptr, nullptr, nullptr, nullptr, nullptr, cg_off.data(), cg.data(), (int64_t)cg.size())) return rc;
     }
@@ -940,7 +988,13 @@ extern "C" int smx_pipeline_stats(smx_handle *h, double *out, int32_t n)
                         st.gpu_dp_ms, (double)st.scan_cells, (double)st.dp_cells, (double)st.n_dp, (double)st.n_host_redo, (double)st.n_failed,
                         (double)st.launches, (double)st.ps.size()};
     const int m = (int)(sizeof(v) / sizeof(v[0]));
-    for (int i = 0; i < n; ++i) out[i] = i < m ? v[i] : 0.0;
+    for (int i = 0; i < n; ++i) {
+        if (i < m) out[i] = v[i];
+        else if (i < m + 10) out[i] = st.dp_kernel_ms[i - m];
+        else if (i < m + 18) out[i] = (double)st.dp_class_cells[i - m - 10];
+        else if (i < m + 28) out[i] = (double)st.dp_kernel_launches[i - m - 18];
+        else out[i] = 0.0;
+    }
     return 0;
 }
 

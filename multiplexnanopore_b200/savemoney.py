@@ -88,15 +88,36 @@ def default_engine() -> Engine:
     return _default_engine
 
 
-def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None, n_threads=0):
+def _merge(parts):
+    from .engine import PipelineResult
+    if len(parts) == 1:
+        return parts[0]
+    offs = [parts[0].cigar_off]
+    base = int(parts[0].cigar_off[-1])
+    for p in parts[1:]:
+        offs.append(p.cigar_off[1:] + base)
+        base += int(p.cigar_off[-1])
+    stats = {k: sum(p.stats[k] for p in parts) for k in parts[0].stats}
+    return PipelineResult(np.concatenate([p.score for p in parts]), np.concatenate([p.new_query_seq_offset for p in parts]),
+                          np.concatenate([p.status for p in parts]), np.concatenate(offs),
+                          np.concatenate([p.cigar_rle for p in parts]), stats)
+
+
+def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None, n_threads=0, batch_queries=2000):
+    """The alignment stage for every (query, reference) pair and both strands (or the explicit `pairs`).
+    Queries are processed in batches of `batch_queries` so that device workspaces stay bounded."""
     _check_params(param_dict)
     eng = engine or default_engine()
     refs = [_seq_of(r) for r in refs]
     queries = [_seq_of(q) for q in queries]
     sig = [sigma_for(len(r)) for r in refs]
-    return eng.pipeline_run(refs, queries, sig, param_dict["gap_open_penalty"], param_dict["gap_extend_penalty"],
-                            param_dict["match_score"], param_dict["mismatch_score"], param_dict["topology_of_dna"],
-                            omit_too_long, pairs=pairs, n_threads=n_threads)
+    args = (param_dict["gap_open_penalty"], param_dict["gap_extend_penalty"], param_dict["match_score"],
+            param_dict["mismatch_score"], param_dict["topology_of_dna"], omit_too_long)
+    if pairs is not None or len(queries) <= batch_queries:
+        return eng.pipeline_run(refs, queries, sig, *args, pairs=pairs, n_threads=n_threads)
+    parts = [eng.pipeline_run(refs, queries[b:b + batch_queries], sig, *args, n_threads=n_threads)
+             for b in range(0, len(queries), batch_queries)]
+    return _merge(parts)
 
 
 def _raise_failed(res):
