@@ -24,7 +24,7 @@ struct DevBuf {
 
 struct Chunk {
     int first = 0, count = 0;            // range in the size-sorted order
-    int cls_first[8] = {0}, cls_count[8] = {0};  // per kernel class (kshift*2 + local) ranges inside order_cls
+    int cls_first[10] = {0}, cls_count[10] = {0};  // per kernel class ranges inside order_cls (see problem_class)
     size_t trace_bytes = 0;
 };
 
@@ -40,13 +40,13 @@ struct smx_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
     int last_launches = 0;
-    // per-kernel timing of the last smx_align_run: [0..7] forward classes (kshift*2 + local), [8] traceback, [9] compaction
+    // per-kernel timing of the last smx_align_run: [0..9] forward classes (problem_class), [10] traceback, [11] compaction
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_tag;
     size_t ev_used = 0;
-    double kernel_ms[10] = {0};
-    int kernel_launches[10] = {0};
-    int64_t class_cells[8] = {0};
+    double kernel_ms[12] = {0};
+    int kernel_launches[12] = {0};
+    int64_t class_cells[10] = {0};
 
     DevBuf pool;
     int64_t pool_len = 0;
@@ -214,12 +214,23 @@ extern "C" int smx_pool_upload(smx_handle *h, const uint8_t *seqs, int64_t n)
 // ------------------------------------------------------------------------------------------------
 // A8: batched DP
 // ------------------------------------------------------------------------------------------------
+// kernel class of a problem: kshift * 2 + local for warp-per-problem kernels (K = 1 << kshift rows per
+// lane), 8 + local for the CTA-per-problem (team) kernel that takes every problem of 3 or more bands
+static const int kTeamMinRows = 513;
+static int problem_class(int m, int mode);
 static int pick_kshift(int m)
 {
     if (m > 128) return 3;
     if (m > 64) return 2;
     if (m > 32) return 1;
     return 0;
+}
+
+static int problem_class(int m, int mode)
+{
+    const int local = mode == SMX_MODE_SW ? 1 : 0;
+    if (m >= kTeamMinRows) return 8 + local;
+    return pick_kshift(m) * 2 + local;
 }
 
 extern "C" int smx_align_prepare(smx_handle *h, const int64_t *s1_off, const int32_t *s1_len, const int64_t *s2_off,
@@ -237,7 +248,7 @@ extern "C" int smx_align_prepare(smx_handle *h, const int64_t *s1_off, const int
     h->sc = SmxScoring{open, extend, match, mismatch};
     h->probs.resize((size_t)n);
     h->cells = 0;
-    for (int c = 0; c < 8; ++c) h->class_cells[c] = 0;
+    for (int c = 0; c < 10; ++c) h->class_cells[c] = 0;
     h->nmax = 1;
     int64_t runs_off = 0;
     for (int p = 0; p < n; ++p) {
@@ -252,7 +263,7 @@ extern "C" int smx_align_prepare(smx_handle *h, const int64_t *s1_off, const int
         SmxProblem &q = h->probs[(size_t)p];
         q.s1_off = s1_off[p]; q.s2_off = s2_off[p]; q.m = m; q.n = nn; q.mode = mode[p];
         q.kshift = pick_kshift(m);
-        h->class_cells[q.kshift * 2 + (mode[p] == SMX_MODE_SW ? 1 : 0)] += (int64_t)m * nn;
+        h->class_cells[problem_class(m, mode[p])] += (int64_t)m * nn;
         q.trace_off = 0;
         q.cigar_off = runs_off;
         runs_off += (int64_t)m + nn + 2;
@@ -288,11 +299,11 @@ extern "C" int smx_align_prepare(smx_handle *h, const int64_t *s1_off, const int
         h->max_chunk_trace = std::max(h->max_chunk_trace, bytes);
         // class lists (stable: keeps largest-first inside each class)
         int w = c.first;
-        for (int cls = 7; cls >= 0; --cls) {
+        for (int cls = 9; cls >= 0; --cls) {
             c.cls_first[cls] = w;
             for (int x = c.first; x < c.first + c.count; ++x) {
                 const SmxProblem &q = h->probs[(size_t)order[x]];
-                const int qc = q.kshift * 2 + (q.mode == SMX_MODE_SW ? 1 : 0);
+                const int qc = problem_class(q.m, q.mode);
                 if (qc == cls) h->order_cls[(size_t)w++] = order[x];
             }
             c.cls_count[cls] = w - c.cls_first[cls];
@@ -307,7 +318,7 @@ extern "C" int smx_align_prepare(smx_handle *h, const int64_t *s1_off, const int
     if (int rc = ensure(h, h->d_trace, h->max_chunk_trace + 256)) return rc;
     if (int rc = ensure(h, h->d_runs, sizeof(uint32_t) * (size_t)h->runs_scratch)) return rc;
     if (int rc = ensure(h, h->d_dense_off, sizeof(int64_t) * ((size_t)n + 1))) return rc;
-    if (int rc = ensure(h, h->d_tickets, sizeof(int32_t) * 8 * h->chunks.size())) return rc;
+    if (int rc = ensure(h, h->d_tickets, sizeof(int32_t) * 10 * h->chunks.size())) return rc;
     SMX_CUDA(h, cudaMemcpyAsync(h->d_probs.p, h->probs.data(), sizeof(SmxProblem) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     SMX_CUDA(h, cudaMemcpyAsync(h->d_order_cls.p, h->order_cls.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     SMX_CUDA(h, cudaMemcpyAsync(h->d_order_all.p, h->order_all.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
@@ -316,32 +327,32 @@ extern "C" int smx_align_prepare(smx_handle *h, const int64_t *s1_off, const int
     return 0;
 }
 
-template <int K, bool LOCAL>
-static int launch_forward(smx_handle *h, const Chunk &c, int cls, int chunk_idx, int blocks_per_sm_hint)
+template <int K, bool LOCAL, bool TEAM>
+static int launch_forward(smx_handle *h, const Chunk &c, int cls, int chunk_idx)
 {
     const int count = c.cls_count[cls];
     if (count == 0) return 0;
+    const int threads = TEAM ? SMX_TEAM_WARPS * 32 : 128;
     int occ = 0;
-    SMX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, smx_dp_forward<K, LOCAL>, 128, 0));
+    SMX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, smx_dp_forward<K, LOCAL, TEAM>, threads, 0));
     if (occ < 1) occ = 1;
-    (void)blocks_per_sm_hint;
-    const int warps_per_block = 4;
-    int blocks = std::min(h->sm_count * occ, (count + warps_per_block - 1) / warps_per_block);
+    const int per_block = TEAM ? 1 : threads / 32;  // problems in flight per CTA
+    int blocks = std::min(h->sm_count * occ, (count + per_block - 1) / per_block);
     if (blocks < 1) blocks = 1;
-    const size_t line_bytes = sizeof(int2) * 2 * (size_t)h->nmax * (size_t)blocks * warps_per_block;
-    if (int rc = ensure(h, h->d_boundary, line_bytes)) return rc;
+    const size_t workers = TEAM ? (size_t)blocks : (size_t)blocks * (threads / 32);
+    if (int rc = ensure(h, h->d_boundary, sizeof(int2) * 2 * (size_t)h->nmax * workers)) return rc;
     SmxFwdArgs a;
     a.pool = (const uint8_t *)h->pool.p;
     a.probs = (const SmxProblem *)h->d_probs.p;
     a.order = (const int32_t *)h->d_order_cls.p + c.cls_first[cls];
     a.n_order = count;
-    a.ticket = (int32_t *)h->d_tickets.p + chunk_idx * 8 + cls;
+    a.ticket = (int32_t *)h->d_tickets.p + chunk_idx * 10 + cls;
     a.trace = (uint8_t *)h->d_trace.p;
     a.boundary = (int2 *)h->d_boundary.p;
     a.nmax = h->nmax;
     a.results = (SmxResult *)h->d_results.p;
     a.sc = h->sc;
-    smx_dp_forward<K, LOCAL><<<blocks, 128, 0, h->stream>>>(a);
+    smx_dp_forward<K, LOCAL, TEAM><<<blocks, threads, 0, h->stream>>>(a);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
     return mark(h, cls);
@@ -357,25 +368,27 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
     SMX_CUDA(h, cudaSetDevice(h->device));
     // boundary lines must be sized before the timed region (no allocation between launches)
     {
-        const size_t line_bytes = sizeof(int2) * 2 * (size_t)h->nmax * (size_t)h->sm_count * 16 * 4;
+        const size_t line_bytes = sizeof(int2) * 2 * (size_t)h->nmax * (size_t)h->sm_count * 16 * 4;  // >= workers of any class
         if (int rc = ensure(h, h->d_boundary, line_bytes)) return rc;
     }
     SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    SMX_CUDA(h, cudaMemsetAsync(h->d_tickets.p, 0, sizeof(int32_t) * 8 * h->chunks.size(), h->stream));
+    SMX_CUDA(h, cudaMemsetAsync(h->d_tickets.p, 0, sizeof(int32_t) * 10 * h->chunks.size(), h->stream));
     h->ev_used = 0;
-    for (int c = 0; c < 10; ++c) { h->kernel_ms[c] = 0.0; h->kernel_launches[c] = 0; }
+    for (int c = 0; c < 12; ++c) { h->kernel_ms[c] = 0.0; h->kernel_launches[c] = 0; }
     if (int rc = mark(h, -1)) return rc;
     for (size_t ci = 0; ci < h->chunks.size(); ++ci) {
         const Chunk &c = h->chunks[ci];
         int rc = 0;
-        if ((rc = launch_forward<8, false>(h, c, 6, (int)ci, 0))) return rc;
-        if ((rc = launch_forward<8, true>(h, c, 7, (int)ci, 0))) return rc;
-        if ((rc = launch_forward<4, false>(h, c, 4, (int)ci, 0))) return rc;
-        if ((rc = launch_forward<4, true>(h, c, 5, (int)ci, 0))) return rc;
-        if ((rc = launch_forward<2, false>(h, c, 2, (int)ci, 0))) return rc;
-        if ((rc = launch_forward<2, true>(h, c, 3, (int)ci, 0))) return rc;
-        if ((rc = launch_forward<1, false>(h, c, 0, (int)ci, 0))) return rc;
-        if ((rc = launch_forward<1, true>(h, c, 1, (int)ci, 0))) return rc;
+        if ((rc = launch_forward<8, false, true>(h, c, 8, (int)ci))) return rc;
+        if ((rc = launch_forward<8, true, true>(h, c, 9, (int)ci))) return rc;
+        if ((rc = launch_forward<8, false, false>(h, c, 6, (int)ci))) return rc;
+        if ((rc = launch_forward<8, true, false>(h, c, 7, (int)ci))) return rc;
+        if ((rc = launch_forward<4, false, false>(h, c, 4, (int)ci))) return rc;
+        if ((rc = launch_forward<4, true, false>(h, c, 5, (int)ci))) return rc;
+        if ((rc = launch_forward<2, false, false>(h, c, 2, (int)ci))) return rc;
+        if ((rc = launch_forward<2, true, false>(h, c, 3, (int)ci))) return rc;
+        if ((rc = launch_forward<1, false, false>(h, c, 0, (int)ci))) return rc;
+        if ((rc = launch_forward<1, true, false>(h, c, 1, (int)ci))) return rc;
         SmxTbArgs t;
         t.pool = (const uint8_t *)h->pool.p;
         t.probs = (const SmxProblem *)h->d_probs.p;
@@ -387,7 +400,7 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
         smx_traceback<<<(c.count + 127) / 128, 128, 0, h->stream>>>(t);
         SMX_CUDA(h, cudaGetLastError());
         h->last_launches++;
-        if (int rc2 = mark(h, 8)) return rc2;
+        if (int rc2 = mark(h, 10)) return rc2;
     }
     SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     // results header to host: run counts -> dense offsets -> compaction
@@ -408,7 +421,7 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
                                                                         (uint32_t *)h->d_dense.p, h->n);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
-    if (int rc = mark(h, 9)) return rc;
+    if (int rc = mark(h, 11)) return rc;
     SMX_CUDA(h, cudaStreamSynchronize(h->stream));
     for (size_t i = 1; i < h->ev_used; ++i) {
         if (h->ev_tag[i] < 0) continue;
@@ -453,11 +466,11 @@ extern "C" int smx_debug_copy_trace(smx_handle *h, uint8_t *dst, int64_t nbytes)
     return 0;
 }
 
-extern "C" int smx_align_kernel_ms(const smx_handle *h, double *ms10, int64_t *cells8)
+extern "C" int smx_align_kernel_ms(const smx_handle *h, double *ms12, int64_t *cells10)
 {
     if (!h) return -1;
-    if (ms10) for (int c = 0; c < 10; ++c) ms10[c] = h->kernel_ms[c];
-    if (cells8) for (int c = 0; c < 8; ++c) cells8[c] = h->class_cells[c];
+    if (ms12) for (int c = 0; c < 12; ++c) ms12[c] = h->kernel_ms[c];
+    if (cells10) for (int c = 0; c < 10; ++c) cells10[c] = h->class_cells[c];
     return 0;
 }
 
@@ -909,9 +922,9 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         int64_t truns = 0;
         if (int rc = smx_align_run(h, &truns)) return rc;
         st.gpu_dp_ms = h->last_ms; st.dp_cells = h->cells; st.launches += h->last_launches;
-        for (int c = 0; c < 10; ++c) st.dp_kernel_ms[c] = h->kernel_ms[c];
-        for (int c = 0; c < 8; ++c) st.dp_class_cells[c] = h->class_cells[c];
-        for (int c = 0; c < 10; ++c) st.dp_kernel_launches[c] = h->kernel_launches[c];
+        for (int c = 0; c < 12; ++c) st.dp_kernel_ms[c] = h->kernel_ms[c];
+        for (int c = 0; c < 10; ++c) st.dp_class_cells[c] = h->class_cells[c];
+        for (int c = 0; c < 12; ++c) st.dp_kernel_launches[c] = h->kernel_launches[c];
         cg.resize((size_t)std::max<int64_t>(truns, 1));
         if (int rc = smx_align_fetch(h, nullptr, nullptr, nullptr, nullptr, nullptr, cg_off.data(), cg.data(), (int64_t)cg.size())) return rc;
     }
@@ -990,9 +1003,9 @@ extern "C" int smx_pipeline_stats(smx_handle *h, double *out, int32_t n)
     const int m = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < n; ++i) {
         if (i < m) out[i] = v[i];
-        else if (i < m + 10) out[i] = st.dp_kernel_ms[i - m];
-        else if (i < m + 18) out[i] = (double)st.dp_class_cells[i - m - 10];
-        else if (i < m + 28) out[i] = (double)st.dp_kernel_launches[i - m - 18];
+        else if (i < m + 12) out[i] = st.dp_kernel_ms[i - m];
+        else if (i < m + 22) out[i] = (double)st.dp_class_cells[i - m - 12];
+        else if (i < m + 34) out[i] = (double)st.dp_kernel_launches[i - m - 22];
         else out[i] = 0.0;
     }
     return 0;

@@ -67,26 +67,45 @@ struct SmxFwdArgs {
     int32_t n_order;
     int32_t *ticket;
     uint8_t *trace;
-    int2 *boundary;  // per warp: 2 lines of nmax (H, F) pairs
+    int2 *boundary;  // per worker (warp, or CTA in team mode): 2 lines of nmax (H, F) pairs
     int32_t nmax;
     SmxResult *results;
     SmxScoring sc;
 };
 
-template <int K, bool LOCAL>
-__global__ void __launch_bounds__(128) smx_dp_forward(const SmxFwdArgs a)
+#define SMX_TEAM_WARPS 8  // warps of a CTA that share one large problem (bands interleaved)
+
+// WORKER = one warp (TEAM == false: a warp owns a problem and walks its bands one after the other) or
+// one CTA of SMX_TEAM_WARPS warps (TEAM == true: band b belongs to warp b % W and runs two 32-column
+// chunks behind band b-1; the (H, F) bottom line goes through L2, progress through shared memory).
+template <int K, bool LOCAL, bool TEAM>
+__global__ void __launch_bounds__(TEAM ? SMX_TEAM_WARPS * 32 : 128) smx_dp_forward(const SmxFwdArgs a)
 {
     typedef typename SmxTraceWord<K>::type TW;
+    constexpr int W = TEAM ? SMX_TEAM_WARPS : 1;
     const int lane = threadIdx.x & 31;
-    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int2 *line0 = a.boundary + (size_t)gwarp * 2 * (size_t)a.nmax;
+    const int wib = threadIdx.x >> 5;  // warp in block
+    const int worker = TEAM ? blockIdx.x : ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    int2 *line0 = a.boundary + (size_t)worker * 2 * (size_t)a.nmax;
     int2 *line1 = line0 + a.nmax;
     const int go = a.sc.go, ge = a.sc.ge;
 
+    __shared__ int s_ticket;
+    __shared__ volatile int s_prog[SMX_TEAM_WARPS];      // band * nchunks + chunks done, per warp
+    __shared__ int s_red[SMX_TEAM_WARPS][6];
+
     for (;;) {
         int ticket = 0;
-        if (lane == 0) ticket = atomicAdd(a.ticket, 1);
-        ticket = __shfl_sync(SMX_FULL_MASK, ticket, 0);
+        if (TEAM) {
+            __syncthreads();  // previous problem fully retired (s_red / s_prog reuse)
+            if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1);
+            if (threadIdx.x < SMX_TEAM_WARPS) s_prog[threadIdx.x] = -1;
+            __syncthreads();
+            ticket = s_ticket;
+        } else {
+            if (lane == 0) ticket = atomicAdd(a.ticket, 1);
+            ticket = __shfl_sync(SMX_FULL_MASK, ticket, 0);
+        }
         if (ticket >= a.n_order) break;
         const int pid = a.order[ticket];
         const SmxProblem pr = a.probs[pid];
@@ -97,16 +116,17 @@ __global__ void __launch_bounds__(128) smx_dp_forward(const SmxFwdArgs a)
         TW *trace = reinterpret_cast<TW *>(a.trace + pr.trace_off);
         const int nbands = (m + 32 * K - 1) / (32 * K);
         const int steps = n + 31;
+        const int nchunks = (steps + 31) >> 5;
 
         // end-cell candidates: last column (rows ascending) then last row (columns ascending)
-        int col_best = SMX_NEG_INF, col_best_i = 0;
+        int col_best = SMX_NEG_INF, col_best_i = 0x7fffffff;
         int row_best = SMX_NEG_INF, row_best_j = 0;
         int corner = 0;
         int loc_best = 0, loc_i = m - 1, loc_j = n - 1;  // local mode: first maximum in row-major order
         const int last_lane = ((m - 1) % (32 * K)) / K;
         const int last_k = (m - 1) % K;
 
-        for (int band = 0; band < nbands; ++band) {
+        for (int band = wib % W; band < nbands; band += W) {
             const int i0 = band * 32 * K + lane * K;
             const int2 *top_line = (band & 1) ? line1 : line0;  // written by the previous band
             int2 *bot_line = (band & 1) ? line0 : line1;
@@ -126,7 +146,14 @@ __global__ void __launch_bounds__(128) smx_dp_forward(const SmxFwdArgs a)
             int hd = (i0 == 0 || free_beg) ? 0 : -(go + (i0 - 1) * ge);  // H[i0-1][-1]
             int out_h = 0, out_f = 0, rc_prev = 4;
 
-            for (int s0 = 0; s0 < steps; s0 += 32) {
+            for (int s0 = 0, chunk = 0; s0 < steps; s0 += 32, ++chunk) {
+                if (TEAM && band > 0) {
+                    // columns s0..s0+31 of the previous band are complete once it finished chunk + 1
+                    const int need = (band - 1) * nchunks + min(chunk + 2, nchunks);
+                    if (lane == 0) { while (s_prog[(band - 1) % W] < need) __nanosleep(64); }
+                    __syncwarp();
+                    __threadfence_block();
+                }
                 // chunk prefetch for lane 0's inputs: top boundary (H, F) and reference codes of columns s0..s0+31
                 const int jc = s0 + lane;
                 int2 top = make_int2(0, SMX_NEG_INF);
@@ -204,7 +231,7 @@ __global__ void __launch_bounds__(128) smx_dp_forward(const SmxFwdArgs a)
                                     if (i == m - 1) corner = Hl[k];
                                 }
                             }
-                            if (last_band && lane == last_lane) {
+                            if (mode == 1 && last_band && lane == last_lane) {
                                 int hv = Hl[0];
 #pragma unroll
                                 for (int k = 1; k < K; ++k) if (k == last_k) hv = Hl[k];
@@ -212,6 +239,10 @@ __global__ void __launch_bounds__(128) smx_dp_forward(const SmxFwdArgs a)
                             }
                         }
                     }
+                }
+                if (TEAM && !last_band) {
+                    // lane 31 wrote the bottom line of this chunk: publish after a block-scope fence
+                    if (lane == 31) { __threadfence_block(); s_prog[wib] = band * nchunks + chunk + 1; }
                 }
             }
             __syncwarp();
@@ -230,6 +261,18 @@ __global__ void __launch_bounds__(128) smx_dp_forward(const SmxFwdArgs a)
                     loc_best = ob; loc_i = oi; loc_j = oj;
                 }
             }
+            if (TEAM) {
+                if (lane == 0) { s_red[wib][0] = loc_best; s_red[wib][1] = loc_i; s_red[wib][2] = loc_j; }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    for (int w = 1; w < W; ++w) {
+                        const int ob = s_red[w][0], oi = s_red[w][1], oj = s_red[w][2];
+                        if (ob > loc_best || (ob == loc_best && ob > 0 && (oi < loc_i || (oi == loc_i && oj < loc_j)))) {
+                            loc_best = ob; loc_i = oi; loc_j = oj;
+                        }
+                    }
+                }
+            }
             r.score = loc_best; r.end_q = loc_i; r.end_r = loc_j;
         } else {
 #pragma unroll
@@ -238,9 +281,24 @@ __global__ void __launch_bounds__(128) smx_dp_forward(const SmxFwdArgs a)
                 const int oi = __shfl_xor_sync(SMX_FULL_MASK, col_best_i, off);
                 if (ob > col_best || (ob == col_best && oi < col_best_i)) { col_best = ob; col_best_i = oi; }
             }
+            const int owner = TEAM ? ((nbands - 1) % W) : 0;  // warp that ran the last band
             row_best = __shfl_sync(SMX_FULL_MASK, row_best, last_lane);
             row_best_j = __shfl_sync(SMX_FULL_MASK, row_best_j, last_lane);
             corner = __shfl_sync(SMX_FULL_MASK, corner, last_lane);
+            if (TEAM) {
+                if (lane == 0) {
+                    s_red[wib][0] = col_best; s_red[wib][1] = col_best_i;
+                    if (wib == owner) { s_red[0][2] = row_best; s_red[0][3] = row_best_j; s_red[0][4] = corner; }
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    for (int w = 1; w < W; ++w) {
+                        const int ob = s_red[w][0], oi = s_red[w][1];
+                        if (ob > col_best || (ob == col_best && oi < col_best_i)) { col_best = ob; col_best_i = oi; }
+                    }
+                    row_best = s_red[0][2]; row_best_j = s_red[0][3]; corner = s_red[0][4];
+                }
+            }
             if (mode == 1) {  // SMX_MODE_SG_QE_DE
                 int best = SMX_NEG_INF, bi = m - 1, bj = n - 1;
                 if (col_best > best) { best = col_best; bi = col_best_i; bj = n - 1; }
@@ -250,6 +308,6 @@ __global__ void __launch_bounds__(128) smx_dp_forward(const SmxFwdArgs a)
                 r.score = corner; r.end_q = m - 1; r.end_r = n - 1;
             }
         }
-        if (lane == 0) a.results[pid] = r;
+        if (TEAM ? (threadIdx.x == 0) : (lane == 0)) a.results[pid] = r;
     }
 }
