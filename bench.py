@@ -141,7 +141,7 @@ def config_dict(args, **extra):
                      f"{args.reads} ONT-like reads (~8% error), circular, post_analysis alignment stage",
          "reads_per_rank": args.reads, "plasmids": 6, "pair_strands_per_rank": args.reads * 12,
          "scoring": [3, 1, 1, -2], "cache": "inputs_exceed_l2 (per-step direction-bit arena is GBs >> 126 MB L2)",
-         "batch_reads_per_call": args.batch}
+         "batch_reads_per_call": args.batch, "batches_in_flight": args.overlap}
     d.update(extra)
     return d
 
@@ -170,7 +170,7 @@ def run_engine(args, rank, world, local_rank):
     in_bytes = sum(len(p) for p in refs) + sum(len(r) for r in reads)
 
     def step():
-        return sm.align_all(refs, reads, PARAMS, True, engine=eng, n_threads=n_threads, batch_queries=args.batch)
+        return sm.align_all(refs, reads, PARAMS, True, engine=eng, n_threads=n_threads, batch_queries=args.batch, overlap=args.overlap)
 
     for _ in range(args.warmup):
         step()
@@ -272,7 +272,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--reads", type=int, default=20000, help="reads per rank (C2 = 20000)")
-    ap.add_argument("--batch", type=int, default=2000, help="reads per smx_pipeline_run call")
+    ap.add_argument("--batch", type=int, default=1000, help="reads per smx_pipeline_run call")
+    ap.add_argument("--overlap", type=int, default=2, help="batches in flight per rank (engine handles)")
     ap.add_argument("--cpu-reads", type=int, default=0, help="reads of the CPU sample (default: max(cores, 8))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -233,9 +233,21 @@ static int problem_class(int m, int mode)
     return pick_kshift(m) * 2 + local;
 }
 
+static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_t *s1_len, const int64_t *s2_off,
+                              const int32_t *s2_len, const uint8_t *mode, const uint8_t *clip, int32_t n, int32_t open, int32_t extend,
+                              int32_t match, int32_t mismatch);
+
 extern "C" int smx_align_prepare(smx_handle *h, const int64_t *s1_off, const int32_t *s1_len, const int64_t *s2_off,
                                  const int32_t *s2_len, const uint8_t *mode, int32_t n, int32_t open, int32_t extend,
                                  int32_t match, int32_t mismatch)
+{
+    return align_prepare_impl(h, s1_off, s1_len, s2_off, s2_len, mode, nullptr, n, open, extend, match, mismatch);
+}
+
+// clip[p] != 0 (semi-global modes only): re-clip the CIGAR on the device (rows A9) and deliver only the kept part
+static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_t *s1_len, const int64_t *s2_off,
+                              const int32_t *s2_len, const uint8_t *mode, const uint8_t *clip, int32_t n, int32_t open, int32_t extend,
+                              int32_t match, int32_t mismatch)
 {
     if (!h) return -1;
     h->total_runs = -1;
@@ -262,6 +274,11 @@ extern "C" int smx_align_prepare(smx_handle *h, const int64_t *s1_off, const int
         if (bound > (int64_t)(1 << 29)) return fail(h, -1, "problem %d: score range exceeds int32 headroom", p);
         SmxProblem &q = h->probs[(size_t)p];
         q.s1_off = s1_off[p]; q.s2_off = s2_off[p]; q.m = m; q.n = nn; q.mode = mode[p];
+        if (clip && clip[p]) {
+            if (mode[p] != SMX_MODE_SG_QE_DE && mode[p] != SMX_MODE_SG_QB_DB) return fail(h, -1, "problem %d: only semi-global problems can be re-clipped", p);
+            if (match <= 0 || mismatch >= 0) return fail(h, -1, "device re-clipping needs match > 0 and mismatch < 0 (my_classes.py:547-552)");
+            q.mode |= SMX_MODE_CLIP;
+        }
         q.kshift = pick_kshift(m);
         h->class_cells[problem_class(m, mode[p])] += (int64_t)m * nn;
         q.trace_off = 0;
@@ -303,7 +320,7 @@ extern "C" int smx_align_prepare(smx_handle *h, const int64_t *s1_off, const int
             c.cls_first[cls] = w;
             for (int x = c.first; x < c.first + c.count; ++x) {
                 const SmxProblem &q = h->probs[(size_t)order[x]];
-                const int qc = problem_class(q.m, q.mode);
+                const int qc = problem_class(q.m, q.mode & SMX_MODE_MASK);
                 if (qc == cls) h->order_cls[(size_t)w++] = order[x];
             }
             c.cls_count[cls] = w - c.cls_first[cls];
@@ -397,6 +414,7 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
         t.trace = (const uint8_t *)h->d_trace.p;
         t.results = (SmxResult *)h->d_results.p;
         t.runs = (uint32_t *)h->d_runs.p;
+        t.sc = h->sc;
         smx_traceback<<<(c.count + 127) / 128, 128, 0, h->stream>>>(t);
         SMX_CUDA(h, cudaGetLastError());
         h->last_launches++;
@@ -897,7 +915,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     // global problem ids
     std::vector<int64_t> p_s1, p_s2;
     std::vector<int32_t> p_m, p_n;
-    std::vector<uint8_t> p_mode;
+    std::vector<uint8_t> p_mode, p_clip;
     for (size_t ti = 0; ti < todo.size(); ++ti) {
         PairStrand &x = st.ps[(size_t)todo[ti]];
         if (x.failed) { ++st.n_failed; continue; }
@@ -905,6 +923,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         for (const PlannedProblem &pp : local[ti]) {
             if (pp.m <= 0 || pp.n <= 0) return fail(h, -5, "internal: empty DP slice planned");
             p_s1.push_back(pp.s1_off); p_s2.push_back(pp.s2_off); p_m.push_back(pp.m); p_n.push_back(pp.n); p_mode.push_back(pp.mode);
+            p_clip.push_back(pp.mode == SMX_MODE_NW ? 0 : 1);
         }
         for (Piece &pc : x.pieces) for (int z = 0; z < 2; ++z) if (pc.prob[z] >= 0) pc.prob[z] += base;
     }
@@ -918,7 +937,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     std::vector<uint32_t> cg;
     st.n_dp = n_prob;
     if (n_prob > 0) {
-        if (int rc = smx_align_prepare(h, p_s1.data(), p_m.data(), p_s2.data(), p_n.data(), p_mode.data(), n_prob, open, extend, match, mismatch)) return rc;
+        if (int rc = align_prepare_impl(h, p_s1.data(), p_m.data(), p_s2.data(), p_n.data(), p_mode.data(), p_clip.data(), n_prob, open, extend, match, mismatch)) return rc;
         int64_t truns = 0;
         if (int rc = smx_align_run(h, &truns)) return rc;
         st.gpu_dp_ms = h->last_ms; st.dp_cells = h->cells; st.launches += h->last_launches;
@@ -930,37 +949,49 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     }
     st.t_dp = now_s() - t0;
 
-    // ---- A9-A11 on host threads ----
+    // ---- A9-A11 on host threads (run-length domain; re-clipping already happened in the traceback kernel) ----
     t0 = now_s();
     std::atomic<int> n_bad(0);
+    const std::vector<SmxResult> &dres = h->h_results;
     parallel_for((int)todo.size(), n_threads, [&](int ti, int) {
         PairStrand &x = st.ps[(size_t)todo[(size_t)ti]];
         if (x.failed) return;
-        std::string cig, tmp;
-        auto expand = [&](int pid, std::string &dst) { expand_runs(&cg[(size_t)cg_off[(size_t)pid]], cg_off[(size_t)pid + 1] - cg_off[(size_t)pid], dst); };
+        Runs &cig = x.runs;
+        cig.clear();
+        auto clipped = [&](int pid) {
+            ClippedSg c;
+            c.kept = &cg[(size_t)cg_off[(size_t)pid]];
+            c.n_kept = cg_off[(size_t)pid + 1] - cg_off[(size_t)pid];
+            c.n_s = dres[(size_t)pid].n_s; c.n_h = dres[(size_t)pid].n_h;
+            return c;
+        };
         for (const Piece &pc : x.pieces) {
             switch (pc.kind) {
-            case PIECE_LITERAL: cig.append((size_t)pc.len, pc.letter); break;
-            case PIECE_NW: expand(pc.prob[0], cig); break;
-            case PIECE_SG_HEAD: { SgResult r; expand(pc.prob[0], r.cig); finish_qb_db(r, sc); cig += r.cig; break; }
-            case PIECE_SG_TAIL: { SgResult r; expand(pc.prob[0], r.cig); finish_qe_de(r, sc); cig += r.cig; break; }
+            case PIECE_LITERAL: push_run(cig, op_code(pc.letter), pc.len); break;
+            case PIECE_NW: append_runs(cig, &cg[(size_t)cg_off[(size_t)pc.prob[0]]], cg_off[(size_t)pc.prob[0] + 1] - cg_off[(size_t)pc.prob[0]]); break;
+            case PIECE_SG_HEAD: {  // my_special_sg_qb_db: H.. S.. aligned
+                const ClippedSg c = clipped(pc.prob[0]);
+                push_run(cig, 5, c.n_h); push_run(cig, 4, c.n_s); append_runs(cig, c.kept, c.n_kept);
+                break;
+            }
+            case PIECE_SG_TAIL: {  // my_special_sg_qe_de: aligned S.. H..
+                const ClippedSg c = clipped(pc.prob[0]);
+                append_runs(cig, c.kept, c.n_kept); push_run(cig, 4, c.n_s); push_run(cig, 5, c.n_h);
+                break;
+            }
             case PIECE_SPECIAL: {
-                SgResult r1, r2;
-                if (pc.prob[0] >= 0) { expand(pc.prob[0], r1.cig); finish_qe_de(r1, sc); }
-                else { r1.cig.assign((size_t)pc.n_ref, 'H'); r1.beg_ref = -1; r1.end_ref = -1; }
-                if (pc.prob[1] >= 0) { expand(pc.prob[1], r2.cig); finish_qb_db(r2, sc); }
-                else { r2.cig.assign((size_t)pc.n_ref, 'H'); r2.beg_ref = pc.n_ref; r2.end_ref = pc.n_ref; }
-                if (!merge_special(r1, r2, (size_t)pc.n_ref, (size_t)pc.nq1, (size_t)pc.nq2, sc, tmp)) { x.failed = true; n_bad++; return; }
-                cig += tmp;
+                ClippedSg r1, r2;
+                if (pc.prob[0] >= 0) r1 = clipped(pc.prob[0]); else r1.n_h = pc.n_ref;   // "H" * len(ref), end_ref = -1
+                if (pc.prob[1] >= 0) r2 = clipped(pc.prob[1]); else r2.n_h = pc.n_ref;   // "H" * len(ref), beg_ref = len(ref)
+                if (!merge_special_runs(r1, r2, pc.n_ref, pc.nq1, pc.nq2, sc, cig)) { x.failed = true; n_bad++; return; }
                 break;
             }
             }
         }
         int64_t new_off = 0;
-        if (topology == 0) new_off = rotate_to_ref0(cig, x.ref_off, x.q_off);
-        x.score = (int32_t)cigar_score(cig, sc);
+        if (topology == 0) new_off = rotate_to_ref0_runs(cig, x.ref_off, x.q_off);
+        x.score = (int32_t)cigar_score_runs(cig, sc);
         x.new_q_off = (int32_t)new_off;
-        encode_runs(cig, x.runs);
     });
     st.n_failed += n_bad.load();
     st.t_stitch = now_s() - t0;

@@ -19,9 +19,15 @@ struct SmxProblem {
 };
 
 struct SmxResult {
-    int32_t score, end_q, end_r, beg_q, beg_r, n_runs;
-    int32_t pad0, pad1;
+    int32_t score, end_q, end_r, beg_q, beg_r;
+    int32_t n_runs;     // runs to deliver (for re-clipped problems: the kept, aligned part only)
+    int32_t run_start;  // index of the first delivered run in the problem's scratch (walk order)
+    int32_t n_s, n_h;   // re-clipped problems: query bases turned into 'S', reference bases turned into 'H'
+    int32_t pad0, pad1, pad2;
 };
+
+#define SMX_MODE_MASK 0xff
+#define SMX_MODE_CLIP 0x100  // semi-global problem whose CIGAR is re-clipped on the device (MyResult.set_soft_clipping)
 
 struct SmxScoring {
     int32_t go, ge, match, mismatch;

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(TEAM ? SMX_TEAM_WARPS * 32 : 128) smx_dp_forwa
         if (ticket >= a.n_order) break;
         const int pid = a.order[ticket];
         const SmxProblem pr = a.probs[pid];
-        const int m = pr.m, n = pr.n, mode = pr.mode;
+        const int m = pr.m, n = pr.n, mode = pr.mode & SMX_MODE_MASK;
         const bool free_beg = LOCAL || mode == 2;  // SMX_MODE_SG_QB_DB
         const uint8_t *s1 = a.pool + pr.s1_off;
         const uint8_t *s2 = a.pool + pr.s2_off;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(TEAM ? SMX_TEAM_WARPS * 32 : 128) smx_dp_forwa
 
         // ---- end cell / score -------------------------------------------------------------
         SmxResult r;
-        r.beg_q = 0; r.beg_r = 0; r.n_runs = 0; r.pad0 = 0; r.pad1 = 0;
+        r.beg_q = 0; r.beg_r = 0; r.n_runs = 0; r.run_start = 0; r.n_s = 0; r.n_h = 0; r.pad0 = 0; r.pad1 = 0; r.pad2 = 0;
         if (LOCAL) {
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {

@@ -251,4 +251,138 @@ inline int64_t cigar_score(const std::string &cig, const Scoring &sc)
     return s;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// run-length versions (uint32 len << 4 | op); adjacent runs of one letter are always merged, so a
+// vector of runs is the maximal-run decomposition that set_cigar_score / MyResult.cigar iterate over
+// ---------------------------------------------------------------------------------------------
+typedef std::vector<uint32_t> Runs;
+
+inline void push_run(Runs &v, uint32_t op, int64_t len)
+{
+    if (len <= 0) return;
+    if (!v.empty() && (v.back() & 15u) == op) v.back() += (uint32_t)(len << 4);
+    else v.push_back((uint32_t)(len << 4) | op);
+}
+
+inline void append_runs(Runs &v, const uint32_t *r, int64_t n)
+{
+    for (int64_t i = 0; i < n; ++i) push_run(v, r[i] & 15u, (int64_t)(r[i] >> 4));
+}
+
+inline int64_t total_columns(const Runs &v)
+{
+    int64_t n = 0;
+    for (uint32_t r : v) n += r >> 4;
+    return n;
+}
+
+// columns among the last `a` columns whose op is in `mask` (bit per op code); a beyond the length clamps
+inline int64_t tail_count(const Runs &v, int64_t a, uint32_t mask)
+{
+    int64_t cnt = 0;
+    for (size_t i = v.size(); i-- > 0 && a > 0;) {
+        const int64_t len = v[i] >> 4, take = len < a ? len : a;
+        if ((mask >> (v[i] & 15u)) & 1u) cnt += take;
+        a -= take;
+    }
+    return cnt;
+}
+
+inline int64_t aligned_offset_runs(const Runs &v, int64_t off, uint32_t mask)
+{
+    if (off == 0) return 0;
+    int64_t a = off, prev = 0, cnt = tail_count(v, a, mask);
+    while (off != a - cnt) {
+        a += cnt - prev;
+        prev = cnt;
+        cnt = tail_count(v, a, mask);
+    }
+    return a;
+}
+
+// set_ref_seq_offset_as_0 on runs: rotates in place, returns new_query_seq_offset
+inline int64_t rotate_to_ref0_runs(Runs &v, int64_t ref_off, int64_t q_off)
+{
+    const uint32_t IS = (1u << 1) | (1u << 4), DH = (1u << 2) | (1u << 5);
+    const int64_t a_r = aligned_offset_runs(v, ref_off, IS);
+    const int64_t a_q = aligned_offset_runs(v, q_off, DH);
+    const int64_t diff = a_q - a_r;
+    int64_t new_off;
+    if (a_q > a_r) new_off = diff - (tail_count(v, a_q, DH) - tail_count(v, a_r, DH));
+    else if (a_q != 0) new_off = diff + (tail_count(v, a_r, DH) - tail_count(v, a_q, DH));
+    else if (a_r != 0) new_off = diff + tail_count(v, a_r, DH);
+    else new_off = 0;
+    if (a_r > 0) {
+        const int64_t n = total_columns(v);
+        int64_t head = a_r >= n ? 0 : n - a_r;  // columns that move to the back
+        Runs front, back;
+        for (uint32_t r : v) {
+            const int64_t len = r >> 4;
+            const uint32_t op = r & 15u;
+            if (head >= len) { push_run(back, op, len); head -= len; }
+            else if (head > 0) { push_run(back, op, head); push_run(front, op, len - head); head = 0; }
+            else push_run(front, op, len);
+        }
+        append_runs(front, back.data(), (int64_t)back.size());
+        v.swap(front);
+    }
+    return new_off;
+}
+
+inline int64_t cigar_score_runs(const Runs &v, const Scoring &sc)
+{
+    int64_t s = 0;
+    for (uint32_t r : v) {
+        const int64_t len = r >> 4;
+        switch (r & 15u) {
+        case 7: s += sc.ma * len; break;
+        case 8: s += sc.mi * len; break;
+        case 1: case 2: s -= sc.go + sc.ge * (len - 1); break;
+        default: break;
+        }
+    }
+    return s;
+}
+
+// a semi-global result after device-side re-clipping: kept aligned runs (forward order) + counts
+struct ClippedSg {
+    const uint32_t *kept = nullptr;
+    int64_t n_kept = 0, n_s = 0, n_h = 0;
+};
+
+// my_special_DP on re-clipped results; r1 = sg_qe_de(q1, ref) = kept1 + S*n_s1 + H*n_h1,
+// r2 = sg_qb_db(q2, ref) = H*n_h2 + S*n_s2 + kept2.  Appends the merged column runs to `out`.
+inline bool merge_special_runs(const ClippedSg &r1, const ClippedSg &r2, int64_t n_ref, int64_t nq1, int64_t nq2, const Scoring &sc, Runs &out)
+{
+    const int64_t gap = r2.n_h + r1.n_h - n_ref;  // r2.beg_ref - r1.end_ref - 1
+    if (gap > 0) {
+        append_runs(out, r1.kept, r1.n_kept);
+        push_run(out, 4, r1.n_s);
+        push_run(out, 5, gap);
+        push_run(out, 4, r2.n_s);
+        append_runs(out, r2.kept, r2.n_kept);
+        return true;
+    }
+    SgResult a, b;
+    expand_runs(r1.kept, r1.n_kept, a.cig);
+    a.cig.append((size_t)r1.n_s, 'S');
+    a.cig.append((size_t)r1.n_h, 'H');
+    a.end_ref = n_ref - r1.n_h - 1;
+    b.cig.assign((size_t)r2.n_h, 'H');
+    b.cig.append((size_t)r2.n_s, 'S');
+    expand_runs(r2.kept, r2.n_kept, b.cig);
+    b.beg_ref = r2.n_h;
+    std::string merged;
+    if (!merge_special(a, b, (size_t)n_ref, (size_t)nq1, (size_t)nq2, sc, merged)) return false;
+    size_t i = 0;
+    while (i < merged.size()) {
+        size_t j = i;
+        while (j < merged.size() && merged[j] == merged[i]) ++j;
+        push_run(out, op_code(merged[i]), (int64_t)(j - i));
+        i = j;
+    }
+    return true;
+}
+
 }  // namespace smx

@@ -13,6 +13,7 @@ struct SmxTbArgs {
     const uint8_t *trace;
     SmxResult *results;
     uint32_t *runs;  // scratch, reversed order per problem
+    SmxScoring sc;
 };
 
 __device__ __forceinline__ uint32_t smx_trace_nibble(const uint8_t *tr, int n, int kshift, int i, int j)
@@ -29,6 +30,55 @@ __device__ __forceinline__ uint32_t smx_trace_nibble(const uint8_t *tr, int n, i
     return (byte >> ((k & 1) * 4)) & 15u;
 }
 
+// Walk state shared by the emit helper.  Besides run-length encoding it evaluates, for problems flagged
+// SMX_MODE_CLIP, the re-clipping of MyResult.set_soft_clipping(_core) (ref_query_alignment.py:562-622) while
+// walking: the running affine score of the column string peaks at the end of an '=' run (match > 0,
+// mismatch < 0, gaps > 0), so only run boundaries are candidates.
+//   sg_qb_db (side="end"): the reference scores the REVERSED string = our walk order; keep the walk
+//       prefix up to the first maximum.
+//   sg_qe_de (side="beg"): the reference scores the forward string; walking backwards we minimise the
+//       score of the suffix walked so far, ties resolved towards the forward-earliest cut ('<=').
+struct SmxWalk {
+    uint32_t *out;
+    int nruns;
+    uint32_t cur_op, cur_len;
+    int clip;          // 0 none, 1 = sg_qe_de, 2 = sg_qb_db
+    int go, ge, ma, mi;
+    long long acc;     // score of the completed runs
+    int q_used, r_used;
+    long long best;    // qb_db: best prefix score; qe_de: minimal suffix score
+    int have, cut_runs, cut_q, cut_r;
+
+    __device__ __forceinline__ void candidate_qe_de()
+    {
+        if (!have || acc <= best) { best = acc; cut_runs = nruns; cut_q = q_used; cut_r = r_used; have = 1; }
+    }
+    __device__ __forceinline__ void flush()
+    {
+        if (!cur_len) return;
+        out[nruns++] = (cur_len << 4) | cur_op;
+        if (clip) {
+            const int len = (int)cur_len;
+            if (cur_op == SMX_OP_EQ) { acc += (long long)ma * len; q_used += len; r_used += len; }
+            else if (cur_op == SMX_OP_X) { acc += (long long)mi * len; q_used += len; r_used += len; }
+            else {
+                acc -= go + (long long)ge * (len - 1);
+                if (cur_op == SMX_OP_I) q_used += len; else r_used += len;
+            }
+            if (clip == 2 && cur_op == SMX_OP_EQ && (!have || acc > best)) { best = acc; cut_runs = nruns; cut_q = q_used; cut_r = r_used; have = 1; }
+        }
+        cur_len = 0;
+    }
+    __device__ __forceinline__ void emit(uint32_t op, uint32_t len)
+    {
+        if (!len) return;
+        if (op == cur_op && cur_len) { cur_len += len; return; }
+        flush();
+        if (clip == 1 && op == SMX_OP_EQ) candidate_qe_de();
+        cur_op = op; cur_len = len;
+    }
+};
+
 // one thread per problem; runs are emitted while walking back, i.e. in reverse order
 __global__ void __launch_bounds__(128) smx_traceback(const SmxTbArgs a)
 {
@@ -40,64 +90,62 @@ __global__ void __launch_bounds__(128) smx_traceback(const SmxTbArgs a)
     const uint8_t *s1 = a.pool + pr.s1_off;
     const uint8_t *s2 = a.pool + pr.s2_off;
     const uint8_t *tr = a.trace + pr.trace_off;
-    uint32_t *out = a.runs + pr.cigar_off;
     const int m = pr.m, n = pr.n;
-    const bool local = pr.mode == SMX_MODE_SW;
+    const int mode = pr.mode & SMX_MODE_MASK;
+    const bool local = mode == SMX_MODE_SW;
 
-    int nruns = 0;
-    uint32_t cur_op = 0, cur_len = 0;
-#define SMX_EMIT(op_, len_)                                             \
-    do {                                                                \
-        const uint32_t o_ = (op_);                                      \
-        const uint32_t l_ = (uint32_t)(len_);                           \
-        if (l_ > 0) {                                                   \
-            if (o_ == cur_op) cur_len += l_;                            \
-            else {                                                      \
-                if (cur_len) out[nruns++] = (cur_len << 4) | cur_op;    \
-                cur_op = o_; cur_len = l_;                              \
-            }                                                           \
-        }                                                               \
-    } while (0)
+    SmxWalk w;
+    w.out = a.runs + pr.cigar_off; w.nruns = 0; w.cur_op = 0; w.cur_len = 0;
+    w.clip = (pr.mode & SMX_MODE_CLIP) ? mode : 0;
+    w.go = a.sc.go; w.ge = a.sc.ge; w.ma = a.sc.match; w.mi = a.sc.mismatch;
+    w.acc = 0; w.q_used = 0; w.r_used = 0; w.best = 0; w.have = 0; w.cut_runs = 0; w.cut_q = 0; w.cut_r = 0;
 
     int i = r.end_q, j = r.end_r;
-    if (pr.mode == SMX_MODE_SG_QE_DE) {
+    if (mode == SMX_MODE_SG_QE_DE) {
         // semi-global: the CIGAR also covers the free trailing part
-        if (i + 1 == m) SMX_EMIT(SMX_OP_D, n - 1 - j);
-        else if (j + 1 == n) SMX_EMIT(SMX_OP_I, m - 1 - i);
+        if (i + 1 == m) w.emit(SMX_OP_D, n - 1 - j);
+        else if (j + 1 == n) w.emit(SMX_OP_I, m - 1 - i);
     }
     int where = 0;  // 0 = DIAG (H), 1 = INS (E, emits 'D'), 2 = DEL (F, emits 'I')
     while (local ? (i >= 0 && j >= 0) : (i >= 0 || j >= 0)) {
-        if (i < 0) { SMX_EMIT(SMX_OP_D, j + 1); j = -1; break; }
-        if (j < 0) { SMX_EMIT(SMX_OP_I, i + 1); i = -1; break; }
+        if (i < 0) { w.emit(SMX_OP_D, j + 1); j = -1; break; }
+        if (j < 0) { w.emit(SMX_OP_I, i + 1); i = -1; break; }
         const uint32_t nib = smx_trace_nibble(tr, n, pr.kshift, i, j);
         if (where == 0) {
             const uint32_t src = nib & 3u;
             if (src == SMX_SRC_DIAG) {
-                SMX_EMIT(s1[i] == s2[j] ? SMX_OP_EQ : SMX_OP_X, 1);
+                w.emit(s1[i] == s2[j] ? SMX_OP_EQ : SMX_OP_X, 1);
                 --i; --j;
             } else if (src == SMX_SRC_INS) where = 1;
             else if (src == SMX_SRC_DEL) where = 2;
             else break;  // ZERO: local alignment starts here
         } else if (where == 1) {
-            SMX_EMIT(SMX_OP_D, 1);
+            w.emit(SMX_OP_D, 1);
             --j;
             where = (nib & SMX_BIT_EOPEN) ? 0 : 1;
         } else {
-            SMX_EMIT(SMX_OP_I, 1);
+            w.emit(SMX_OP_I, 1);
             --i;
             where = (nib & SMX_BIT_FOPEN) ? 0 : 2;
         }
     }
-    if (cur_len) out[nruns++] = (cur_len << 4) | cur_op;
-#undef SMX_EMIT
+    w.flush();
     r.beg_q = local ? i + 1 : 0;
     r.beg_r = local ? j + 1 : 0;
-    r.n_runs = nruns;
+    r.n_runs = w.nruns; r.run_start = 0; r.n_s = 0; r.n_h = 0;
+    if (w.clip == 2) {
+        if (!w.have || w.best < 0) { r.n_runs = 0; r.n_s = m; r.n_h = n; }
+        else { r.n_runs = w.cut_runs; r.n_s = m - w.cut_q; r.n_h = n - w.cut_r; }
+    } else if (w.clip == 1) {
+        // acc is now the score of the whole string; the best forward prefix scores acc - best
+        if (!w.have || w.acc - w.best < 0) { r.n_runs = 0; r.n_s = m; r.n_h = n; }
+        else { r.run_start = w.cut_runs; r.n_runs = w.nruns - w.cut_runs; r.n_s = w.cut_q; r.n_h = w.cut_r; }
+    }
     a.results[pid] = r;
 }
 
 // gathers the per-problem reversed runs into one dense forward-order array
-// dense[off[p] + x] = runs[cigar_off[p] + n_runs[p] - 1 - x]; one warp per problem.
+// dense[off[p] + x] = runs[cigar_off[p] + run_start[p] + n_runs[p] - 1 - x]; one warp per problem.
 __global__ void __launch_bounds__(256) smx_compact_runs(const SmxProblem *probs, const SmxResult *results,
                                                         const int64_t *dense_off, const uint32_t *runs,
                                                         uint32_t *dense, int32_t n)
@@ -106,7 +154,7 @@ __global__ void __launch_bounds__(256) smx_compact_runs(const SmxProblem *probs,
     const int lane = threadIdx.x & 31;
     if (w >= n) return;
     const int nr = results[w].n_runs;
-    const uint32_t *src = runs + probs[w].cigar_off;
+    const uint32_t *src = runs + probs[w].cigar_off + results[w].run_start;
     uint32_t *dst = dense + dense_off[w];
     for (int x = lane; x < nr; x += 32) dst[x] = src[nr - 1 - x];
 }

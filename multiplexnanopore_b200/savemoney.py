@@ -103,9 +103,24 @@ def _merge(parts):
                           np.concatenate([p.cigar_rle for p in parts]), stats)
 
 
-def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None, n_threads=0, batch_queries=2000):
+_engine_pools = {}
+
+
+def _engines_for(engine, n):
+    """`n` engines on the device of `engine`: the caller's engine plus lazily created siblings.  Two handles
+    let the host stages (chain search, stitching) of one batch overlap the GPU stages of the next one."""
+    key = id(engine)
+    pool = _engine_pools.setdefault(key, [engine])
+    while len(pool) < n:
+        pool.append(Engine(engine.device))
+    return pool[:n]
+
+
+def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None, n_threads=0, batch_queries=1000,
+              overlap=2):
     """The alignment stage for every (query, reference) pair and both strands (or the explicit `pairs`).
-    Queries are processed in batches of `batch_queries` so that device workspaces stay bounded."""
+    Queries are processed in batches of `batch_queries` so that device workspaces stay bounded; `overlap`
+    batches are in flight at once (one engine handle and one Python thread each; ctypes drops the GIL)."""
     _check_params(param_dict)
     eng = engine or default_engine()
     refs = [_seq_of(r) for r in refs]
@@ -115,8 +130,26 @@ def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None,
             param_dict["mismatch_score"], param_dict["topology_of_dna"], omit_too_long)
     if pairs is not None or len(queries) <= batch_queries:
         return eng.pipeline_run(refs, queries, sig, *args, pairs=pairs, n_threads=n_threads)
-    parts = [eng.pipeline_run(refs, queries[b:b + batch_queries], sig, *args, n_threads=n_threads)
-             for b in range(0, len(queries), batch_queries)]
+    starts = list(range(0, len(queries), batch_queries))
+    if overlap <= 1:
+        parts = [eng.pipeline_run(refs, queries[b:b + batch_queries], sig, *args, n_threads=n_threads) for b in starts]
+        return _merge(parts)
+    from concurrent.futures import ThreadPoolExecutor
+    import queue
+    engines = _engines_for(eng, min(overlap, len(starts)))
+    free = queue.SimpleQueue()
+    for e in engines:
+        free.put(e)
+
+    def work(b):
+        e = free.get()
+        try:
+            return e.pipeline_run(refs, queries[b:b + batch_queries], sig, *args, n_threads=n_threads)
+        finally:
+            free.put(e)
+
+    with ThreadPoolExecutor(max_workers=len(engines)) as ex:
+        parts = list(ex.map(work, starts))
     return _merge(parts)
 
 
