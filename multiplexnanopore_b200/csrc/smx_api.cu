@@ -75,6 +75,7 @@ struct smx_handle {
 
     // pipeline state (smx_pipeline.cuh)
     DevBuf d_sel_pairs, d_sel_out, d_regions;
+    DevBuf d_chain_tasks, d_chain_regions, d_chain_traces, d_chain_out;
     std::vector<uint8_t> host_pool;
     struct SmxPipelineState *pipe = nullptr;
 };
@@ -181,7 +182,8 @@ extern "C" void smx_destroy(smx_handle *h)
     cudaStreamSynchronize(h->stream);
     DevBuf *bufs[] = {&h->pool, &h->d_probs, &h->d_order_cls, &h->d_order_all, &h->d_results, &h->d_trace, &h->d_boundary,
                       &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts,
-                      &h->d_sel_pairs, &h->d_sel_out, &h->d_regions};
+                      &h->d_sel_pairs, &h->d_sel_out, &h->d_regions, &h->d_chain_tasks, &h->d_chain_regions, &h->d_chain_traces,
+                      &h->d_chain_out};
     smx_pipeline_free(h);
     for (DevBuf *b : bufs) release(*b);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -642,6 +644,8 @@ extern "C" int smx_measure_int_peak(smx_handle *h, int32_t iters, double *out_go
 // A1: the whole alignment stage (scan -> select -> chain -> DP -> stitch)
 // ------------------------------------------------------------------------------------------------
 #include "smx_pipeline.cuh"
+#include "smx_chain.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -828,17 +832,88 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         pos = end;
     }
 
-    // ---- A5/A6/A7: chain + plan on host threads ----
+    // ---- A6: chain search on the device (one CTA per pair-strand, one warp per origin); pair-strands with more
+    //      than SMX_CHAIN_MAXN regions, or SMX_CHAIN=host, use the host implementation (smx_chain.hpp) ----
     double t0 = now_s();
     std::vector<int> todo;
     for (size_t i = 0; i < st.ps.size(); ++i) if (!st.ps[i].skip) todo.push_back((int)i);
+    std::vector<std::vector<int>> traces((size_t)todo.size());
+    std::vector<uint8_t> on_host((size_t)todo.size(), 1);
+    {
+        const char *env = getenv("SMX_CHAIN");
+        const bool force_host = env && std::string(env) == "host";
+        static const int cls_n[4] = {32, 64, 128, 256};
+        std::vector<int> members[4];
+        if (!force_host)
+            for (size_t ti = 0; ti < todo.size(); ++ti) {
+                const int n = (int)st.ps[(size_t)todo[ti]].regions.size();
+                for (int c = 0; c < 4; ++c) if (n <= cls_n[c]) { members[c].push_back((int)ti); on_host[ti] = 0; break; }
+            }
+        std::vector<SmxChainTask> tasks;
+        std::vector<int4> regs;
+        std::vector<int> task_ti;
+        int cls_first[5] = {0, 0, 0, 0, 0};
+        int64_t trace_total = 0;
+        for (int c = 0; c < 4; ++c) {
+            cls_first[c] = (int)tasks.size();
+            for (int ti : members[c]) {
+                const PairStrand &x = st.ps[(size_t)todo[(size_t)ti]];
+                SmxChainTask tk;
+                tk.region_off = (int64_t)regs.size(); tk.trace_off = trace_total; tk.n = (int)x.regions.size();
+                tk.n_ref = x.nr; tk.n_q = x.nq; tk.pad = 0;
+                for (const Region &g : x.regions) regs.push_back(make_int4(g.rs, g.re, g.qs, g.qe));
+                trace_total += tk.n;
+                tasks.push_back(tk); task_ti.push_back(ti);
+            }
+        }
+        cls_first[4] = (int)tasks.size();
+        if (!tasks.empty()) {
+            if (int rc = ensure(h, h->d_chain_tasks, sizeof(SmxChainTask) * tasks.size())) return rc;
+            if (int rc = ensure(h, h->d_chain_regions, sizeof(int4) * regs.size())) return rc;
+            if (int rc = ensure(h, h->d_chain_traces, sizeof(int32_t) * (size_t)std::max<int64_t>(trace_total, 1))) return rc;
+            if (int rc = ensure(h, h->d_chain_out, sizeof(SmxChainOut) * tasks.size())) return rc;
+            SMX_CUDA(h, cudaMemcpyAsync(h->d_chain_tasks.p, tasks.data(), sizeof(SmxChainTask) * tasks.size(), cudaMemcpyHostToDevice, h->stream));
+            SMX_CUDA(h, cudaMemcpyAsync(h->d_chain_regions.p, regs.data(), sizeof(int4) * regs.size(), cudaMemcpyHostToDevice, h->stream));
+            SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+            for (int c = 0; c < 4; ++c) {
+                const int cnt = cls_first[c + 1] - cls_first[c];
+                if (cnt == 0) continue;
+                const int nmax = cls_n[c];
+                const size_t smem = sizeof(int) * (size_t)(7 * nmax + SMX_CHAIN_WARPS * (15 * nmax + nmax * (nmax / 32)));
+                if (smem > 48 * 1024) SMX_CUDA(h, cudaFuncSetAttribute(smx_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                SmxChainArgs ca;
+                ca.tasks = (const SmxChainTask *)h->d_chain_tasks.p + cls_first[c];
+                ca.regions = (const int4 *)h->d_chain_regions.p;
+                ca.traces = (int32_t *)h->d_chain_traces.p;
+                ca.out = (SmxChainOut *)h->d_chain_out.p + cls_first[c];
+                ca.topology = topology; ca.nmax = nmax;
+                smx_chain_kernel<<<cnt, SMX_CHAIN_WARPS * 32, smem, h->stream>>>(ca);
+                SMX_CUDA(h, cudaGetLastError());
+                st.launches += 1;
+            }
+            SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+            std::vector<SmxChainOut> couts(tasks.size());
+            std::vector<int32_t> tr((size_t)std::max<int64_t>(trace_total, 1));
+            SMX_CUDA(h, cudaMemcpyAsync(couts.data(), h->d_chain_out.p, sizeof(SmxChainOut) * tasks.size(), cudaMemcpyDeviceToHost, h->stream));
+            SMX_CUDA(h, cudaMemcpyAsync(tr.data(), h->d_chain_traces.p, sizeof(int32_t) * (size_t)std::max<int64_t>(trace_total, 1), cudaMemcpyDeviceToHost, h->stream));
+            SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+            { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1); st.gpu_chain_ms += ms; }
+            for (size_t k = 0; k < tasks.size(); ++k) {
+                std::vector<int> &t = traces[(size_t)task_ti[k]];
+                t.assign(tr.begin() + tasks[k].trace_off, tr.begin() + tasks[k].trace_off + couts[k].trace_len);
+            }
+        }
+    }
+    // ---- A5/A7: plan on host threads (and A6 for the pair-strands kept on the host) ----
     std::vector<std::vector<PlannedProblem>> local((size_t)todo.size());
     std::vector<ChainSearch> searchers((size_t)std::max(1, n_threads));
     parallel_for((int)todo.size(), n_threads, [&](int ti, int tid) {
         PairStrand &x = st.ps[(size_t)todo[(size_t)ti]];
         std::vector<PlannedProblem> &probs = local[(size_t)ti];
-        std::vector<int> trace;
-        const bool ok = topology == 0 ? searchers[(size_t)tid].circular(x.regions, x.nr, x.nq, trace) : searchers[(size_t)tid].linear(x.regions, trace);
+        std::vector<int> &trace = traces[(size_t)ti];
+        bool ok = true;
+        if (on_host[(size_t)ti])
+            ok = topology == 0 ? searchers[(size_t)tid].circular(x.regions, x.nr, x.nq, trace) : searchers[(size_t)tid].linear(x.regions, trace);
         if (!ok || trace.empty()) { x.failed = true; return; }
         std::vector<Region> P(trace.size());
         for (size_t t = 0; t < trace.size(); ++t) P[t] = x.regions[(size_t)trace[t]];
@@ -1028,7 +1103,7 @@ extern "C" int smx_pipeline_stats(smx_handle *h, double *out, int32_t n)
 {
     if (!h || !out) return -1;
     const SmxPipelineState &st = *pipeline_state(h);
-    const double v[] = {st.t_total, st.t_pool, st.t_scan, st.t_select, st.t_chain, st.t_dp, st.t_stitch, st.gpu_scan_ms, st.gpu_select_ms,
+    const double v[] = {st.t_total, st.t_pool, st.t_scan, st.t_select, st.t_chain, st.t_dp, st.t_stitch, st.gpu_scan_ms, st.gpu_select_ms + st.gpu_chain_ms,
                         st.gpu_dp_ms, (double)st.scan_cells, (double)st.dp_cells, (double)st.n_dp, (double)st.n_host_redo, (double)st.n_failed,
                         (double)st.launches, (double)st.ps.size()};
     const int m = (int)(sizeof(v) / sizeof(v[0]));

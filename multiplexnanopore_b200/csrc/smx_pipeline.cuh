@@ -125,7 +125,7 @@ struct SmxPipelineState {
     std::vector<int64_t> out_off;
     int64_t total_runs = 0;
     double t_pool = 0, t_scan = 0, t_select = 0, t_chain = 0, t_dp = 0, t_stitch = 0, t_total = 0;
-    double gpu_scan_ms = 0, gpu_select_ms = 0, gpu_dp_ms = 0;
+    double gpu_scan_ms = 0, gpu_select_ms = 0, gpu_dp_ms = 0, gpu_chain_ms = 0;
     int64_t scan_cells = 0, dp_cells = 0, n_dp = 0, n_host_redo = 0, n_failed = 0;
     int launches = 0;
     double dp_kernel_ms[12] = {0};

@@ -5,6 +5,8 @@
 #include "smx_common.cuh"
 #include "../../include/smx.h"
 
+#define SMX_TB_AHEAD 48
+
 struct SmxTbArgs {
     const uint8_t *pool;
     const SmxProblem *probs;
@@ -107,9 +109,27 @@ __global__ void __launch_bounds__(128) smx_traceback(const SmxTbArgs a)
         else if (j + 1 == n) w.emit(SMX_OP_I, m - 1 - i);
     }
     int where = 0;  // 0 = DIAG (H), 1 = INS (E, emits 'D'), 2 = DEL (F, emits 'I')
+    // The walk is one dependent 1-byte load per step on direction bits that left L2 long ago.  Lines are
+    // laid out [band][step][lane] and every move lowers the step index by 0..2, so the lines the walk is
+    // about to touch are known without knowing the path: prefetch the two lines SMX_TB_AHEAD steps ahead
+    // (at the sector of the current lane) into L2 on every iteration.
+    const int kshift = pr.kshift;
+    const int wbytes = kshift >= 1 ? (1 << kshift) >> 1 : 1;
+    const int rows_per_band = 32 << kshift;
     while (local ? (i >= 0 && j >= 0) : (i >= 0 || j >= 0)) {
         if (i < 0) { w.emit(SMX_OP_D, j + 1); j = -1; break; }
         if (j < 0) { w.emit(SMX_OP_I, i + 1); i = -1; break; }
+        {
+            const int band = i / rows_per_band;
+            const int lane_t = (i - band * rows_per_band) >> kshift;
+            const int s_now = j + lane_t;
+            const int s_pf = s_now - SMX_TB_AHEAD;
+            if (s_pf >= 1) {
+                const uint8_t *p = tr + (((size_t)band * (size_t)(n + 31) + (size_t)s_pf) * 32 + (size_t)lane_t) * wbytes;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p - 32 * wbytes));
+            }
+        }
         const uint32_t nib = smx_trace_nibble(tr, n, pr.kshift, i, j);
         if (where == 0) {
             const uint32_t src = nib & 3u;

@@ -117,3 +117,21 @@ def test_c4_linear_subset(engine):
     sc = res.score.reshape(len(reads), 24).astype(float) / np.repeat([len(p) for p in plasmids], 2)[None, :]
     expected = np.array([2 * pi + int(rc) for pi, rc in truth])
     assert (sc.argmax(1) == expected).mean() > 0.99
+
+
+@pytest.mark.parametrize("topology", [0, 1])
+def test_device_chain_equals_host_chain(engine, topology, monkeypatch):
+    """row A6 has two independent implementations (smx_chain.cuh on the device, smx_chain.hpp on the host,
+    selected by SMX_CHAIN=host); on a few thousand pair-strands every output must be identical."""
+    rng = np.random.default_rng(77 + topology)
+    plasmids = synth.plasmid_set(rng, 6, 4000, 9000, backbone=2500)
+    reads, _ = synth.reads_for(rng, plasmids, 600, topology=topology, homopolymer_rate=0.5)
+    params = dict(PARAMS, topology_of_dna=topology)
+    monkeypatch.delenv("SMX_CHAIN", raising=False)
+    dev = sm.align_all(plasmids, reads, params, True, engine=engine)
+    monkeypatch.setenv("SMX_CHAIN", "host")
+    host = sm.align_all(plasmids, reads, params, True, engine=engine)
+    assert np.array_equal(dev.status, host.status)
+    assert np.array_equal(dev.score, host.score)
+    assert np.array_equal(dev.new_query_seq_offset, host.new_query_seq_offset)
+    assert np.array_equal(dev.cigar_off, host.cigar_off) and np.array_equal(dev.cigar_rle, host.cigar_rle)
