@@ -169,8 +169,9 @@ def run_engine(args, rank, world, local_rank):
     reads = [r.upper() for r in reads]
     in_bytes = sum(len(p) for p in refs) + sum(len(r) for r in reads)
 
-    def step():
-        return sm.align_all(refs, reads, PARAMS, True, engine=eng, n_threads=n_threads, batch_queries=args.batch, overlap=args.overlap)
+    def step(overlap=None):
+        return sm.align_all(refs, reads, PARAMS, True, engine=eng, n_threads=n_threads, batch_queries=args.batch,
+                            overlap=args.overlap if overlap is None else overlap)
 
     for _ in range(args.warmup):
         step()
@@ -192,24 +193,34 @@ def run_engine(args, rank, world, local_rank):
     if dist is not None:
         dist.barrier()
     cells = agg["dp_cells"]
+    timed_stats = agg
+    if args.overlap > 1:
+        # Device-time pass: with several batches in flight the CUDA-event intervals of one handle also contain
+        # the other handle's kernels, so the per-kernel times behind `value` and `roofline` come from one extra
+        # pass over the same inputs with the batches serialised (not part of the K timed steps).
+        one = step(overlap=1)
+        agg = {k: v * args.steps for k, v in one.stats.items()}
     dev_s = (agg["gpu_scan_ms"] + agg["gpu_select_ms"] + agg["gpu_dp_ms"]) * 1e-3
     if dist is not None:
         t = torch.tensor([wall, dev_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wall, dev_s = float(t[0]), float(t[1])
-        c = torch.tensor([cells, agg["scan_cells"], float(len(reads) * args.steps), agg["kernel_launches"]], device="cuda", dtype=torch.float64)
+        c = torch.tensor([cells, agg["scan_cells"], float(len(reads) * args.steps), timed_stats["kernel_launches"]], device="cuda", dtype=torch.float64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         cells_all, scan_all, reads_all, launches_all = (float(x) for x in c)
     else:
-        cells_all, scan_all, reads_all, launches_all = cells, agg["scan_cells"], float(len(reads) * args.steps), agg["kernel_launches"]
+        cells_all, scan_all, reads_all, launches_all = cells, agg["scan_cells"], float(len(reads) * args.steps), timed_stats["kernel_launches"]
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # dominant kernel: forward DP, K = 8 rows per lane, global/semi-global: the CTA-per-problem (team) class 8
-    # carries the problems of more than 512 query rows, class 6 the warp-per-problem rest; both run the same loop
-    dom = 8 if agg["dp_ms_class8"] >= agg["dp_ms_class6"] else 6
+    # dominant kernel = the forward DP class with the largest device time.  Classes: 6 = int32 warp-per-problem K=8,
+    # 8 = int32 CTA-per-problem, 10..13 = packed s16x2 with 1/2/4/8 warps per problem (two cells per DPX lane-instruction).
+    names = {6: "smx_dp_forward<K=8,int32,warp-per-problem>", 8: "smx_dp_forward<K=8,int32,CTA-per-problem>",
+             10: "smx_dp_forward16<W=1> (s16x2, warp per problem)", 11: "smx_dp_forward16<W=2> (s16x2, 2 warps per problem)",
+             12: "smx_dp_forward16<W=4> (s16x2, 4 warps per problem)", 13: "smx_dp_forward16<W=8> (s16x2, 8 warps per problem)"}
+    dom = max(names, key=lambda c: agg[f"dp_ms_class{c}"])
     k8_ms = agg[f"dp_ms_class{dom}"]
     k8_cells = agg[f"dp_cells_class{dom}"]
     peak = eng.measure_int_peak(3000)
@@ -219,7 +230,7 @@ def run_engine(args, rank, world, local_rank):
     n_launch_k8 = max(1, int(agg[f"dp_launches_{dom}"]))
     roofline = {
         "bound": "alu",  # int32 ALU / DPX issue rate binds this kernel, not HBM and not tensor cores
-        "kernel": f"smx_dp_forward<K=8,global,{'team' if dom == 8 else 'solo'}> (forward affine-gap DP with packed direction bits)",
+        "kernel": names[dom] + " -- forward affine-gap DP with packed direction bits",
         "achieved": k8_tcups * OPS_PER_CELL_TRACE, "peak": int_peak_tops, "unit": "Tops/s (int32 lane-instructions)",
         "frac": k8_tcups * OPS_PER_CELL_TRACE / int_peak_tops if int_peak_tops else None,
         "peak_source": "measured live by smx_measure_int_peak (dependency-free VIADDMNMX / VIMNMX3 chains on all SMs)",
@@ -250,9 +261,13 @@ def run_engine(args, rank, world, local_rank):
                 "note": "smx_pipeline_run from host buffers: pool upload, descriptors, region lists, CIGAR runs and results cross PCIe inside the timed region"},
         "reads_per_s_device": reads_all / dev_s, "scan_gcups_device": scan_all / (agg["gpu_scan_ms"] * 1e-3) / 1e9 if agg["gpu_scan_ms"] else None,
         "device_ms_per_step": 1e3 * dev_s / args.steps,
+        "device_timing": "CUDA events on the engine stream, one extra serialised pass" if args.overlap > 1 else "CUDA events on the engine stream, timed steps",
         "stage_seconds_per_step_rank0": {k: agg[k] / args.steps for k in ("t_pool", "t_scan", "t_select", "t_chain", "t_dp", "t_stitch", "t_total")},
-        "kernel_ms_per_step_rank0": {"scan": agg["gpu_scan_ms"] / args.steps, "select": agg["gpu_select_ms"] / args.steps,
-                                     "dp_all": agg["gpu_dp_ms"] / args.steps, "dp_forward_k8_team": agg["dp_ms_class8"] / args.steps,
+        "stage_seconds_per_step_rank0_overlapped": {k: timed_stats[k] / args.steps for k in ("t_pool", "t_scan", "t_select", "t_chain", "t_dp", "t_stitch", "t_total")},
+        "kernel_ms_per_step_rank0": {"scan": agg["gpu_scan_ms"] / args.steps, "select_and_chain": agg["gpu_select_ms"] / args.steps,
+                                     "dp_all": agg["gpu_dp_ms"] / args.steps, "dp_forward16_w8": agg["dp_ms_class13"] / args.steps, "dp_forward16_w4": agg["dp_ms_class12"] / args.steps,
+                                     "dp_forward16_w2": agg["dp_ms_class11"] / args.steps, "dp_forward16_w1": agg["dp_ms_class10"] / args.steps,
+                                     "dp_forward_k8_team": agg["dp_ms_class8"] / args.steps,
                                      "dp_forward_k8_solo": agg["dp_ms_class6"] / args.steps,
                                      "dp_forward_k4": agg["dp_ms_class4"] / args.steps, "dp_forward_k2": agg["dp_ms_class2"] / args.steps,
                                      "dp_forward_k1": agg["dp_ms_class0"] / args.steps, "traceback": agg["dp_ms_traceback"] / args.steps,

@@ -94,10 +94,12 @@ int64_t smx_align_cells(const smx_handle *h);
 int32_t smx_last_run_launches(const smx_handle *h);
 
 /* device milliseconds per kernel of the last smx_align_run, measured with CUDA events on the engine's
- * stream.  Forward DP kernel classes c: kshift*2 + local for the warp-per-problem kernels (K = 1 << kshift
- * rows per lane, c = 0..7) and 8 + local for the CTA-per-problem kernel that takes problems of more than
- * 512 query rows; ms12[10] = traceback, ms12[11] = CIGAR compaction; cells10[c] = DP cells per class. */
-int smx_align_kernel_ms(const smx_handle *h, double *ms12, int64_t *cells10);
+ * stream.  Forward DP kernel classes c: kshift*2 + local for the int32 warp-per-problem kernels (K = 1 << kshift
+ * rows per lane, c = 0..7), 8 + local for the int32 CTA-per-problem kernel (more than 512 query rows), 10..13 =
+ * packed s16x2 kernel with 1 / 2 / 4 / 8 warps per problem (two bands per warp; problems of more than 256 rows
+ * whose score range fits 16 bits and whose reference slice is pure ACGT); ms16[14] = traceback, ms16[15] = CIGAR
+ * compaction; cells14[c] = DP cells per class.  SMX_S16=0 in the environment keeps everything on int32. */
+int smx_align_kernel_ms(const smx_handle *h, double *ms16, int64_t *cells14);
 
 /* diagnostic: raw copy of the first nbytes of the direction-bit arena of the last chunk */
 int smx_debug_copy_trace(smx_handle *h, uint8_t *dst, int64_t nbytes);
@@ -145,8 +147,8 @@ int smx_pipeline_fetch(smx_handle *h, int32_t *score, int32_t *new_query_seq_off
                        int64_t *cigar_off, uint32_t *cigar_rle, int64_t cigar_capacity);
 /* out[0..16]: t_total, t_pool, t_scan, t_select, t_chain, t_dp, t_stitch (host seconds), gpu_scan_ms,
  * gpu_select_ms, gpu_dp_ms, scan_cells, dp_cells, n_dp_problems, n_host_redecisions, n_failed,
- * kernel_launches, n_pair_strands, then out[17..28] = smx_align_kernel_ms ms12 of the DP run,
- * out[29..38] = its cells10, out[39..50] = launches per kernel (same order as ms12) */
+ * kernel_launches, n_pair_strands, then out[17..32] = smx_align_kernel_ms ms16 of the DP run,
+ * out[33..46] = its cells14, out[47..62] = launches per kernel (same order as ms16) */
 int smx_pipeline_stats(smx_handle *h, double *out, int32_t n);
 
 /* ---- measurement helper: dependency-free int32 / DPX issue-rate microbenchmark ---------------

@@ -7,11 +7,13 @@
 #include <new>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/smx.h"
 #include "smx_common.cuh"
 #include "smx_dp.cuh"
+#include "smx_dp16.cuh"
 #include "smx_scan.cuh"
 #include "smx_traceback.cuh"
 
@@ -24,7 +26,7 @@ struct DevBuf {
 
 struct Chunk {
     int first = 0, count = 0;            // range in the size-sorted order
-    int cls_first[10] = {0}, cls_count[10] = {0};  // per kernel class ranges inside order_cls (see problem_class)
+    int cls_first[14] = {0}, cls_count[14] = {0};  // per kernel class ranges inside order_cls (see problem_class)
     size_t trace_bytes = 0;
 };
 
@@ -37,19 +39,22 @@ struct smx_handle {
     int sm_count = 148;
     std::string err;
     int64_t trace_budget = (int64_t)24 << 30;
+    bool use_s16 = true;  // SMX_S16=0 forces the int32 kernels (cross-check)
+    int s16_max_wsel = 1;  // warps per problem of the s16 kernel are capped at 2 (measured best); SMX_S16_MAXW=1|2|4|8 overrides
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
     int last_launches = 0;
-    // per-kernel timing of the last smx_align_run: [0..9] forward classes (problem_class), [10] traceback, [11] compaction
+    // per-kernel timing of the last smx_align_run: [0..13] forward classes (problem_class), [14] traceback, [15] compaction
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_tag;
     size_t ev_used = 0;
-    double kernel_ms[12] = {0};
-    int kernel_launches[12] = {0};
-    int64_t class_cells[10] = {0};
+    double kernel_ms[16] = {0};
+    int kernel_launches[16] = {0};
+    int64_t class_cells[14] = {0};
 
     DevBuf pool;
     int64_t pool_len = 0;
+    std::vector<int32_t> pool_nonacgt;  // prefix count of bytes other than A/C/G/T (s16 kernel eligibility)
 
     // align state
     int32_t n = 0;
@@ -210,14 +215,36 @@ extern "C" int smx_pool_upload(smx_handle *h, const uint8_t *seqs, int64_t n)
     SMX_CUDA(h, cudaMemcpyAsync(h->pool.p, seqs, (size_t)n, cudaMemcpyHostToDevice, h->stream));
     SMX_CUDA(h, cudaStreamSynchronize(h->stream));
     h->pool_len = n;
+    // per 64-byte block: does it hold a byte other than A/C/G/T?  prefix over blocks (s16 kernel eligibility)
+    {
+        const int64_t nb = (n + 63) / 64;
+        h->pool_nonacgt.assign((size_t)nb + 1, 0);
+        std::vector<uint8_t> flag((size_t)nb, 0);
+        const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t)
+            th.emplace_back([&, t]() {
+                for (int64_t b = t; b < nb; b += nt) {
+                    const int64_t lo = b * 64, hi = std::min(n, lo + 64);
+                    uint8_t f = 0;
+                    for (int64_t i = lo; i < hi; ++i) { const uint8_t c = seqs[i]; f |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T'); }
+                    flag[(size_t)b] = f;
+                }
+            });
+        for (auto &x : th) x.join();
+        int32_t acc = 0;
+        for (int64_t b = 0; b < nb; ++b) { acc += flag[(size_t)b]; h->pool_nonacgt[(size_t)b + 1] = acc; }
+    }
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
 // A8: batched DP
 // ------------------------------------------------------------------------------------------------
-// kernel class of a problem: kshift * 2 + local for warp-per-problem kernels (K = 1 << kshift rows per
-// lane), 8 + local for the CTA-per-problem (team) kernel that takes every problem of 3 or more bands
+// kernel class of a problem: kshift * 2 + local for the int32 warp-per-problem kernels (K = 1 << kshift rows per
+// lane), 8 + local for the int32 CTA-per-problem (team) kernel that takes every problem of 3 or more bands,
+// 10..13 for the packed s16x2 kernel with 1, 2, 4, 8 warps per problem
+enum { kClsS16 = 10, kNumFwdClasses = 14, kSlotTraceback = 14, kSlotCompact = 15, kNumSlots = 16 };
 static const int kTeamMinRows = 513;
 static int problem_class(int m, int mode);
 static int pick_kshift(int m)
@@ -233,6 +260,20 @@ static int problem_class(int m, int mode)
     const int local = mode == SMX_MODE_SW ? 1 : 0;
     if (m >= kTeamMinRows) return 8 + local;
     return pick_kshift(m) * 2 + local;
+}
+
+// classes 10 (warp per problem) and 11 (CTA per problem): packed s16x2 kernel, smx_dp16.cuh
+static bool s16_eligible(const smx_handle *h, int64_t s2_off, int m, int n, int mode)
+{
+    if (mode == SMX_MODE_SW || m <= 256) return false;
+    const SmxScoring &sc = h->sc;
+    if (sc.go > 256 || sc.ge > 256) return false;
+    const int64_t m_pad = (int64_t)(((m + 255) / 256 + 1) / 2) * 512;
+    if ((int64_t)sc.go * 3 + (int64_t)sc.ge * (m_pad + n) + 256 > 31000) return false;
+    if ((int64_t)std::max(sc.match, 0) * std::min(m, n) > 31000) return false;
+    // conservative at block granularity: every 64-byte block the slice touches must be pure ACGT
+    const int64_t b0 = s2_off / 64, b1 = (s2_off + n - 1) / 64 + 1;
+    return h->pool_nonacgt[(size_t)b1] - h->pool_nonacgt[(size_t)b0] == 0;
 }
 
 static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_t *s1_len, const int64_t *s2_off,
@@ -262,7 +303,14 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
     h->sc = SmxScoring{open, extend, match, mismatch};
     h->probs.resize((size_t)n);
     h->cells = 0;
-    for (int c = 0; c < 10; ++c) h->class_cells[c] = 0;
+    for (int c = 0; c < kNumFwdClasses; ++c) h->class_cells[c] = 0;
+    {
+        const char *env = getenv("SMX_S16");
+        h->use_s16 = !(env && env[0] == '0');
+        const char *mw = getenv("SMX_S16_MAXW");
+        h->s16_max_wsel = 1;
+        if (mw) { const int v = atoi(mw); h->s16_max_wsel = v >= 8 ? 3 : v >= 4 ? 2 : v >= 2 ? 1 : 0; }
+    }
     h->nmax = 1;
     int64_t runs_off = 0;
     for (int p = 0; p < n; ++p) {
@@ -282,7 +330,14 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
             q.mode |= SMX_MODE_CLIP;
         }
         q.kshift = pick_kshift(m);
-        h->class_cells[problem_class(m, mode[p])] += (int64_t)m * nn;
+        q.cls = problem_class(m, mode[p]);
+        if (h->use_s16 && s16_eligible(h, s2_off[p], m, nn, mode[p])) {
+            const int pairs = ((m + 255) / 256 + 1) / 2;
+            int wsel = pairs >= 8 ? 3 : pairs >= 4 ? 2 : pairs >= 2 ? 1 : 0;
+            if (wsel > h->s16_max_wsel) wsel = h->s16_max_wsel;
+            q.cls = (int16_t)(kClsS16 + wsel);
+        }
+        h->class_cells[q.cls] += (int64_t)m * nn;
         q.trace_off = 0;
         q.cigar_off = runs_off;
         runs_off += (int64_t)m + nn + 2;
@@ -318,12 +373,11 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         h->max_chunk_trace = std::max(h->max_chunk_trace, bytes);
         // class lists (stable: keeps largest-first inside each class)
         int w = c.first;
-        for (int cls = 9; cls >= 0; --cls) {
+        for (int cls = kNumFwdClasses - 1; cls >= 0; --cls) {
             c.cls_first[cls] = w;
             for (int x = c.first; x < c.first + c.count; ++x) {
                 const SmxProblem &q = h->probs[(size_t)order[x]];
-                const int qc = problem_class(q.m, q.mode & SMX_MODE_MASK);
-                if (qc == cls) h->order_cls[(size_t)w++] = order[x];
+                if (q.cls == cls) h->order_cls[(size_t)w++] = order[x];
             }
             c.cls_count[cls] = w - c.cls_first[cls];
         }
@@ -337,7 +391,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
     if (int rc = ensure(h, h->d_trace, h->max_chunk_trace + 256)) return rc;
     if (int rc = ensure(h, h->d_runs, sizeof(uint32_t) * (size_t)h->runs_scratch)) return rc;
     if (int rc = ensure(h, h->d_dense_off, sizeof(int64_t) * ((size_t)n + 1))) return rc;
-    if (int rc = ensure(h, h->d_tickets, sizeof(int32_t) * 10 * h->chunks.size())) return rc;
+    if (int rc = ensure(h, h->d_tickets, sizeof(int32_t) * kNumFwdClasses * h->chunks.size())) return rc;
     SMX_CUDA(h, cudaMemcpyAsync(h->d_probs.p, h->probs.data(), sizeof(SmxProblem) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     SMX_CUDA(h, cudaMemcpyAsync(h->d_order_cls.p, h->order_cls.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
     SMX_CUDA(h, cudaMemcpyAsync(h->d_order_all.p, h->order_all.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
@@ -365,13 +419,45 @@ static int launch_forward(smx_handle *h, const Chunk &c, int cls, int chunk_idx)
     a.probs = (const SmxProblem *)h->d_probs.p;
     a.order = (const int32_t *)h->d_order_cls.p + c.cls_first[cls];
     a.n_order = count;
-    a.ticket = (int32_t *)h->d_tickets.p + chunk_idx * 10 + cls;
+    a.ticket = (int32_t *)h->d_tickets.p + chunk_idx * kNumFwdClasses + cls;
     a.trace = (uint8_t *)h->d_trace.p;
     a.boundary = (int2 *)h->d_boundary.p;
     a.nmax = h->nmax;
     a.results = (SmxResult *)h->d_results.p;
     a.sc = h->sc;
     smx_dp_forward<K, LOCAL, TEAM><<<blocks, threads, 0, h->stream>>>(a);
+    SMX_CUDA(h, cudaGetLastError());
+    h->last_launches++;
+    return mark(h, cls);
+}
+
+template <int W>
+static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_idx)
+{
+    const int count = c.cls_count[cls];
+    if (count == 0) return 0;
+    const bool TEAM = W > 1;
+    const int threads = TEAM ? W * 32 : 128;
+    int occ = 0;
+    SMX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, smx_dp_forward16<W>, threads, 0));
+    if (occ < 1) occ = 1;
+    const int per_block = TEAM ? 1 : threads / 32;
+    int blocks = std::min(h->sm_count * occ, (count + per_block - 1) / per_block);
+    if (blocks < 1) blocks = 1;
+    const size_t workers = TEAM ? (size_t)blocks : (size_t)blocks * (threads / 32);
+    if (int rc = ensure(h, h->d_boundary, sizeof(int2) * 2 * (size_t)h->nmax * workers)) return rc;
+    SmxFwdArgs a;
+    a.pool = (const uint8_t *)h->pool.p;
+    a.probs = (const SmxProblem *)h->d_probs.p;
+    a.order = (const int32_t *)h->d_order_cls.p + c.cls_first[cls];
+    a.n_order = count;
+    a.ticket = (int32_t *)h->d_tickets.p + chunk_idx * kNumFwdClasses + cls;
+    a.trace = (uint8_t *)h->d_trace.p;
+    a.boundary = (int2 *)h->d_boundary.p;
+    a.nmax = h->nmax;
+    a.results = (SmxResult *)h->d_results.p;
+    a.sc = h->sc;
+    smx_dp_forward16<W><<<blocks, threads, 0, h->stream>>>(a);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
     return mark(h, cls);
@@ -391,13 +477,17 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
         if (int rc = ensure(h, h->d_boundary, line_bytes)) return rc;
     }
     SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    SMX_CUDA(h, cudaMemsetAsync(h->d_tickets.p, 0, sizeof(int32_t) * 10 * h->chunks.size(), h->stream));
+    SMX_CUDA(h, cudaMemsetAsync(h->d_tickets.p, 0, sizeof(int32_t) * kNumFwdClasses * h->chunks.size(), h->stream));
     h->ev_used = 0;
-    for (int c = 0; c < 12; ++c) { h->kernel_ms[c] = 0.0; h->kernel_launches[c] = 0; }
+    for (int c = 0; c < kNumSlots; ++c) { h->kernel_ms[c] = 0.0; h->kernel_launches[c] = 0; }
     if (int rc = mark(h, -1)) return rc;
     for (size_t ci = 0; ci < h->chunks.size(); ++ci) {
         const Chunk &c = h->chunks[ci];
         int rc = 0;
+        if ((rc = launch_forward16<8>(h, c, kClsS16 + 3, (int)ci))) return rc;
+        if ((rc = launch_forward16<4>(h, c, kClsS16 + 2, (int)ci))) return rc;
+        if ((rc = launch_forward16<2>(h, c, kClsS16 + 1, (int)ci))) return rc;
+        if ((rc = launch_forward16<1>(h, c, kClsS16, (int)ci))) return rc;
         if ((rc = launch_forward<8, false, true>(h, c, 8, (int)ci))) return rc;
         if ((rc = launch_forward<8, true, true>(h, c, 9, (int)ci))) return rc;
         if ((rc = launch_forward<8, false, false>(h, c, 6, (int)ci))) return rc;
@@ -420,7 +510,7 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
         smx_traceback<<<(c.count + 127) / 128, 128, 0, h->stream>>>(t);
         SMX_CUDA(h, cudaGetLastError());
         h->last_launches++;
-        if (int rc2 = mark(h, 10)) return rc2;
+        if (int rc2 = mark(h, kSlotTraceback)) return rc2;
     }
     SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     // results header to host: run counts -> dense offsets -> compaction
@@ -441,7 +531,7 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
                                                                         (uint32_t *)h->d_dense.p, h->n);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
-    if (int rc = mark(h, 11)) return rc;
+    if (int rc = mark(h, kSlotCompact)) return rc;
     SMX_CUDA(h, cudaStreamSynchronize(h->stream));
     for (size_t i = 1; i < h->ev_used; ++i) {
         if (h->ev_tag[i] < 0) continue;
@@ -486,11 +576,11 @@ extern "C" int smx_debug_copy_trace(smx_handle *h, uint8_t *dst, int64_t nbytes)
     return 0;
 }
 
-extern "C" int smx_align_kernel_ms(const smx_handle *h, double *ms12, int64_t *cells10)
+extern "C" int smx_align_kernel_ms(const smx_handle *h, double *ms16, int64_t *cells14)
 {
     if (!h) return -1;
-    if (ms12) for (int c = 0; c < 12; ++c) ms12[c] = h->kernel_ms[c];
-    if (cells10) for (int c = 0; c < 10; ++c) cells10[c] = h->class_cells[c];
+    if (ms16) for (int c = 0; c < kNumSlots; ++c) ms16[c] = h->kernel_ms[c];
+    if (cells14) for (int c = 0; c < kNumFwdClasses; ++c) cells14[c] = h->class_cells[c];
     return 0;
 }
 
@@ -1016,9 +1106,9 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         int64_t truns = 0;
         if (int rc = smx_align_run(h, &truns)) return rc;
         st.gpu_dp_ms = h->last_ms; st.dp_cells = h->cells; st.launches += h->last_launches;
-        for (int c = 0; c < 12; ++c) st.dp_kernel_ms[c] = h->kernel_ms[c];
-        for (int c = 0; c < 10; ++c) st.dp_class_cells[c] = h->class_cells[c];
-        for (int c = 0; c < 12; ++c) st.dp_kernel_launches[c] = h->kernel_launches[c];
+        for (int c = 0; c < 16; ++c) st.dp_kernel_ms[c] = h->kernel_ms[c];
+        for (int c = 0; c < 14; ++c) st.dp_class_cells[c] = h->class_cells[c];
+        for (int c = 0; c < 16; ++c) st.dp_kernel_launches[c] = h->kernel_launches[c];
         cg.resize((size_t)std::max<int64_t>(truns, 1));
         if (int rc = smx_align_fetch(h, nullptr, nullptr, nullptr, nullptr, nullptr, cg_off.data(), cg.data(), (int64_t)cg.size())) return rc;
     }
@@ -1109,9 +1199,9 @@ extern "C" int smx_pipeline_stats(smx_handle *h, double *out, int32_t n)
     const int m = (int)(sizeof(v) / sizeof(v[0]));
     for (int i = 0; i < n; ++i) {
         if (i < m) out[i] = v[i];
-        else if (i < m + 12) out[i] = st.dp_kernel_ms[i - m];
-        else if (i < m + 22) out[i] = (double)st.dp_class_cells[i - m - 12];
-        else if (i < m + 34) out[i] = (double)st.dp_kernel_launches[i - m - 22];
+        else if (i < m + 16) out[i] = st.dp_kernel_ms[i - m];
+        else if (i < m + 30) out[i] = (double)st.dp_class_cells[i - m - 16];
+        else if (i < m + 46) out[i] = (double)st.dp_kernel_launches[i - m - 30];
         else out[i] = 0.0;
     }
     return 0;

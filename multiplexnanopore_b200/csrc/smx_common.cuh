@@ -13,7 +13,8 @@ struct SmxProblem {
     int32_t m;          // query length  (rows)
     int32_t n;          // reference length (columns)
     int32_t mode;       // SMX_MODE_*
-    int32_t kshift;     // log2(rows per lane) of its kernel class: K = 1 << kshift
+    int16_t kshift;     // log2(rows per lane) of its kernel class: K = 1 << kshift
+    int16_t cls;        // forward kernel class (host planning only)
     int64_t trace_off;  // byte offset of its packed direction bits in the trace arena
     int64_t cigar_off;  // offset (in uint32 runs) of its scratch run buffer
 };

@@ -60,6 +60,15 @@ __device__ __forceinline__ int smx_subst(uint32_t profile, uint32_t sel)
     return r;
 }
 
+// both halves at once: low 16 bits from the profile of the low row (bytes 0-3), high 16 bits from the profile
+// of the high row (bytes 4-7); selector built per column by smx_dp_forward16
+__device__ __forceinline__ uint32_t smx_subst_u(uint32_t profile_lo, uint32_t profile_hi, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(profile_lo), "r"(profile_hi), "r"(sel));
+    return r;
+}
+
 struct SmxFwdArgs {
     const uint8_t *pool;
     const SmxProblem *probs;

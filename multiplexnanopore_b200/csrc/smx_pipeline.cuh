@@ -128,8 +128,8 @@ struct SmxPipelineState {
     double gpu_scan_ms = 0, gpu_select_ms = 0, gpu_dp_ms = 0, gpu_chain_ms = 0;
     int64_t scan_cells = 0, dp_cells = 0, n_dp = 0, n_host_redo = 0, n_failed = 0;
     int launches = 0;
-    double dp_kernel_ms[12] = {0};
-    int64_t dp_class_cells[10] = {0};
-    int dp_kernel_launches[12] = {0};
+    double dp_kernel_ms[16] = {0};
+    int64_t dp_class_cells[14] = {0};
+    int dp_kernel_launches[16] = {0};
     bool valid = false;
 };

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(128) smx_traceback(const SmxTbArgs a)
     const int m = pr.m, n = pr.n;
     const int mode = pr.mode & SMX_MODE_MASK;
     const bool local = mode == SMX_MODE_SW;
+    const bool enc16 = pr.cls >= 10;
 
     SmxWalk w;
     w.out = a.runs + pr.cigar_off; w.nruns = 0; w.cur_op = 0; w.cur_len = 0;
@@ -132,7 +133,9 @@ __global__ void __launch_bounds__(128) smx_traceback(const SmxTbArgs a)
         }
         const uint32_t nib = smx_trace_nibble(tr, n, pr.kshift, i, j);
         if (where == 0) {
-            const uint32_t src = nib & 3u;
+            // int32 kernels store the H source as a 2-bit code; the s16x2 kernels (classes >= 10) store
+            // "diagonal lost" in bit 0 and "E beat F" in bit 1 (smx_dp16.cuh)
+            const uint32_t src = enc16 ? (!(nib & 1u) ? SMX_SRC_DIAG : ((nib & 2u) ? SMX_SRC_INS : SMX_SRC_DEL)) : (nib & 3u);
             if (src == SMX_SRC_DIAG) {
                 w.emit(s1[i] == s2[j] ? SMX_OP_EQ : SMX_OP_X, 1);
                 --i; --j;

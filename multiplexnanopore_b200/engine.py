@@ -148,10 +148,11 @@ class Engine:
         return self.align_fetch()
 
     def align_kernel_ms(self) -> tuple[np.ndarray, np.ndarray]:
-        """(ms[12], cells[10]) of the last align run: forward classes (0..7 warp-per-problem kshift*2+local,
-        8/9 CTA-per-problem global/local), traceback, compaction."""
-        ms = np.zeros(12, dtype=np.float64)
-        cells = np.zeros(10, dtype=np.int64)
+        """(ms[16], cells[14]) of the last align run: forward classes (0..7 int32 warp-per-problem kshift*2+local,
+        8/9 int32 CTA-per-problem global/local, 10..13 packed s16x2 with 1/2/4/8 warps per problem), traceback,
+        compaction."""
+        ms = np.zeros(16, dtype=np.float64)
+        cells = np.zeros(14, dtype=np.int64)
         self._check(self._lib.smx_align_kernel_ms(self._h, _ptr(ms), _ptr(cells)), "smx_align_kernel_ms")
         return ms, cells
 
@@ -231,8 +232,8 @@ class PipelineResult:
 
 _STAT_KEYS = ("t_total", "t_pool", "t_scan", "t_select", "t_chain", "t_dp", "t_stitch", "gpu_scan_ms", "gpu_select_ms",
               "gpu_dp_ms", "scan_cells", "dp_cells", "n_dp_problems", "n_host_redecisions", "n_failed", "kernel_launches",
-              "n_pair_strands") + tuple(f"dp_ms_class{c}" for c in range(10)) + ("dp_ms_traceback", "dp_ms_compact") \
-    + tuple(f"dp_cells_class{c}" for c in range(10)) + tuple(f"dp_launches_{c}" for c in range(12))
+              "n_pair_strands") + tuple(f"dp_ms_class{c}" for c in range(14)) + ("dp_ms_traceback", "dp_ms_compact") \
+    + tuple(f"dp_cells_class{c}" for c in range(14)) + tuple(f"dp_launches_{c}" for c in range(16))
 
 
 def _pack(seqs):
