@@ -24,6 +24,13 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+// page-locked host staging (grow-only): large D2H / H2D copies run at PCIe speed instead of through the
+// driver's pageable bounce buffers
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
 struct Chunk {
     int first = 0, count = 0;            // range in the size-sorted order
     int cls_first[14] = {0}, cls_count[14] = {0};  // per kernel class ranges inside order_cls (see problem_class)
@@ -82,6 +89,7 @@ struct smx_handle {
     DevBuf d_sel_pairs, d_sel_out, d_regions;
     DevBuf d_chain_tasks, d_chain_regions, d_chain_traces, d_chain_out;
     std::vector<uint8_t> host_pool;
+    PinBuf pin_regions, pin_cigar, pin_pool;
     struct SmxPipelineState *pipe = nullptr;
 };
 
@@ -116,6 +124,17 @@ static int ensure(smx_handle *h, DevBuf &b, size_t bytes)
         e = cudaMalloc(&b.p, want);
     }
     if (e != cudaSuccess) { b.p = nullptr; return fail(h, -3, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e)); }
+    b.cap = want;
+    return 0;
+}
+
+static int ensure_pinned(smx_handle *h, PinBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return 0;
+    if (b.p) { cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+    const size_t want = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { b.p = nullptr; return fail(h, -3, "cudaHostAlloc(%zu bytes) failed: %s", want, cudaGetErrorString(e)); }
     b.cap = want;
     return 0;
 }
@@ -190,6 +209,7 @@ extern "C" void smx_destroy(smx_handle *h)
                       &h->d_sel_pairs, &h->d_sel_out, &h->d_regions, &h->d_chain_tasks, &h->d_chain_regions, &h->d_chain_traces,
                       &h->d_chain_out};
     smx_pipeline_free(h);
+    for (PinBuf *b : {&h->pin_regions, &h->pin_cigar, &h->pin_pool}) if (b->p) cudaFreeHost(b->p);
     for (DevBuf *b : bufs) release(*b);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -739,7 +759,7 @@ extern "C" int smx_measure_int_peak(smx_handle *h, int32_t iters, double *out_go
 
 namespace {
 
-const int kRegionCap = 256;                 // device slots per pair-strand (overflow -> host re-decision)
+const int kRegionCap = SMX_SEL_REGION_CAP;   // device slots per pair-strand (overflow -> host re-decision)
 const int64_t kCountsBudget = 400ll << 20;  // int32 diagonal counts kept on the device per chunk
 
 uint8_t g_comp[256];
@@ -789,7 +809,8 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         qpool[(size_t)q * 2 + 1] = total; total += 2ll * qry_len[q];
     }
     {
-        std::vector<uint8_t> pool((size_t)total);
+        if (int rc = ensure_pinned(h, h->pin_pool, (size_t)total)) return rc;
+        uint8_t *pool = (uint8_t *)h->pin_pool.p;
         for (int r = 0; r < n_refs; ++r) {
             const uint8_t *s = ref_seqs + ref_off[r];
             memcpy(&pool[(size_t)rpool[(size_t)r]], s, (size_t)ref_len[r]);
@@ -803,9 +824,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
             for (int i = 0; i < L; ++i) c[i] = g_comp[s[L - 1 - i]];
             memcpy(c + L, c, (size_t)L);
         });
-        if (int rc = smx_pool_upload(h, pool.data(), total)) return rc;
-        // keep a host copy for the rare host re-decisions
-        h->host_pool.swap(pool);
+        if (int rc = smx_pool_upload(h, pool, total)) return rc;  // the pinned copy stays for the rare host re-decisions
     }
     st.t_pool = now_s() - t_begin;
 
@@ -835,7 +854,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     std::vector<int32_t> s_rlen, s_qlen;
     std::vector<SmxSelPair> sel_pairs;
     std::vector<SmxSelOut> sel_out;
-    std::vector<SmxRegion> reg_host, redo;
+    std::vector<SmxRegion> redo;
     std::vector<int32_t> counts_host;
     while (pos < active.size()) {
         size_t end = pos;
@@ -872,31 +891,39 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         }
         if (int rc = ensure(h, h->d_sel_pairs, sizeof(SmxSelPair) * (size_t)n)) return rc;
         if (int rc = ensure(h, h->d_sel_out, sizeof(SmxSelOut) * (size_t)n)) return rc;
-        if (int rc = ensure(h, h->d_regions, sizeof(SmxRegion) * (size_t)n * kRegionCap)) return rc;
+        if (int rc = ensure(h, h->d_regions, sizeof(SmxRegion) * (size_t)n * kRegionCap + 64)) return rc;
+        int32_t *d_region_counter = (int32_t *)((char *)h->d_regions.p + sizeof(SmxRegion) * (size_t)n * kRegionCap);
+        SMX_CUDA(h, cudaMemsetAsync(d_region_counter, 0, sizeof(int32_t), h->stream));
         SMX_CUDA(h, cudaMemcpyAsync(h->d_sel_pairs.p, sel_pairs.data(), sizeof(SmxSelPair) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
         SmxSelArgs sa;
         sa.pool = (const uint8_t *)h->pool.p; sa.pairs = (const SmxSelPair *)h->d_sel_pairs.p; sa.counts = (const int32_t *)h->d_counts.p;
-        sa.regions = (SmxRegion *)h->d_regions.p; sa.out = (SmxSelOut *)h->d_sel_out.p; sa.topology = topology;
+        sa.regions = (SmxRegion *)h->d_regions.p; sa.out = (SmxSelOut *)h->d_sel_out.p; sa.region_counter = d_region_counter; sa.topology = topology;
         SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
         smx_select_kernel<<<n, SMX_SEL_THREADS, 0, h->stream>>>(sa);
         SMX_CUDA(h, cudaGetLastError());
         SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
         st.launches += 1;
-        reg_host.resize((size_t)n * kRegionCap);
+        int32_t n_regions_total = 0;
         SMX_CUDA(h, cudaMemcpyAsync(sel_out.data(), h->d_sel_out.p, sizeof(SmxSelOut) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
-        SMX_CUDA(h, cudaMemcpyAsync(reg_host.data(), h->d_regions.p, sizeof(SmxRegion) * (size_t)n * kRegionCap, cudaMemcpyDeviceToHost, h->stream));
+        SMX_CUDA(h, cudaMemcpyAsync(&n_regions_total, d_region_counter, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
         SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (int rc = ensure_pinned(h, h->pin_regions, sizeof(SmxRegion) * (size_t)std::max(n_regions_total, 1))) return rc;
+        SmxRegion *reg_host = (SmxRegion *)h->pin_regions.p;
+        if (n_regions_total > 0) {
+            SMX_CUDA(h, cudaMemcpyAsync(reg_host, h->d_regions.p, sizeof(SmxRegion) * (size_t)n_regions_total, cudaMemcpyDeviceToHost, h->stream));
+            SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+        }
         { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1); st.gpu_select_ms += ms; }
         for (int i = 0; i < n; ++i) {
             PairStrand &x = st.ps[(size_t)active[pos + i]];
             const SmxSelOut &o = sel_out[i];
-            const SmxRegion *rg = &reg_host[(size_t)i * kRegionCap];
+            const SmxRegion *rg = &reg_host[(size_t)o.region_base];
             int nreg = o.n_regions;
             if (o.flags) {  // ambiguous threshold or overflow: decide on the host from this pair-strand's counts
                 const SmxSelPair &s = sel_pairs[i];
                 counts_host.resize((size_t)s.max_k);
                 SMX_CUDA(h, cudaMemcpy(counts_host.data(), (const int32_t *)h->d_counts.p + s.counts_off, sizeof(int32_t) * (size_t)s.max_k, cudaMemcpyDeviceToHost));
-                host_regions(&h->host_pool[(size_t)x.ref_pool], &h->host_pool[(size_t)x.qry_pool], x.nr, x.nq, topology, counts_host.data(),
+                host_regions((const uint8_t *)h->pin_pool.p + x.ref_pool, (const uint8_t *)h->pin_pool.p + x.qry_pool, x.nr, x.nq, topology, counts_host.data(),
                              s.max_k, s.slice_lo, s.slice_hi, s.sigma, redo);
                 rg = redo.data(); nreg = (int)redo.size();
                 ++st.n_host_redo;
@@ -1099,7 +1126,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     t0 = now_s();
     const int n_prob = (int)p_m.size();
     std::vector<int64_t> cg_off((size_t)n_prob + 1, 0);
-    std::vector<uint32_t> cg;
+    uint32_t *cg = nullptr;
     st.n_dp = n_prob;
     if (n_prob > 0) {
         if (int rc = align_prepare_impl(h, p_s1.data(), p_m.data(), p_s2.data(), p_n.data(), p_mode.data(), p_clip.data(), n_prob, open, extend, match, mismatch)) return rc;
@@ -1109,8 +1136,9 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         for (int c = 0; c < 16; ++c) st.dp_kernel_ms[c] = h->kernel_ms[c];
         for (int c = 0; c < 14; ++c) st.dp_class_cells[c] = h->class_cells[c];
         for (int c = 0; c < 16; ++c) st.dp_kernel_launches[c] = h->kernel_launches[c];
-        cg.resize((size_t)std::max<int64_t>(truns, 1));
-        if (int rc = smx_align_fetch(h, nullptr, nullptr, nullptr, nullptr, nullptr, cg_off.data(), cg.data(), (int64_t)cg.size())) return rc;
+        if (int rc = ensure_pinned(h, h->pin_cigar, sizeof(uint32_t) * (size_t)std::max<int64_t>(truns, 1))) return rc;
+        cg = (uint32_t *)h->pin_cigar.p;
+        if (int rc = smx_align_fetch(h, nullptr, nullptr, nullptr, nullptr, nullptr, cg_off.data(), cg, std::max<int64_t>(truns, 1))) return rc;
     }
     st.t_dp = now_s() - t0;
 

@@ -13,6 +13,7 @@
 #define SMX_SEL_THREADS 256
 #define SMX_SEL_MAX_K 2048   // selected diagonals kept per pair-strand (overflow -> host path)
 #define SMX_RUN_MIN 20       // WindowAnalysis.consecutive_true_threshold
+#define SMX_SEL_REGION_CAP 256  // regions kept per pair-strand (overflow -> host path)
 
 struct SmxSelPair {
     int64_t ref_off, qry_off, counts_off, region_off;
@@ -25,7 +26,7 @@ struct SmxSelOut {
     int32_t n_regions;  // may exceed region_cap (then flagged)
     int32_t n_selected;
     int32_t flags;      // 1 = threshold ambiguous, 2 = selected overflow, 4 = region overflow
-    int32_t pad;
+    int32_t region_base;  // offset of this pair-strand's regions in the compact region array
 };
 
 struct SmxRegion { int32_t k, qs, qe; };
@@ -34,8 +35,9 @@ struct SmxSelArgs {
     const uint8_t *pool;
     const SmxSelPair *pairs;
     const int32_t *counts;
-    SmxRegion *regions;
+    SmxRegion *regions;   // compact: every CTA reserves its slots with one atomicAdd on *region_counter
     SmxSelOut *out;
+    int32_t *region_counter;
     int32_t topology;
 };
 
@@ -76,6 +78,8 @@ __global__ void __launch_bounds__(SMX_SEL_THREADS) smx_select_kernel(const SmxSe
     __shared__ int bcast[4];
     __shared__ long long red[2 * (SMX_SEL_THREADS / 32)];
     __shared__ int sel[SMX_SEL_MAX_K];
+    __shared__ SmxRegion s_regs[SMX_SEL_REGION_CAP];
+    __shared__ int s_base;
     __shared__ int n_sel, n_reg;
     __shared__ double thr_s;
 
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(SMX_SEL_THREADS) smx_select_kernel(const SmxSe
     const uint8_t *qry = a.pool + pr.qry_off;
     const int nr = pr.nr, nq = pr.nq;
     const bool linear = a.topology == 1;
-    SmxRegion *out = a.regions + pr.region_off;
+    SmxRegion *out = s_regs;
     for (int si = warp; si < nsel; si += SMX_SEL_THREADS / 32) {
         const int k = sel[si];
         int start = -1;  // lane 0: start of the open run
@@ -177,6 +181,10 @@ __global__ void __launch_bounds__(SMX_SEL_THREADS) smx_select_kernel(const SmxSe
         }
     }
     __syncthreads();
+    const int n_keep = min(n_reg, pr.region_cap);
+    if (tid == 0) s_base = n_keep > 0 ? atomicAdd(a.region_counter, n_keep) : 0;
+    __syncthreads();
+    for (int x = tid; x < n_keep; x += SMX_SEL_THREADS) a.regions[s_base + x] = s_regs[x];
     if (tid == 0) {
         SmxSelOut o;
         o.thr = thr;
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(SMX_SEL_THREADS) smx_select_kernel(const SmxSe
         o.n_selected = n_sel;
         if (n_reg > pr.region_cap) flags |= 4;
         o.flags = flags;
-        o.pad = 0;
+        o.region_base = s_base;
         a.out[blockIdx.x] = o;
     }
 }
