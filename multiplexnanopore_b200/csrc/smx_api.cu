@@ -87,7 +87,7 @@ struct smx_handle {
 
     // pipeline state (smx_pipeline.cuh)
     DevBuf d_sel_pairs, d_sel_out, d_regions;
-    DevBuf d_chain_tasks, d_chain_regions, d_chain_traces, d_chain_out;
+    DevBuf d_chain_tasks, d_chain_regions, d_chain_traces, d_chain_out, d_chain_scratch;
     std::vector<uint8_t> host_pool;
     PinBuf pin_regions, pin_cigar, pin_pool;
     struct SmxPipelineState *pipe = nullptr;
@@ -207,7 +207,7 @@ extern "C" void smx_destroy(smx_handle *h)
     DevBuf *bufs[] = {&h->pool, &h->d_probs, &h->d_order_cls, &h->d_order_all, &h->d_results, &h->d_trace, &h->d_boundary,
                       &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts,
                       &h->d_sel_pairs, &h->d_sel_out, &h->d_regions, &h->d_chain_tasks, &h->d_chain_regions, &h->d_chain_traces,
-                      &h->d_chain_out};
+                      &h->d_chain_out, &h->d_chain_scratch};
     smx_pipeline_free(h);
     for (PinBuf *b : {&h->pin_regions, &h->pin_cigar, &h->pin_pool}) if (b->p) cudaFreeHost(b->p);
     for (DevBuf *b : bufs) release(*b);
@@ -989,6 +989,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
             if (int rc = ensure(h, h->d_chain_regions, sizeof(int4) * regs.size())) return rc;
             if (int rc = ensure(h, h->d_chain_traces, sizeof(int32_t) * (size_t)std::max<int64_t>(trace_total, 1))) return rc;
             if (int rc = ensure(h, h->d_chain_out, sizeof(SmxChainOut) * tasks.size())) return rc;
+            if (int rc = ensure(h, h->d_chain_scratch, sizeof(int32_t) * 3 * regs.size())) return rc;
             SMX_CUDA(h, cudaMemcpyAsync(h->d_chain_tasks.p, tasks.data(), sizeof(SmxChainTask) * tasks.size(), cudaMemcpyHostToDevice, h->stream));
             SMX_CUDA(h, cudaMemcpyAsync(h->d_chain_regions.p, regs.data(), sizeof(int4) * regs.size(), cudaMemcpyHostToDevice, h->stream));
             SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
@@ -996,17 +997,29 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
                 const int cnt = cls_first[c + 1] - cls_first[c];
                 if (cnt == 0) continue;
                 const int nmax = cls_n[c];
-                const size_t smem = sizeof(int) * (size_t)(7 * nmax + SMX_CHAIN_WARPS * (15 * nmax + nmax * (nmax / 32)));
+                const size_t smem = sizeof(int) * (size_t)(4 * nmax + SMX_CHAIN_WARPS * (15 * nmax + nmax * (nmax / 32)));
                 if (smem > 48 * 1024) SMX_CUDA(h, cudaFuncSetAttribute(smx_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 SmxChainArgs ca;
                 ca.tasks = (const SmxChainTask *)h->d_chain_tasks.p + cls_first[c];
                 ca.regions = (const int4 *)h->d_chain_regions.p;
                 ca.traces = (int32_t *)h->d_chain_traces.p;
                 ca.out = (SmxChainOut *)h->d_chain_out.p + cls_first[c];
+                ca.origin_scratch = (int32_t *)h->d_chain_scratch.p;
                 ca.topology = topology; ca.nmax = nmax;
-                smx_chain_kernel<<<cnt, SMX_CHAIN_WARPS * 32, smem, h->stream>>>(ca);
+                // few pair-strands with many regions: spread the origins of one pair-strand over several CTAs so
+                // that the launch fills the GPU, then pick across the slices in a second launch
+                int slices = 1;
+                if (topology == 0 && cnt < 2 * h->sm_count) slices = std::max(1, std::min(nmax / SMX_CHAIN_WARPS, (2 * h->sm_count + cnt - 1) / cnt));
+                ca.n_slices = slices; ca.phase = 0;
+                smx_chain_kernel<<<cnt * slices, SMX_CHAIN_WARPS * 32, smem, h->stream>>>(ca);
                 SMX_CUDA(h, cudaGetLastError());
                 st.launches += 1;
+                if (slices > 1) {
+                    ca.n_slices = 1; ca.phase = 1;
+                    smx_chain_kernel<<<cnt, SMX_CHAIN_WARPS * 32, smem, h->stream>>>(ca);
+                    SMX_CUDA(h, cudaGetLastError());
+                    st.launches += 1;
+                }
             }
             SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
             std::vector<SmxChainOut> couts(tasks.size());

@@ -32,8 +32,11 @@ struct SmxChainArgs {
     const int4 *regions;
     int32_t *traces;
     SmxChainOut *out;
+    int32_t *origin_scratch;  // 3 ints per region (score, g1, g2 of the search with that region as origin)
     int32_t topology;
-    int32_t nmax;  // smem is sized for this many regions (multiple of 32)
+    int32_t nmax;      // smem is sized for this many regions (multiple of 32)
+    int32_t n_slices;  // CTAs per pair-strand: CTA s evaluates the origins r with r % (n_slices * warps) in its share
+    int32_t phase;     // 0 = evaluate origins (and finish when n_slices == 1), 1 = pick the best origin and emit its trace
 };
 
 struct SmxChainScratch {
@@ -217,13 +220,12 @@ __device__ int smx_chain_search(const SmxChainScratch &sc, const int4 *R, int N,
 __global__ void __launch_bounds__(SMX_CHAIN_WARPS * 32) smx_chain_kernel(const SmxChainArgs a)
 {
     extern __shared__ int chain_smem[];
-    const SmxChainTask tk = a.tasks[blockIdx.x];
+    const int task_id = blockIdx.x / a.n_slices, slice = blockIdx.x % a.n_slices;
+    const SmxChainTask tk = a.tasks[task_id];
     const int N = tk.n, nmax = a.nmax;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int4 *R = reinterpret_cast<int4 *>(chain_smem);            // 4 * nmax ints
-    int *o_score = chain_smem + 4 * nmax;                       // per-origin results
-    int *o_g1 = o_score + nmax, *o_g2 = o_g1 + nmax;
-    int *wbase = o_g2 + nmax + warp * smx_chain_scratch_ints(nmax);
+    int4 *R = reinterpret_cast<int4 *>(chain_smem);      // 4 * nmax ints
+    int *wbase = chain_smem + 4 * nmax + warp * smx_chain_scratch_ints(nmax);
     SmxChainScratch sc;
     sc.rs = wbase; sc.re = sc.rs + nmax; sc.qs = sc.re + nmax; sc.qe = sc.qs + nmax; sc.keep = sc.qe + nmax;
     sc.op_r = sc.keep + nmax; sc.cl_r = sc.op_r + nmax; sc.op_q = sc.cl_r + nmax; sc.cl_q = sc.op_q + nmax;
@@ -233,56 +235,61 @@ __global__ void __launch_bounds__(SMX_CHAIN_WARPS * 32) smx_chain_kernel(const S
     sc.nw = nmax / 32;
     for (int i = threadIdx.x; i < N; i += blockDim.x) R[i] = a.regions[tk.region_off + i];
     __syncthreads();
-    __shared__ int s_best, s_fail;
-    if (threadIdx.x == 0) { s_best = -1; s_fail = 0; }
-    __syncthreads();
     int *trace_out = a.traces + tk.trace_off;
+    int *o_score = a.origin_scratch + 3 * tk.region_off, *o_g1 = o_score + N, *o_g2 = o_g1 + N;
 
     if (a.topology == 1) {
         // exec_linear (:793-810): only the search with the LAST listed region as origin is returned; no wrap
-        if (warp == 0) {
+        if (warp == 0 && slice == 0 && a.phase == 0) {
             int score = 0;
             const int len = smx_chain_search(sc, R, N, N - 1, false, tk.n_ref, tk.n_q, &score);
             for (int t = lane; t < len; t += 32) trace_out[t] = sc.trace[t];
-            if (lane == 0) { a.out[blockIdx.x].trace_len = len; a.out[blockIdx.x].score = score; }
+            if (lane == 0) { a.out[task_id].trace_len = len; a.out[task_id].score = score; }
         }
         return;
     }
-    // exec_circular (:811-862): every region as origin
-    for (int r = warp; r < N; r += SMX_CHAIN_WARPS) {
-        int score = 0;
-        const int len = smx_chain_search(sc, R, N, r, true, tk.n_ref, tk.n_q, &score);
-        if (lane == 0) {
-            if (len == 0) { s_fail = 1; o_score[r] = -1; o_g1[r] = 0; o_g2[r] = 0; }
-            else {
-                // tie metrics on the path in original coordinates (:838-856)
-                int am = 0, bm = 0;
-                for (int t = 1; t < len; ++t) {
-                    if (R[sc.trace[t]].z < R[sc.trace[am]].z) am = t;
-                    if (R[sc.trace[t]].w > R[sc.trace[bm]].w) bm = t;
+    if (a.phase == 0) {
+        // exec_circular (:811-862): every region as origin; origins are dealt to (slice, warp)
+        for (int r = slice * SMX_CHAIN_WARPS + warp; r < N; r += a.n_slices * SMX_CHAIN_WARPS) {
+            int score = 0;
+            const int len = smx_chain_search(sc, R, N, r, true, tk.n_ref, tk.n_q, &score);
+            if (lane == 0) {
+                if (len == 0) { o_score[r] = -1; o_g1[r] = 0; o_g2[r] = 0; }
+                else {
+                    // tie metrics on the path in original coordinates (:838-856)
+                    int am = 0, bm = 0;
+                    for (int t = 1; t < len; ++t) {
+                        if (R[sc.trace[t]].z < R[sc.trace[am]].z) am = t;
+                        if (R[sc.trace[t]].w > R[sc.trace[bm]].w) bm = t;
+                    }
+                    int d = (R[sc.trace[am]].x - R[sc.trace[bm]].y) % tk.n_ref;
+                    if (d < 0) d += tk.n_ref;
+                    int g = R[sc.trace[0]].z - R[sc.trace[len - 1]].w;
+                    for (int t = 0; t + 1 < len; ++t) g = max(g, R[sc.trace[t + 1]].z - R[sc.trace[t]].w);
+                    o_score[r] = score; o_g1[r] = d; o_g2[r] = g;
                 }
-                int d = (R[sc.trace[am]].x - R[sc.trace[bm]].y) % tk.n_ref;
-                if (d < 0) d += tk.n_ref;
-                int g = R[sc.trace[0]].z - R[sc.trace[len - 1]].w;
-                for (int t = 0; t + 1 < len; ++t) g = max(g, R[sc.trace[t + 1]].z - R[sc.trace[t]].w);
-                o_score[r] = score; o_g1[r] = d; o_g2[r] = g;
             }
+            __syncwarp();
         }
-        __syncwarp();
+        if (a.n_slices > 1) return;  // phase 1 (separate launch) picks across the slices
+        __threadfence_block();
+        __syncthreads();
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && !s_fail) {
-        int best = -1;
-        for (int r = 0; r < N; ++r) best = max(best, o_score[r]);
-        int cnt = 0, first = -1;
-        for (int r = 0; r < N; ++r) if (o_score[r] == best) { ++cnt; if (first < 0) first = r; }
-        int pick = first;
-        if (cnt > 1) {
+    // pick: max score, then max g1, then first max g2 (:830-861); any failed origin fails the pair-strand
+    __shared__ int s_best;
+    if (threadIdx.x == 0) {
+        int best = -1, fail = 0;
+        for (int r = 0; r < N; ++r) { if (o_score[r] < 0) fail = 1; best = max(best, o_score[r]); }
+        int pick = -1;
+        if (!fail) {
             int top = -1;
             for (int r = 0; r < N; ++r) if (o_score[r] == best) top = max(top, o_g1[r]);
-            pick = -1;
-            for (int r = 0; r < N; ++r)
-                if (o_score[r] == best && o_g1[r] == top && (pick < 0 || o_g2[r] > o_g2[pick])) pick = r;
+            int cnt = 0, first = -1;
+            for (int r = 0; r < N; ++r) if (o_score[r] == best) { ++cnt; if (first < 0) first = r; }
+            if (cnt == 1) pick = first;
+            else
+                for (int r = 0; r < N; ++r)
+                    if (o_score[r] == best && o_g1[r] == top && (pick < 0 || o_g2[r] > o_g2[pick])) pick = r;
         }
         s_best = pick;
     }
@@ -291,6 +298,6 @@ __global__ void __launch_bounds__(SMX_CHAIN_WARPS * 32) smx_chain_kernel(const S
         int len = 0, score = 0;
         if (s_best >= 0) len = smx_chain_search(sc, R, N, s_best, true, tk.n_ref, tk.n_q, &score);
         for (int t = lane; t < len; t += 32) trace_out[t] = sc.trace[t];
-        if (lane == 0) { a.out[blockIdx.x].trace_len = len; a.out[blockIdx.x].score = score; }
+        if (lane == 0) { a.out[task_id].trace_len = len; a.out[task_id].score = score; }
     }
 }

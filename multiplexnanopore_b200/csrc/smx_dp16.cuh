@@ -86,8 +86,11 @@ __device__ __forceinline__ int smx16_hi(uint32_t v) { return (int)v >> 16; }
 // boundary lines of the s16 kernel: one uint32 per column = F << 16 | (H & 0xffff)
 // W = warps that share one problem (1: every warp of the 128-thread CTA owns its own problem; 2, 4, 8: the CTA
 // is one team whose warps take band pairs round-robin).  The host picks W = min(8, largest power of two <= pairs).
+#ifndef SMX16_MIN_WARPS_PER_SM
+#define SMX16_MIN_WARPS_PER_SM 16
+#endif
 template <int W>
-__global__ void __launch_bounds__(W == 1 ? 128 : W * 32) smx_dp_forward16(const SmxFwdArgs a)
+__global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM / (W == 1 ? 4 : W)) smx_dp_forward16(const SmxFwdArgs a)
 {
     constexpr int K = 8;
     constexpr bool TEAM = W > 1;
