@@ -46,6 +46,25 @@ __device__ __forceinline__ uint32_t smx16_max_tr(uint32_t a, uint32_t b, uint32_
     return r;
 }
 
+// first flag of a cell: starts the cell's own nibble registers (selp instead of a predicated OR), so that the
+// eight cells of a column do not serialise on one accumulator
+template <uint32_t IMM>
+__device__ __forceinline__ uint32_t smx16_max_tr_first(uint32_t a, uint32_t b, uint32_t &n_lo, uint32_t &n_hi)
+{
+    uint32_t r;
+    asm("{.reg .pred pu, pv; .reg .s16 r0, r1, r2, r3;\n\t"
+        "max.s16x2 %0, %3, %4;\n\t"
+        "mov.b32 {r0, r1}, %0;\n\t"
+        "mov.b32 {r2, r3}, %3;\n\t"
+        "setp.eq.s16 pv, r0, r2;\n\t"
+        "setp.eq.s16 pu, r1, r3;\n\t"
+        "selp.b32 %1, 0, %5, pv;\n\t"
+        "selp.b32 %2, 0, %5, pu;}\n\t"
+        : "=r"(r), "=r"(n_lo), "=r"(n_hi)
+        : "r"(a), "r"(b), "n"(IMM));
+    return r;
+}
+
 struct Smx16Col {  // per-column scalars threaded through the K cells of a lane
     uint32_t hd, fu, hugo, h, f, w_lo, w_hi;
 };
@@ -55,13 +74,16 @@ struct Smx16Cell {
     static __device__ __forceinline__ void run(uint32_t (&Hl)[K], uint32_t (&Hlgo)[K], uint32_t (&El)[K], const uint32_t (&plo)[K],
                                                const uint32_t (&phi)[K], Smx16Col &c, uint32_t sel, uint32_t nge2, uint32_t ngo2)
     {
+        uint32_t n_lo, n_hi;  // this cell's nibble in place (bits 4k .. 4k+3) for the low / high band
         const uint32_t e_ext = smx16_add(El[k], nge2);
-        const uint32_t e = smx16_max_tr<(4u << (4 * k))>(e_ext, Hlgo[k], c.w_lo, c.w_hi);
+        const uint32_t e = smx16_max_tr_first<(4u << (4 * k))>(e_ext, Hlgo[k], n_lo, n_hi);
         const uint32_t f_ext = smx16_add(c.fu, nge2);
-        const uint32_t f = smx16_max_tr<(8u << (4 * k))>(f_ext, c.hugo, c.w_lo, c.w_hi);
+        const uint32_t f = smx16_max_tr<(8u << (4 * k))>(f_ext, c.hugo, n_lo, n_hi);
         const uint32_t hdiag = smx16_add(c.hd, smx_subst_u(plo[k], phi[k], sel));
-        const uint32_t t = smx16_max_tr<(2u << (4 * k))>(f, e, c.w_lo, c.w_hi);
-        const uint32_t h = smx16_max_tr<(1u << (4 * k))>(hdiag, t, c.w_lo, c.w_hi);
+        const uint32_t t = smx16_max_tr<(2u << (4 * k))>(f, e, n_lo, n_hi);
+        const uint32_t h = smx16_max_tr<(1u << (4 * k))>(hdiag, t, n_lo, n_hi);
+        c.w_lo |= n_lo;
+        c.w_hi |= n_hi;
         c.hd = Hl[k];
         Hl[k] = h;
         c.hugo = smx16_add(h, ngo2);

@@ -5,7 +5,12 @@
 #include "smx_common.cuh"
 #include "../../include/smx.h"
 
-#define SMX_TB_AHEAD 48
+#ifndef SMX_TB_AHEAD
+#define SMX_TB_AHEAD 16
+#endif
+#ifndef SMX_TB_PF
+#define SMX_TB_PF 3
+#endif
 
 struct SmxTbArgs {
     const uint8_t *pool;
@@ -110,46 +115,70 @@ __global__ void __launch_bounds__(128) smx_traceback(const SmxTbArgs a)
         else if (j + 1 == n) w.emit(SMX_OP_I, m - 1 - i);
     }
     int where = 0;  // 0 = DIAG (H), 1 = INS (E, emits 'D'), 2 = DEL (F, emits 'I')
-    // The walk is one dependent 1-byte load per step on direction bits that left L2 long ago.  Lines are
-    // laid out [band][step][lane] and every move lowers the step index by 0..2, so the lines the walk is
-    // about to touch are known without knowing the path: prefetch the two lines SMX_TB_AHEAD steps ahead
-    // (at the sector of the current lane) into L2 on every iteration.
+    // The walk is one dependent 1-byte load per step, so the loop keeps the position incrementally: `wp` points
+    // at the lane-step word of the current cell (layout [band][step = j + lane][lane]), `k` is the row inside the
+    // lane.  A column move lowers the step by one line, a row move changes k or, every K rows, the lane (one
+    // more line and one word back).  Only a band crossing (every 32*K rows) recomputes the address.
+    // Direction bits left L2 long ago: every move lowers the step index by 0..2, so the lines the walk is about
+    // to touch are known without knowing the path and are prefetched SMX_TB_AHEAD lines ahead.
     const int kshift = pr.kshift;
-    const int wbytes = kshift >= 1 ? (1 << kshift) >> 1 : 1;
+    const int K = 1 << kshift;
+    const int wbytes = K >= 2 ? K >> 1 : 1;
     const int rows_per_band = 32 << kshift;
+    const long long line = 32ll * wbytes;
+    const long long band_bytes = (long long)(n + 31) * line;
+    int lane_t = 0, k = 0;
+    const uint8_t *wp = tr;
+    if (i >= 0 && j >= 0) {
+        const int band = i / rows_per_band;
+        const int rin = i - band * rows_per_band;
+        lane_t = rin >> kshift;
+        k = rin & (K - 1);
+        wp = tr + (long long)band * band_bytes + (long long)(j + lane_t) * line + (long long)lane_t * wbytes;
+    }
     while (local ? (i >= 0 && j >= 0) : (i >= 0 || j >= 0)) {
         if (i < 0) { w.emit(SMX_OP_D, j + 1); j = -1; break; }
         if (j < 0) { w.emit(SMX_OP_I, i + 1); i = -1; break; }
-        {
-            const int band = i / rows_per_band;
-            const int lane_t = (i - band * rows_per_band) >> kshift;
-            const int s_now = j + lane_t;
-            const int s_pf = s_now - SMX_TB_AHEAD;
-            if (s_pf >= 1) {
-                const uint8_t *p = tr + (((size_t)band * (size_t)(n + 31) + (size_t)s_pf) * 32 + (size_t)lane_t) * wbytes;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p - 32 * wbytes));
-            }
-        }
-        const uint32_t nib = smx_trace_nibble(tr, n, pr.kshift, i, j);
+#if SMX_TB_PF == 1
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(wp - SMX_TB_AHEAD * line));
+#elif SMX_TB_PF == 2
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(wp - SMX_TB_AHEAD * line));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(wp - SMX_TB_AHEAD * line - 32));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(wp - (SMX_TB_AHEAD + 1) * line - 32));
+#elif SMX_TB_PF == 3
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(wp - SMX_TB_AHEAD * line));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(wp - SMX_TB_AHEAD * line - 32));
+#endif
+        const uint32_t nib = ((uint32_t)wp[k >> 1] >> ((k & 1) * 4)) & 15u;
+        int di = 0, dj = 0;
         if (where == 0) {
             // int32 kernels store the H source as a 2-bit code; the s16x2 kernels (classes >= 10) store
             // "diagonal lost" in bit 0 and "E beat F" in bit 1 (smx_dp16.cuh)
             const uint32_t src = enc16 ? (!(nib & 1u) ? SMX_SRC_DIAG : ((nib & 2u) ? SMX_SRC_INS : SMX_SRC_DEL)) : (nib & 3u);
             if (src == SMX_SRC_DIAG) {
                 w.emit(s1[i] == s2[j] ? SMX_OP_EQ : SMX_OP_X, 1);
-                --i; --j;
+                di = 1; dj = 1;
             } else if (src == SMX_SRC_INS) where = 1;
             else if (src == SMX_SRC_DEL) where = 2;
             else break;  // ZERO: local alignment starts here
         } else if (where == 1) {
             w.emit(SMX_OP_D, 1);
-            --j;
+            dj = 1;
             where = (nib & SMX_BIT_EOPEN) ? 0 : 1;
         } else {
             w.emit(SMX_OP_I, 1);
-            --i;
+            di = 1;
             where = (nib & SMX_BIT_FOPEN) ? 0 : 2;
+        }
+        if (dj) { --j; wp -= line; }
+        if (di) {
+            --i;
+            if (k > 0) --k;
+            else if (lane_t > 0) { --lane_t; k = K - 1; wp -= line + wbytes; }
+            else if (i >= 0) {  // previous band: last lane, last row
+                lane_t = 31; k = K - 1;
+                wp = tr + (long long)(i / rows_per_band) * band_bytes + (long long)(j + 31) * line + 31ll * wbytes;
+            }
         }
     }
     w.flush();
