@@ -59,7 +59,7 @@ struct smx_handle {
     int kernel_launches[16] = {0};
     int64_t class_cells[14] = {0};
 
-    DevBuf pool;
+    DevBuf pool, pool2, pool_special;  // ASCII pool, its 2-bit packing and per-word non-ACGT flags (smx_scan.cuh)
     int64_t pool_len = 0;
     std::vector<int32_t> pool_nonacgt;  // prefix count of bytes other than A/C/G/T (s16 kernel eligibility)
 
@@ -204,7 +204,7 @@ extern "C" void smx_destroy(smx_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->pool, &h->d_probs, &h->d_order_cls, &h->d_order_all, &h->d_results, &h->d_trace, &h->d_boundary,
+    DevBuf *bufs[] = {&h->pool, &h->pool2, &h->pool_special, &h->d_probs, &h->d_order_cls, &h->d_order_all, &h->d_results, &h->d_trace, &h->d_boundary,
                       &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts,
                       &h->d_sel_pairs, &h->d_sel_out, &h->d_regions, &h->d_chain_tasks, &h->d_chain_regions, &h->d_chain_traces,
                       &h->d_chain_out, &h->d_chain_scratch};
@@ -233,6 +233,16 @@ extern "C" int smx_pool_upload(smx_handle *h, const uint8_t *seqs, int64_t n)
     SMX_CUDA(h, cudaSetDevice(h->device));
     if (int rc = ensure(h, h->pool, (size_t)n + 64)) return rc;
     SMX_CUDA(h, cudaMemcpyAsync(h->pool.p, seqs, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    {
+        const int64_t n_words = (n + 15) / 16;
+        if (int rc = ensure(h, h->pool2, sizeof(uint32_t) * (size_t)(n_words + 4))) return rc;
+        if (int rc = ensure(h, h->pool_special, (size_t)(n_words + 4))) return rc;
+        SMX_CUDA(h, cudaMemsetAsync(h->pool2.p, 0, sizeof(uint32_t) * (size_t)(n_words + 4), h->stream));
+        SMX_CUDA(h, cudaMemsetAsync(h->pool_special.p, 0, (size_t)(n_words + 4), h->stream));
+        smx_pack_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, h->stream>>>((const uint8_t *)h->pool.p, n, (uint32_t *)h->pool2.p,
+                                                                                 (uint8_t *)h->pool_special.p, n_words);
+        SMX_CUDA(h, cudaGetLastError());
+    }
     SMX_CUDA(h, cudaStreamSynchronize(h->stream));
     h->pool_len = n;
     // per 64-byte block: does it hold a byte other than A/C/G/T?  prefix over blocks (s16 kernel eligibility)
@@ -663,7 +673,7 @@ extern "C" int smx_scan_run(smx_handle *h)
     if (h->scan_n == 0) return 0;
     SMX_CUDA(h, cudaSetDevice(h->device));
     const int qwords = (h->scan_nq_max + 15) / 16;
-    const int rwords = (SMX_SCAN_TILE + h->scan_nq_max - 1 + 15) / 16 + 1;
+    const int rwords = SMX_SCAN_TILE / 16 + qwords + 2;
     const size_t smem = sizeof(uint32_t) * (size_t)(qwords + rwords + 4);
     if (smem > 48 * 1024) SMX_CUDA(h, cudaFuncSetAttribute(smx_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SmxScanArgs a;
@@ -672,9 +682,10 @@ extern "C" int smx_scan_run(smx_handle *h)
     a.tile_pair = (const int32_t *)h->d_scan_tile_pair.p;
     a.counts = (int32_t *)h->d_counts.p;
     a.topology = h->scan_topology;
-    a.smem_words_q = qwords;
+    a.pool2 = (const uint32_t *)h->pool2.p;
+    a.special = (const uint8_t *)h->pool_special.p;
     SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    smx_scan_kernel<<<h->scan_tiles, SMX_SCAN_TILE, smem, h->stream>>>(a);
+    smx_scan_kernel<<<h->scan_tiles, SMX_SCAN_THREADS, smem, h->stream>>>(a);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches = 1;
     SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
