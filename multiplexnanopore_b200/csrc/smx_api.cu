@@ -45,7 +45,7 @@ struct smx_handle {
     bool owns_stream = false;
     int sm_count = 148;
     std::string err;
-    int64_t trace_budget = (int64_t)24 << 30;
+    int64_t trace_budget = (int64_t)40 << 30;  // clamped to a quarter of the free device memory at creation
     bool use_s16 = true;  // SMX_S16=0 forces the int32 kernels (cross-check)
     int s16_max_wsel = 1;  // warps per problem of the s16 kernel are capped at 2 (measured best); SMX_S16_MAXW=1|2|4|8 overrides
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -195,6 +195,11 @@ extern "C" int smx_create(smx_handle **out, int device_ordinal, void *stream)
     }
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) h->trace_budget = std::max<int64_t>((int64_t)2 << 30, std::min<int64_t>(h->trace_budget, (int64_t)(free_b / 4)));
+    }
+    if (const char *tb = getenv("SMX_TRACE_BUDGET_GB")) { const long v = atol(tb); if (v >= 1 && v <= 160) h->trace_budget = (int64_t)v << 30; }
     *out = h;
     return 0;
 }
