@@ -164,7 +164,7 @@ def run_engine(args, rank, world, local_rank):
     eng = Engine(local_rank)
     plasmids, reads, _ = workload(rank, args.reads)
     cores = os.cpu_count() or 1
-    n_threads = max(1, cores // max(world, 1))
+    n_threads = args.threads or max(1, cores // max(world, 1))
     refs = [p.upper() for p in plasmids]
     reads = [r.upper() for r in reads]
     in_bytes = sum(len(p) for p in refs) + sum(len(r) for r in reads)
@@ -291,6 +291,7 @@ def main():
     ap.add_argument("--overlap", type=int, default=2, help="batches in flight per rank (engine handles)")
     ap.add_argument("--cpu-reads", type=int, default=0, help="reads of the CPU sample (default: max(cores, 8))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--threads", type=int, default=0, help="host threads per rank (default: cores / ranks)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
