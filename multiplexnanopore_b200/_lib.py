@@ -9,8 +9,11 @@ import ctypes
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 from pathlib import Path
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libsmx.so"
+# SMX_LIB_PATH: developer override to A/B-test differently compiled builds of the same sources
+LIB_PATH = Path(os.environ["SMX_LIB_PATH"]).resolve() if os.environ.get("SMX_LIB_PATH") else _PKG / "libsmx.so"
 
 # every symbol include/smx.h declares: (restype, argtypes)
 _SIGNATURES = {

@@ -460,6 +460,7 @@ static int launch_forward(smx_handle *h, const Chunk &c, int cls, int chunk_idx)
     a.nmax = h->nmax;
     a.results = (SmxResult *)h->d_results.p;
     a.sc = h->sc;
+    a.one = 1u;
     smx_dp_forward<K, LOCAL, TEAM><<<blocks, threads, 0, h->stream>>>(a);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
@@ -492,6 +493,7 @@ static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_id
     a.nmax = h->nmax;
     a.results = (SmxResult *)h->d_results.p;
     a.sc = h->sc;
+    a.one = 1u;
     smx_dp_forward16<W><<<blocks, threads, 0, h->stream>>>(a);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;

@@ -80,6 +80,7 @@ struct SmxFwdArgs {
     int32_t nmax;
     SmxResult *results;
     SmxScoring sc;
+    uint32_t one;  // always 1 (a kernel parameter so that ptxas cannot fold the IMAD it feeds, smx_dp16.cuh)
 };
 
 #define SMX_TEAM_WARPS 8  // warps of a CTA that share one large problem (bands interleaved)

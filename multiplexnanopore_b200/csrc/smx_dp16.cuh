@@ -15,6 +15,11 @@
 #include "smx_dp.cuh"
 
 #define SMX16_NEG (-32000)
+#ifndef SMX16_UNROLL
+#define SMX16_UNROLL 4  // steps of the interior chunk loop unrolled together
+#endif
+#define SMX16_PRAGMA_(x) _Pragma(#x)
+#define SMX16_PRAGMA(x) SMX16_PRAGMA_(x)
 #define SMX16_LAG 64  // columns the high-half band trails the low-half band (two 32-column chunks)
 
 __device__ __forceinline__ uint32_t smx16_add(uint32_t a, uint32_t b)
@@ -29,8 +34,12 @@ __device__ __forceinline__ uint32_t smx16_add(uint32_t a, uint32_t b)
 // high band when b won.  Direction-bit encoding of the s16 kernels (decoded by smx_traceback for classes >= 10):
 //   bit 0: diagonal lost against max(E, F)      bit 1: E beat F (F >= E keeps it clear: DEL before INS)
 //   bit 2: E opened from H (tie -> extend)      bit 3: F opened from H
+// The flag is dropped with a predicated IMAD (w = one * IMM + w, `one` an opaque register holding 1): the
+// integer ALU pipe of an SMSP issues one warp instruction every two cycles and carries every VIADD / VIMNMX / PRMT
+// / SEL / LOP3 of this kernel, while the FMA pipe (IMAD) would otherwise idle -- measured: the kernel is bound by
+// the ALU pipe, not by the issue slot.
 template <uint32_t IMM>
-__device__ __forceinline__ uint32_t smx16_max_tr(uint32_t a, uint32_t b, uint32_t &w_lo, uint32_t &w_hi)
+__device__ __forceinline__ uint32_t smx16_max_tr(uint32_t a, uint32_t b, uint32_t &w_lo, uint32_t &w_hi, uint32_t one)
 {
     uint32_t r;
     asm("{.reg .pred pu, pv; .reg .s16 r0, r1, r2, r3;\n\t"
@@ -39,10 +48,10 @@ __device__ __forceinline__ uint32_t smx16_max_tr(uint32_t a, uint32_t b, uint32_
         "mov.b32 {r2, r3}, %3;\n\t"
         "setp.eq.s16 pv, r0, r2;\n\t"
         "setp.eq.s16 pu, r1, r3;\n\t"
-        "@!pv or.b32 %1, %1, %5;\n\t"
-        "@!pu or.b32 %2, %2, %5;}\n\t"
+        "@!pv mad.lo.u32 %1, %6, %5, %1;\n\t"
+        "@!pu mad.lo.u32 %2, %6, %5, %2;}\n\t"
         : "=r"(r), "+r"(w_lo), "+r"(w_hi)
-        : "r"(a), "r"(b), "n"(IMM));
+        : "r"(a), "r"(b), "n"(IMM), "r"(one));
     return r;
 }
 
@@ -66,7 +75,7 @@ __device__ __forceinline__ uint32_t smx16_max_tr_first(uint32_t a, uint32_t b, u
 }
 
 struct Smx16Col {  // per-column scalars threaded through the K cells of a lane
-    uint32_t hd, fu, hugo, h, f, w_lo, w_hi;
+    uint32_t hd, fu, hugo, h, f, w_lo, w_hi, w_lo2, w_hi2, one;
 };
 
 template <int K, int k>
@@ -74,16 +83,17 @@ struct Smx16Cell {
     static __device__ __forceinline__ void run(uint32_t (&Hl)[K], uint32_t (&Hlgo)[K], uint32_t (&El)[K], const uint32_t (&plo)[K],
                                                const uint32_t (&phi)[K], Smx16Col &c, uint32_t sel, uint32_t nge2, uint32_t ngo2)
     {
-        uint32_t n_lo, n_hi;  // this cell's nibble in place (bits 4k .. 4k+3) for the low / high band
+        // the four flags of this cell land in place (bits 4k .. 4k+3) in one of two accumulators per band
+        // (even / odd k), so that the predicated IMADs of neighbouring cells do not serialise
+        uint32_t &n_lo = (k & 1) ? c.w_lo2 : c.w_lo;
+        uint32_t &n_hi = (k & 1) ? c.w_hi2 : c.w_hi;
         const uint32_t e_ext = smx16_add(El[k], nge2);
-        const uint32_t e = smx16_max_tr_first<(4u << (4 * k))>(e_ext, Hlgo[k], n_lo, n_hi);
+        const uint32_t e = smx16_max_tr<(4u << (4 * k))>(e_ext, Hlgo[k], n_lo, n_hi, c.one);
         const uint32_t f_ext = smx16_add(c.fu, nge2);
-        const uint32_t f = smx16_max_tr<(8u << (4 * k))>(f_ext, c.hugo, n_lo, n_hi);
+        const uint32_t f = smx16_max_tr<(8u << (4 * k))>(f_ext, c.hugo, n_lo, n_hi, c.one);
         const uint32_t hdiag = smx16_add(c.hd, smx_subst_u(plo[k], phi[k], sel));
-        const uint32_t t = smx16_max_tr<(2u << (4 * k))>(f, e, n_lo, n_hi);
-        const uint32_t h = smx16_max_tr<(1u << (4 * k))>(hdiag, t, n_lo, n_hi);
-        c.w_lo |= n_lo;
-        c.w_hi |= n_hi;
+        const uint32_t t = smx16_max_tr<(2u << (4 * k))>(f, e, n_lo, n_hi, c.one);
+        const uint32_t h = smx16_max_tr<(1u << (4 * k))>(hdiag, t, n_lo, n_hi, c.one);
         c.hd = Hl[k];
         Hl[k] = h;
         c.hugo = smx16_add(h, ngo2);
@@ -105,6 +115,55 @@ __device__ __forceinline__ uint32_t smx16_pack(int lo, int hi) { return ((uint32
 __device__ __forceinline__ int smx16_lo(uint32_t v) { return (int)(short)(v & 0xffffu); }
 __device__ __forceinline__ int smx16_hi(uint32_t v) { return (int)v >> 16; }
 
+// One interior 32-column chunk of a band pair: every lane is strictly inside the matrix with both halves for all
+// 32 steps, so there is no boundary (re)initialisation, no end-column candidate and the direction-bit stores are
+// unconditional.  Lane 0 takes its inputs from the chunk's staging row in shared memory (one broadcast LDS.128
+// per step) through a lane mask instead of a predicate: VIMNMX.S16x2 needs two predicate registers per
+// instruction and the SM has seven, so long-lived predicates are kept out of this loop (the two bottom-line
+// store predicates are re-derived from a register at their use).
+template <int K, bool HAS_HI, bool TRACK>
+__device__ __forceinline__ void smx16_fast_chunk(uint32_t (&Hl)[K], uint32_t (&Hlgo)[K], uint32_t (&El)[K], const uint32_t (&plo)[K],
+                                                 const uint32_t (&phi)[K], uint32_t &hd, uint32_t &out_h, uint32_t &out_f, uint32_t &sel_prev,
+                                                 const uint4 *tops, uint32_t lane0_mask, uint32_t nge2, uint32_t ngo2, uint32_t *tp_lo,
+                                                 uint32_t *tp_hi, uint32_t *bl, uint32_t *bh, uint32_t st_flags, uint32_t tmask, int last_k,
+                                                 int jbase, int &row_best, int &row_best_j, uint32_t one)
+{
+    SMX16_PRAGMA(unroll SMX16_UNROLL)
+    for (int ss = 0; ss < 32; ++ss) {
+        uint32_t hu = __shfl_up_sync(SMX_FULL_MASK, out_h, 1);
+        uint32_t fu = __shfl_up_sync(SMX_FULL_MASK, out_f, 1);
+        uint32_t sel = __shfl_up_sync(SMX_FULL_MASK, sel_prev, 1);
+        const uint4 tv = tops[ss];
+        hu = (tv.x & lane0_mask) | (hu & ~lane0_mask);
+        fu = (tv.y & lane0_mask) | (fu & ~lane0_mask);
+        sel = (tv.z & lane0_mask) | (sel & ~lane0_mask);
+        sel_prev = sel;
+        Smx16Col c;
+        c.hd = hd; c.fu = fu; c.hugo = smx16_add(hu, ngo2); c.h = 0; c.f = 0; c.w_lo = 0; c.w_hi = 0; c.w_lo2 = 0; c.w_hi2 = 0; c.one = one;
+        Smx16Cell<K, 0>::run(Hl, Hlgo, El, plo, phi, c, sel, nge2, ngo2);
+        hd = hu;
+        out_h = c.h;
+        out_f = c.f;
+        tp_lo[ss * 32] = c.w_lo | c.w_lo2;
+        if (HAS_HI) tp_hi[ss * 32] = c.w_hi | c.w_hi2;
+        uint32_t fl = st_flags;
+        asm volatile("" : "+r"(fl));  // keeps the store predicates short-lived (see above)
+        if (fl & 1u) __stcg(&bl[ss], __byte_perm(out_h, out_f, 0x5410));
+        if (HAS_HI) { if (fl & 2u) __stcg(&bh[ss], __byte_perm(out_h, out_f, 0x7632)); }
+        if (TRACK) {
+            uint32_t tm = tmask;
+            asm volatile("" : "+r"(tm));
+            if (tm) {  // the lane that owns the last query row (semi-global end in the last row)
+                uint32_t hw = Hl[0];
+#pragma unroll
+                for (int k = 1; k < K; ++k) if (k == last_k) hw = Hl[k];
+                const int hv = (tm & 1u) ? smx16_lo(hw) : smx16_hi(hw);
+                if (hv > row_best) { row_best = hv; row_best_j = jbase + ss; }
+            }
+        }
+    }
+}
+
 // boundary lines of the s16 kernel: one uint32 per column = F << 16 | (H & 0xffff)
 // W = warps that share one problem (1: every warp of the 128-thread CTA owns its own problem; 2, 4, 8: the CTA
 // is one team whose warps take band pairs round-robin).  The host picks W = min(8, largest power of two <= pairs).
@@ -125,10 +184,15 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
     uint32_t *line1 = line0 + a.nmax;
     const int go = a.sc.go, ge = a.sc.ge;
     const uint32_t nge2 = smx16_pack(-ge, -ge), ngo2 = smx16_pack(-go, -go);
+    const uint32_t lane0_mask = lane == 0 ? 0xffffffffu : 0u;
+    const uint32_t one = a.one;  // 1, but unknown to ptxas: keeps the predicated flag updates on the FMA pipe (IMAD)
 
     __shared__ int s_ticket;
     __shared__ volatile int s_prog[W];
     __shared__ int s_red[W][6];
+    // lane 0's inputs of the current 32-column chunk, one uint4 per column: {H above (lo | hi << 16), F above, PRMT
+    // selector of the two reference codes, -}; read back with one broadcast LDS.128 per step
+    __shared__ uint4 s_top[W == 1 ? 4 : W][32];
 
     for (;;) {
         int ticket = 0;
@@ -186,8 +250,10 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
                 El[k] = smx16_pack(SMX16_NEG, SMX16_NEG);
             }
             uint32_t hd = free_beg ? 0u : smx16_pack(i0_lo == 0 ? 0 : -(go + (i0_lo - 1) * ge), -(go + (i0_hi - 1) * ge));
-            uint32_t out_h = 0, out_f = 0, rc_prev = 0;
+            uint32_t out_h = 0, out_f = 0, sel_prev = 0;
             int rch1 = 0, rch2 = 0;  // reference codes of the two previous chunks (the high half reads 64 columns back)
+            const bool st_lo = lane == 31 && !lo_is_last, st_hi = lane == 31 && has_hi && !hi_is_last;
+            const bool track_lo = mode == 1 && lo_is_last, track_hi = mode == 1 && hi_is_last;
 
             for (int s0 = 0, chunk = 0; s0 < psteps; s0 += 32, ++chunk) {
                 if (TEAM && pair > 0) {
@@ -211,23 +277,45 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
                 }
                 const int jb = jc - LAG;
                 if (jb >= 0 && jb < n) topB = __ldcg(&top_hi[jb]);
+                {
+                    const uint32_t c_lo = (uint32_t)rch0, c_hi = (uint32_t)rch2;
+                    uint4 tv;
+                    tv.x = (topA & 0xffffu) | (topB << 16);
+                    tv.y = (topA >> 16) | (topB & 0xffff0000u);
+                    tv.z = c_lo | ((c_lo | 8u) << 4) | ((c_hi | 4u) << 8) | ((c_hi | 12u) << 12);
+                    tv.w = 0u;
+                    s_top[wib][lane] = tv;
+                    __syncwarp();
+                }
+                // ---- fast path: every lane is strictly inside the matrix with both halves for all 32 steps
+                //      (1 <= j <= n-2 for the low band, 64 columns behind for the high band): no boundary
+                //      (re)initialisation, no end-column candidates, unconditional direction-bit stores ----
+                if (s0 >= 32 + LAG && s0 + 33 <= n) {
+                    uint32_t *tp_lo = trace + ((size_t)band_lo * steps + s0) * 32 + lane;
+                    uint32_t *tp_hi = trace + ((size_t)band_hi * steps + (s0 - LAG)) * 32 + lane;
+                    uint32_t *bl = bot_lo + (s0 - 31);
+                    uint32_t *bh = bot_hi + (s0 - 31 - LAG);
+                    const uint32_t st_flags = (st_lo ? 1u : 0u) | (st_hi ? 2u : 0u);
+                    if (track_lo | track_hi) {
+                        const int jbase = s0 - lane - (track_lo ? 0 : LAG);
+                        const uint32_t tmask = lane == last_lane ? (track_lo ? 0x0000ffffu : 0xffff0000u) : 0u;
+                        if (has_hi) smx16_fast_chunk<K, true, true>(Hl, Hlgo, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, nge2, ngo2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, row_best, row_best_j, one);
+                        else smx16_fast_chunk<K, false, true>(Hl, Hlgo, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, nge2, ngo2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, row_best, row_best_j, one);
+                    } else {
+                        if (has_hi) smx16_fast_chunk<K, true, false>(Hl, Hlgo, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, nge2, ngo2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, row_best, row_best_j, one);
+                        else smx16_fast_chunk<K, false, false>(Hl, Hlgo, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, nge2, ngo2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, row_best, row_best_j, one);
+                    }
+                } else {
                 const int send = min(32, psteps - s0);
 #pragma unroll 1
                 for (int ss = 0; ss < send; ++ss) {
                     const int s = s0 + ss;
                     uint32_t hu = __shfl_up_sync(SMX_FULL_MASK, out_h, 1);
                     uint32_t fu = __shfl_up_sync(SMX_FULL_MASK, out_f, 1);
-                    uint32_t rc = __shfl_up_sync(SMX_FULL_MASK, rc_prev, 1);
-                    const uint32_t ta = __shfl_sync(SMX_FULL_MASK, topA, ss);
-                    const uint32_t tb = __shfl_sync(SMX_FULL_MASK, topB, ss);
-                    const int ra = __shfl_sync(SMX_FULL_MASK, rch0, ss);
-                    const int rb = __shfl_sync(SMX_FULL_MASK, rch2, ss);
-                    if (lane == 0) {
-                        hu = (ta & 0xffffu) | (tb << 16);
-                        fu = (ta >> 16) | (tb & 0xffff0000u);
-                        rc = (uint32_t)ra | ((uint32_t)rb << 8);
-                    }
-                    rc_prev = rc;
+                    uint32_t sel = __shfl_up_sync(SMX_FULL_MASK, sel_prev, 1);
+                    const uint4 tv = s_top[wib][ss];
+                    if (lane == 0) { hu = tv.x; fu = tv.y; sel = tv.z; }
+                    sel_prev = sel;
                     const int j_lo = s - lane, j_hi = s - lane - LAG;
                     const bool v_lo = j_lo >= 0 && j_lo < n;
                     const bool v_hi = has_hi && j_hi >= 0 && j_hi < n;
@@ -249,11 +337,11 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
                         hd = (hd & keep) | (hdv0 << sh);
                     }
                     {
-                        const uint32_t c_lo = rc & 3u, c_hi = (rc >> 8) & 3u;
-                        const uint32_t sel = c_lo | ((c_lo | 8u) << 4) | ((c_hi | 4u) << 8) | ((c_hi | 12u) << 12);
                         Smx16Col c;
-                        c.hd = hd; c.fu = fu; c.hugo = smx16_add(hu, ngo2); c.h = 0; c.f = 0; c.w_lo = 0; c.w_hi = 0;
+                        c.hd = hd; c.fu = fu; c.hugo = smx16_add(hu, ngo2); c.h = 0; c.f = 0; c.w_lo = 0; c.w_hi = 0; c.w_lo2 = 0; c.w_hi2 = 0; c.one = one;
                         Smx16Cell<K, 0>::run(Hl, Hlgo, El, plo, phi, c, sel, nge2, ngo2);
+                        c.w_lo |= c.w_lo2;
+                        c.w_hi |= c.w_hi2;
                         hd = hu;  // H[i0-1][j] is the diagonal input of the next column
                         out_h = c.h;
                         out_f = c.f;
@@ -297,6 +385,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
                             }
                         }
                     }
+                }
                 }
                 rch2 = rch1;
                 rch1 = rch0;
