@@ -14,6 +14,7 @@
 #include "smx_common.cuh"
 #include "smx_dp.cuh"
 #include "smx_dp16.cuh"
+#include "smx_dp16h.cuh"
 #include "smx_scan.cuh"
 #include "smx_traceback.cuh"
 
@@ -47,6 +48,7 @@ struct smx_handle {
     std::string err;
     int64_t trace_budget = (int64_t)40 << 30;  // clamped to a quarter of the free device memory at creation
     bool use_s16 = true;  // SMX_S16=0 forces the int32 kernels (cross-check)
+    bool use_s16h = true;  // diagonal-frame u16x2 kernel (smx_dp16h.cuh) when the scoring allows it; SMX_S16H=0 keeps smx_dp16.cuh
     int s16_max_wsel = 1;  // warps per problem of the s16 kernel are capped at 2 (measured best); SMX_S16_MAXW=1|2|4|8 overrides
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float last_ms = 0.f;
@@ -298,10 +300,30 @@ static int problem_class(int m, int mode)
 }
 
 // classes 10 (warp per problem) and 11 (CTA per problem): packed s16x2 kernel, smx_dp16.cuh
+// scoring-level condition of the diagonal-frame kernel (smx_dp16h.cuh): stored values never fall along a diagonal
+// (mismatch + 2 ge >= 0), profile bytes s + go + ge fit 0..127
+static bool s16h_scoring_ok(const SmxScoring &sc)
+{
+    if (sc.go > 100 || sc.ge > 100) return false;
+    const int lo = std::min(std::min(sc.match, sc.mismatch), 0), hi = std::max(std::max(sc.match, sc.mismatch), 0);
+    return lo + 2 * sc.ge >= 0 && lo + sc.go + sc.ge >= 0 && hi + sc.go + sc.ge <= 127;
+}
+
 static bool s16_eligible(const smx_handle *h, int64_t s2_off, int m, int n, int mode)
 {
     if (mode == SMX_MODE_SW || m <= 256) return false;
     const SmxScoring &sc = h->sc;
+    if (h->use_s16h) {
+        // biased unsigned halves: BIAS + H^ <= BIAS + max(match, 0) * min(rows, cols) + ge * (rows + cols), with the
+        // padded rows and the 96 extra steps a band pair runs past / before the matrix, plus their growth
+        const int64_t rows = (int64_t)(((m + 255) / 256 + 1) / 2) * 512, cols = (int64_t)n + 96;
+        const int64_t bias = 3ll * sc.go + std::abs(sc.go - sc.ge) + 16;
+        const int64_t top = bias + (int64_t)std::max(sc.match, 0) * std::min(rows, cols) + (int64_t)sc.ge * (rows + cols) +
+                            96ll * (std::abs(sc.match) + sc.go + 2 * sc.ge) + 64;
+        if (top > 65000) return false;
+        const int64_t b0 = s2_off / 64, b1 = (s2_off + n - 1) / 64 + 1;
+        return h->pool_nonacgt[(size_t)b1] - h->pool_nonacgt[(size_t)b0] == 0;
+    }
     if (sc.go > 256 || sc.ge > 256) return false;
     const int64_t m_pad = (int64_t)(((m + 255) / 256 + 1) / 2) * 512;
     if ((int64_t)sc.go * 3 + (int64_t)sc.ge * (m_pad + n) + 256 > 31000) return false;
@@ -342,6 +364,8 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
     {
         const char *env = getenv("SMX_S16");
         h->use_s16 = !(env && env[0] == '0');
+        const char *envh = getenv("SMX_S16H");
+        h->use_s16h = !(envh && envh[0] == '0') && s16h_scoring_ok(h->sc);
         const char *mw = getenv("SMX_S16_MAXW");
         h->s16_max_wsel = 1;
         if (mw) { const int v = atoi(mw); h->s16_max_wsel = v >= 8 ? 3 : v >= 4 ? 2 : v >= 2 ? 1 : 0; }
@@ -475,7 +499,8 @@ static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_id
     const bool TEAM = W > 1;
     const int threads = TEAM ? W * 32 : 128;
     int occ = 0;
-    SMX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, smx_dp_forward16<W>, threads, 0));
+    void (*kern)(const SmxFwdArgs) = h->use_s16h ? smx_dp_forward16h<W> : smx_dp_forward16<W>;
+    SMX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
     if (occ < 1) occ = 1;
     const int per_block = TEAM ? 1 : threads / 32;
     int blocks = std::min(h->sm_count * occ, (count + per_block - 1) / per_block);
@@ -494,7 +519,7 @@ static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_id
     a.results = (SmxResult *)h->d_results.p;
     a.sc = h->sc;
     a.one = 1u;
-    smx_dp_forward16<W><<<blocks, threads, 0, h->stream>>>(a);
+    kern<<<blocks, threads, 0, h->stream>>>(a);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
     return mark(h, cls);

@@ -43,9 +43,9 @@ __device__ __forceinline__ uint32_t smx16_max_tr(uint32_t a, uint32_t b, uint32_
 {
     uint32_t r;
     asm("{.reg .pred pu, pv; .reg .s16 r0, r1, r2, r3;\n\t"
+        "mov.b32 {r2, r3}, %3;\n\t"  // read a before %0 is written: the output may share its register
         "max.s16x2 %0, %3, %4;\n\t"
         "mov.b32 {r0, r1}, %0;\n\t"
-        "mov.b32 {r2, r3}, %3;\n\t"
         "setp.eq.s16 pv, r0, r2;\n\t"
         "setp.eq.s16 pu, r1, r3;\n\t"
         "@!pv mad.lo.u32 %1, %6, %5, %1;\n\t"
@@ -62,9 +62,9 @@ __device__ __forceinline__ uint32_t smx16_max_tr_first(uint32_t a, uint32_t b, u
 {
     uint32_t r;
     asm("{.reg .pred pu, pv; .reg .s16 r0, r1, r2, r3;\n\t"
+        "mov.b32 {r2, r3}, %3;\n\t"  // read a before %0 is written: the output may share its register
         "max.s16x2 %0, %3, %4;\n\t"
         "mov.b32 {r0, r1}, %0;\n\t"
-        "mov.b32 {r2, r3}, %3;\n\t"
         "setp.eq.s16 pv, r0, r2;\n\t"
         "setp.eq.s16 pu, r1, r3;\n\t"
         "selp.b32 %1, 0, %5, pv;\n\t"

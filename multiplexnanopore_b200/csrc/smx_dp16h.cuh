@@ -1,0 +1,402 @@
+// Forward affine-gap DP on packed u16x2 lanes in the "diagonal frame": two bands of a problem per warp, five ALU
+// instructions per cell pair.
+//
+// Same recurrence, tie rules, direction bits and trace layout as smx_dp16.cuh (the traceback kernel cannot tell the
+// two apart), but the values are stored shifted by the gap-extension cost of their anti-diagonal,
+//     X^(i, j) = X(i, j) + ge * (i + j)                       for X in {H, E, F},
+// which turns a gap extension into a plain copy:
+//     E^(i, j) = max(E^(i, j-1), Hc(i, j-1))                   Hc := H^ - (go - ge)
+//     F^(i, j) = max(F^(i-1, j), Hc(i-1, j))
+//     H^(i, j) = max(Hc(i-1, j-1) + s'', E^, F^)               s'' := s(q_i, r_j) + go + ge  (>= 0, in the profile)
+// All three candidates of a cell are shifted by the same amount, so every comparison -- and with it every direction
+// bit and every tie -- is the one the unshifted recurrence makes.  Values are kept as UNSIGNED 16-bit halves with a
+// small bias, and both remaining additions only ever add a non-negative amount to, or subtract a constant from,
+// a half that cannot wrap: they are ordinary 32-bit integer adds (FMA pipe on sm_100a, which would otherwise idle),
+// and the integer ALU pipe -- two cycles per warp instruction, the binding resource of smx_dp16.cuh -- is left with
+// four VIMNMX.U16x2 and one PRMT per cell pair.
+//
+// Eligibility (host, smx_api.cu: s16h_eligible): as smx_dp16.cuh, plus mismatch + 2*ge >= 0 (values never fall along
+// a diagonal), match + go + ge <= 127, and the biased range bound below 65000.
+#pragma once
+#include "smx_dp16.cuh"
+
+// max.u16x2 with both "a won or tied" predicates (ptxas fuses this into one VIMNMX.U16x2 with two predicate
+// outputs); when b won strictly the flag IMM is added to the direction word of the low / high band.
+template <uint32_t IMM>
+__device__ __forceinline__ uint32_t smx16h_max_tr(uint32_t a, uint32_t b, uint32_t &w_lo, uint32_t &w_hi, uint32_t one)
+{
+    uint32_t r;
+    asm("{.reg .pred pu, pv; .reg .u16 r0, r1, r2, r3;\n\t"
+        "mov.b32 {r2, r3}, %3;\n\t"  // read a before %0 is written: the output may share its register
+        "max.u16x2 %0, %3, %4;\n\t"
+        "mov.b32 {r0, r1}, %0;\n\t"
+        "setp.eq.u16 pv, r0, r2;\n\t"
+        "setp.eq.u16 pu, r1, r3;\n\t"
+        "@!pv mad.lo.u32 %1, %6, %5, %1;\n\t"
+        "@!pu mad.lo.u32 %2, %6, %5, %2;}\n\t"
+        : "=r"(r), "+r"(w_lo), "+r"(w_hi)
+        : "r"(a), "r"(b), "n"(IMM), "r"(one));
+    return r;
+}
+
+struct Smx16hCol {  // per-column scalars threaded through the K cells of a lane
+    uint32_t hd;    // Hc(i-1, j-1): diagonal input of the current row
+    uint32_t fu;    // F^(i-1, j)
+    uint32_t hcu;   // Hc(i-1, j)
+    uint32_t w_lo[2], w_hi[2];  // direction-bit accumulators; K = 8: even / odd rows of one word, K = 16: rows 0-7 / 8-15
+    uint32_t one;
+};
+
+template <int K, int k>
+struct Smx16hCell {
+    static __device__ __forceinline__ void run(uint32_t (&Hc)[K], uint32_t (&El)[K], const uint32_t (&plo)[K], const uint32_t (&phi)[K],
+                                               Smx16hCol &c, uint32_t sel, uint32_t negc2)
+    {
+        constexpr int A = K == 8 ? (k & 1) : (k >> 3);
+        constexpr int SH = 4 * (k & 7);
+        uint32_t &n_lo = c.w_lo[A];
+        uint32_t &n_hi = c.w_hi[A];
+        const uint32_t e = smx16h_max_tr<(4u << SH)>(El[k], Hc[k], n_lo, n_hi, c.one);   // extend | open
+        const uint32_t f = smx16h_max_tr<(8u << SH)>(c.fu, c.hcu, n_lo, n_hi, c.one);
+        const uint32_t hdiag = c.hd + smx_subst_u(plo[k], phi[k], sel);  // no carry between the halves: s'' >= 0, no wrap
+        const uint32_t t = smx16h_max_tr<(2u << SH)>(f, e, n_lo, n_hi, c.one);
+        const uint32_t h = smx16h_max_tr<(1u << SH)>(hdiag, t, n_lo, n_hi, c.one);
+        const uint32_t hc = h + negc2;  // - (go - ge) in both halves; the low half never borrows (bias)
+        c.hd = Hc[k];
+        Hc[k] = hc;
+        El[k] = e;
+        c.fu = f;
+        c.hcu = hc;
+        Smx16hCell<K, k + 1>::run(Hc, El, plo, phi, c, sel, negc2);
+    }
+};
+template <int K>
+struct Smx16hCell<K, K> {
+    static __device__ __forceinline__ void run(uint32_t (&)[K], uint32_t (&)[K], const uint32_t (&)[K], const uint32_t (&)[K], Smx16hCol &, uint32_t,
+                                               uint32_t) {}
+};
+
+// per-row substitution profile in the diagonal frame: byte c = s(query base, reference code c) + go + ge (0..127);
+// a query wildcard / padding row scores 0 against everything
+__device__ __forceinline__ uint32_t smx16h_profile(int qcode, int ma2, int mi2, int wild2)
+{
+    if (qcode > 3) return (uint32_t)wild2 * 0x01010101u;
+    uint32_t p = (uint32_t)mi2 * 0x01010101u;
+    p &= ~(0xffu << (8 * qcode));
+    p |= (uint32_t)ma2 << (8 * qcode);
+    return p;
+}
+
+__device__ __forceinline__ uint32_t smx16h_pack(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+__device__ __forceinline__ int smx16h_lo(uint32_t v) { return (int)(v & 0xffffu); }
+__device__ __forceinline__ int smx16h_hi(uint32_t v) { return (int)(v >> 16); }
+
+// One interior 32-column chunk of a band pair (see smx16_fast_chunk for the structure).  `tconst` turns the
+// stored half of the last query row back into H (semi-global end in the last row): H = half - ge * j + tconst.
+template <int K, bool HAS_HI, bool TRACK>
+__device__ __forceinline__ void smx16h_fast_chunk(uint32_t (&Hc)[K], uint32_t (&El)[K], const uint32_t (&plo)[K], const uint32_t (&phi)[K],
+                                                  uint32_t &hd, uint32_t &out_h, uint32_t &out_f, uint32_t &sel_prev, const uint4 *tops,
+                                                  uint32_t lane0_mask, uint32_t negc2, uint32_t *tp_lo, uint32_t *tp_hi, uint32_t *bl, uint32_t *bh,
+                                                  uint32_t st_flags, uint32_t tmask, int last_k, int jbase, int ge, int tconst, int &row_best,
+                                                  int &row_best_j, uint32_t one)
+{
+    SMX16_PRAGMA(unroll SMX16_UNROLL)
+    for (int ss = 0; ss < 32; ++ss) {
+        uint32_t hu = __shfl_up_sync(SMX_FULL_MASK, out_h, 1);
+        uint32_t fu = __shfl_up_sync(SMX_FULL_MASK, out_f, 1);
+        uint32_t sel = __shfl_up_sync(SMX_FULL_MASK, sel_prev, 1);
+        const uint4 tv = tops[ss];
+        hu = (tv.x & lane0_mask) | (hu & ~lane0_mask);
+        fu = (tv.y & lane0_mask) | (fu & ~lane0_mask);
+        sel = (tv.z & lane0_mask) | (sel & ~lane0_mask);
+        sel_prev = sel;
+        Smx16hCol c;
+        c.hd = hd; c.fu = fu; c.hcu = hu; c.w_lo[0] = 0; c.w_lo[1] = 0; c.w_hi[0] = 0; c.w_hi[1] = 0; c.one = one;
+        Smx16hCell<K, 0>::run(Hc, El, plo, phi, c, sel, negc2);
+        hd = hu;
+        out_h = c.hcu;
+        out_f = c.fu;
+        tp_lo[ss * 32] = c.w_lo[0] | c.w_lo[1];
+        if (HAS_HI) tp_hi[ss * 32] = c.w_hi[0] | c.w_hi[1];
+        uint32_t fl = st_flags;
+        asm volatile("" : "+r"(fl));  // keeps the store predicates short-lived (VIMNMX needs the predicate registers)
+        if (fl & 1u) __stcg(&bl[ss], __byte_perm(out_h, out_f, 0x5410));
+        if (HAS_HI) { if (fl & 2u) __stcg(&bh[ss], __byte_perm(out_h, out_f, 0x7632)); }
+        if (TRACK) {
+            uint32_t tm = tmask;
+            asm volatile("" : "+r"(tm));
+            if (tm) {  // the lane that owns the last query row
+                uint32_t hw = Hc[0];
+#pragma unroll
+                for (int k = 1; k < K; ++k) if (k == last_k) hw = Hc[k];
+                const int jj = jbase + ss;
+                const int hv = ((tm & 1u) ? smx16h_lo(hw) : smx16h_hi(hw)) - ge * jj + tconst;
+                if (hv > row_best) { row_best = hv; row_best_j = jj; }
+            }
+        }
+    }
+}
+
+// boundary lines: one uint32 per column = F^ << 16 | Hc (biased unsigned halves)
+template <int W>
+__global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM / (W == 1 ? 4 : W)) smx_dp_forward16h(const SmxFwdArgs a)
+{
+    constexpr int K = 8;
+    constexpr bool TEAM = W > 1;
+    constexpr int LAG = SMX16_LAG;
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int worker = TEAM ? blockIdx.x : ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    uint32_t *line0 = reinterpret_cast<uint32_t *>(a.boundary + (size_t)worker * 2 * (size_t)a.nmax);
+    uint32_t *line1 = line0 + a.nmax;
+    const int go = a.sc.go, ge = a.sc.ge;
+    const int cc = go - ge;                                   // Hc = H^ - cc
+    const int BIAS = 3 * go + (cc < 0 ? -cc : cc) + 16;       // stored half = value + BIAS > 0
+    const uint32_t negc2 = (uint32_t)(-cc) * 0x00010001u;     // 32-bit add that subtracts cc from both halves
+    const int ma2 = a.sc.match + go + ge, mi2 = a.sc.mismatch + go + ge, wild2 = go + ge;
+    const uint32_t lane0_mask = lane == 0 ? 0xffffffffu : 0u;
+    const uint32_t one = a.one;  // 1, but unknown to ptxas: keeps the predicated flag updates on the FMA pipe (IMAD)
+    const int u_edge = BIAS - 2 * go;       // Hc of row -1 / column -1 (global start): H = -(go + x ge)  ->  H^ = -go - ge
+    const int u_corner = BIAS - ge - go;    // Hc(-1, -1): H = 0 -> H^ = -2 ge
+    const int u_free = BIAS - ge - cc;      // free start: H = 0 at (x, -1) / (-1, x)  ->  Hc = ge * x + u_free
+
+    __shared__ int s_ticket;
+    __shared__ volatile int s_prog[W];
+    __shared__ int s_red[W][6];
+    __shared__ uint4 s_top[W == 1 ? 4 : W][32];
+
+    for (;;) {
+        int ticket = 0;
+        if (TEAM) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1);
+            if (threadIdx.x < W) s_prog[threadIdx.x] = -1;
+            __syncthreads();
+            ticket = s_ticket;
+        } else {
+            if (lane == 0) ticket = atomicAdd(a.ticket, 1);
+            ticket = __shfl_sync(SMX_FULL_MASK, ticket, 0);
+        }
+        if (ticket >= a.n_order) break;
+        const int pid = a.order[ticket];
+        const SmxProblem pr = a.probs[pid];
+        const int m = pr.m, n = pr.n, mode = pr.mode & SMX_MODE_MASK;
+        const bool free_beg = mode == 2;  // SMX_MODE_SG_QB_DB
+        const uint8_t *s1 = a.pool + pr.s1_off;
+        const uint8_t *s2 = a.pool + pr.s2_off;
+        uint32_t *trace = reinterpret_cast<uint32_t *>(a.trace + pr.trace_off);
+        const int nbands = (m + 32 * K - 1) / (32 * K);
+        const int npairs = (nbands + 1) >> 1;
+        const int steps = n + 31;          // steps of one band (trace layout)
+        const int psteps = steps + LAG;    // steps of a band pair
+        const int nchunks = (psteps + 31) >> 5;
+        // H(i, j) = half - BIAS + cc - ge * (i + j)
+        const int hconst = cc - BIAS;
+
+        int col_best = SMX_NEG_INF, col_best_i = 0x7fffffff;
+        int row_best = SMX_NEG_INF, row_best_j = 0;
+        int corner = 0;
+        const int last_band_idx = nbands - 1;
+        const int last_lane = ((m - 1) % (32 * K)) / K;
+        const int last_k = (m - 1) % K;
+
+        for (int pair = wib % W; pair < npairs; pair += W) {
+            const int band_lo = 2 * pair, band_hi = 2 * pair + 1;
+            const bool has_hi = band_hi < nbands;
+            const int i0_lo = band_lo * 32 * K + lane * K, i0_hi = band_hi * 32 * K + lane * K;
+            const uint32_t *top_lo = line0;  // band_lo is even: reads line0, writes line1; band_hi the other way round
+            uint32_t *bot_lo = line1;
+            const uint32_t *top_hi = line1;
+            uint32_t *bot_hi = line0;
+            const bool lo_is_last = band_lo == last_band_idx, hi_is_last = band_hi == last_band_idx;
+
+            uint32_t plo[K], phi[K];
+            uint32_t Hc[K], El[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int il = i0_lo + k, ih = i0_hi + k;
+                plo[k] = smx16h_profile(il < m ? smx_code(s1[il]) : 4, ma2, mi2, wild2);
+                phi[k] = smx16h_profile(ih < m ? smx_code(s1[ih]) : 4, ma2, mi2, wild2);
+                Hc[k] = free_beg ? smx16h_pack(ge * il + u_free, ge * ih + u_free) : smx16h_pack(u_edge, u_edge);  // column -1
+                El[k] = 0u;                                                                                        // E^ = -inf
+            }
+            // Hc(i0 - 1, -1): diagonal input of the first row at column 0
+            uint32_t hd = smx16h_pack(i0_lo == 0 ? u_corner : (free_beg ? ge * (i0_lo - 1) + u_free : u_edge),
+                                      free_beg ? ge * (i0_hi - 1) + u_free : u_edge);
+            uint32_t out_h = 0, out_f = 0, sel_prev = 0;
+            int rch1 = 0, rch2 = 0;  // reference codes of the two previous chunks (the high half reads 64 columns back)
+            const bool st_lo = lane == 31 && !lo_is_last, st_hi = lane == 31 && has_hi && !hi_is_last;
+            const bool track_lo = mode == 1 && lo_is_last, track_hi = mode == 1 && hi_is_last;
+
+            for (int s0 = 0, chunk = 0; s0 < psteps; s0 += 32, ++chunk) {
+                if (TEAM && pair > 0) {
+                    const int need = (pair - 1) * nchunks + min(chunk + 4, nchunks);
+                    if (lane == 0) { while (s_prog[(pair - 1) % W] < need) __nanosleep(64); }
+                    __syncwarp();
+                    __threadfence_block();
+                }
+                __syncwarp();
+                // chunk prefetch: lane l holds column s0 + l (low band inputs) and column s0 + l - LAG (high band top line)
+                const int jc = s0 + lane;
+                const int jb = jc - LAG;
+                // row above the low band / above the high band: (Hc, F^ = -inf); band 0 reads the matrix edge
+                uint32_t topA = smx16h_pack(free_beg ? ge * jc + u_free : u_edge, 0);
+                uint32_t topB = smx16h_pack(u_edge, 0);
+                int rch0 = 0;
+                if (jc < n) {
+                    if (band_lo != 0) topA = __ldcg(&top_lo[jc]);
+                    rch0 = smx_code(s2[jc]) & 3;
+                }
+                if (jb >= 0 && jb < n) topB = __ldcg(&top_hi[jb]);
+                {
+                    const uint32_t c_lo = (uint32_t)rch0, c_hi = (uint32_t)rch2;
+                    uint4 tv;
+                    tv.x = (topA & 0xffffu) | (topB << 16);
+                    tv.y = (topA >> 16) | (topB & 0xffff0000u);
+                    tv.z = c_lo | ((c_lo | 8u) << 4) | ((c_hi | 4u) << 8) | ((c_hi | 12u) << 12);
+                    tv.w = 0u;
+                    s_top[wib][lane] = tv;
+                    __syncwarp();
+                }
+                if (s0 >= 32 + LAG && s0 + 33 <= n) {
+                    uint32_t *tp_lo = trace + ((size_t)band_lo * steps + s0) * 32 + lane;
+                    uint32_t *tp_hi = trace + ((size_t)band_hi * steps + (s0 - LAG)) * 32 + lane;
+                    uint32_t *bl = bot_lo + (s0 - 31);
+                    uint32_t *bh = bot_hi + (s0 - 31 - LAG);
+                    const uint32_t st_flags = (st_lo ? 1u : 0u) | (st_hi ? 2u : 0u);
+                    if (track_lo | track_hi) {
+                        const int jbase = s0 - lane - (track_lo ? 0 : LAG);
+                        const uint32_t tmask = lane == last_lane ? (track_lo ? 0x0000ffffu : 0xffff0000u) : 0u;
+                        const int tconst = hconst - ge * (m - 1);
+                        if (has_hi) smx16h_fast_chunk<K, true, true>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, ge, tconst, row_best, row_best_j, one);
+                        else smx16h_fast_chunk<K, false, true>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, ge, tconst, row_best, row_best_j, one);
+                    } else {
+                        if (has_hi) smx16h_fast_chunk<K, true, false>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one);
+                        else smx16h_fast_chunk<K, false, false>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one);
+                    }
+                } else {
+                    const int send = min(32, psteps - s0);
+#pragma unroll 1
+                    for (int ss = 0; ss < send; ++ss) {
+                        const int s = s0 + ss;
+                        uint32_t hu = __shfl_up_sync(SMX_FULL_MASK, out_h, 1);
+                        uint32_t fu = __shfl_up_sync(SMX_FULL_MASK, out_f, 1);
+                        uint32_t sel = __shfl_up_sync(SMX_FULL_MASK, sel_prev, 1);
+                        const uint4 tv = s_top[wib][ss];
+                        if (lane == 0) { hu = tv.x; fu = tv.y; sel = tv.z; }
+                        sel_prev = sel;
+                        const int j_lo = s - lane, j_hi = s - lane - LAG;
+                        const bool v_lo = j_lo >= 0 && j_lo < n;
+                        const bool v_hi = has_hi && j_hi >= 0 && j_hi < n;
+                        // Both halves are computed on every step (no divergence); a half whose column is still left of
+                        // the matrix produces values nobody reads, and its state is (re)set to the boundary column at
+                        // the step where it enters the matrix.  A half right of the matrix is finished.
+                        if (j_lo == 0 || j_hi == 0) {
+                            const uint32_t keep = j_lo == 0 ? 0xffff0000u : 0x0000ffffu;  // the other half keeps its state
+                            const int i0 = j_lo == 0 ? i0_lo : i0_hi;
+                            const int sh = j_lo == 0 ? 0 : 16;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                const uint32_t hv = (uint32_t)(free_beg ? ge * (i0 + k) + u_free : u_edge) & 0xffffu;
+                                Hc[k] = (Hc[k] & keep) | (hv << sh);
+                                El[k] = El[k] & keep;
+                            }
+                            const uint32_t hdv0 = (uint32_t)(i0 == 0 ? u_corner : (free_beg ? ge * (i0 - 1) + u_free : u_edge)) & 0xffffu;
+                            hd = (hd & keep) | (hdv0 << sh);
+                        }
+                        Smx16hCol c;
+                        c.hd = hd; c.fu = fu; c.hcu = hu; c.w_lo[0] = 0; c.w_lo[1] = 0; c.w_hi[0] = 0; c.w_hi[1] = 0; c.one = one;
+                        Smx16hCell<K, 0>::run(Hc, El, plo, phi, c, sel, negc2);
+                        hd = hu;  // Hc(i0-1, j) is the diagonal input of the next column
+                        out_h = c.hcu;
+                        out_f = c.fu;
+                        if (v_lo) {
+                            trace[((size_t)band_lo * steps + s) * 32 + lane] = c.w_lo[0] | c.w_lo[1];
+                            if (lane == 31 && !lo_is_last) __stcg(&bot_lo[j_lo], (out_h & 0xffffu) | (out_f << 16));
+                        }
+                        if (v_hi) {
+                            trace[((size_t)band_hi * steps + (s - LAG)) * 32 + lane] = c.w_hi[0] | c.w_hi[1];
+                            if (lane == 31 && !hi_is_last) __stcg(&bot_hi[j_hi], (out_h >> 16) | (out_f & 0xffff0000u));
+                        }
+                        // end-cell candidates (rare paths, scalar): back to H = half + hconst - ge * (i + j)
+                        if (v_lo && j_lo == n - 1) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                const int i = i0_lo + k, hv = smx16h_lo(Hc[k]) + hconst - ge * (i + n - 1);
+                                if (i < m - 1 && hv > col_best) { col_best = hv; col_best_i = i; }
+                                if (i == m - 1) corner = hv;
+                            }
+                        }
+                        if (v_hi && j_hi == n - 1) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                const int i = i0_hi + k, hv = smx16h_hi(Hc[k]) + hconst - ge * (i + n - 1);
+                                if (i < m - 1 && hv > col_best) { col_best = hv; col_best_i = i; }
+                                if (i == m - 1) corner = hv;
+                            }
+                        }
+                        if (mode == 1 && lane == last_lane) {
+                            if (lo_is_last && v_lo) {
+                                uint32_t hw = Hc[0];
+#pragma unroll
+                                for (int k = 1; k < K; ++k) if (k == last_k) hw = Hc[k];
+                                const int hv = smx16h_lo(hw) + hconst - ge * (m - 1 + j_lo);
+                                if (hv > row_best) { row_best = hv; row_best_j = j_lo; }
+                            }
+                            if (hi_is_last && v_hi) {
+                                uint32_t hw = Hc[0];
+#pragma unroll
+                                for (int k = 1; k < K; ++k) if (k == last_k) hw = Hc[k];
+                                const int hv = smx16h_hi(hw) + hconst - ge * (m - 1 + j_hi);
+                                if (hv > row_best) { row_best = hv; row_best_j = j_hi; }
+                            }
+                        }
+                    }
+                }
+                rch2 = rch1;
+                rch1 = rch0;
+                if (TEAM) {
+                    if (lane == 31) { __threadfence_block(); s_prog[wib] = pair * nchunks + chunk + 1; }
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- end cell / score (same combination as smx_dp_forward) ----
+        SmxResult r;
+        r.beg_q = 0; r.beg_r = 0; r.n_runs = 0; r.run_start = 0; r.n_s = 0; r.n_h = 0; r.pad0 = 0; r.pad1 = 0; r.pad2 = 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const int ob = __shfl_xor_sync(SMX_FULL_MASK, col_best, off);
+            const int oi = __shfl_xor_sync(SMX_FULL_MASK, col_best_i, off);
+            if (ob > col_best || (ob == col_best && oi < col_best_i)) { col_best = ob; col_best_i = oi; }
+        }
+        const int owner = TEAM ? (((nbands - 1) >> 1) % W) : 0;  // warp that ran the last band
+        row_best = __shfl_sync(SMX_FULL_MASK, row_best, last_lane);
+        row_best_j = __shfl_sync(SMX_FULL_MASK, row_best_j, last_lane);
+        corner = __shfl_sync(SMX_FULL_MASK, corner, last_lane);
+        if (TEAM) {
+            if (lane == 0) {
+                s_red[wib][0] = col_best; s_red[wib][1] = col_best_i;
+                if (wib == owner) { s_red[0][2] = row_best; s_red[0][3] = row_best_j; s_red[0][4] = corner; }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int w = 1; w < W; ++w) {
+                    const int ob = s_red[w][0], oi = s_red[w][1];
+                    if (ob > col_best || (ob == col_best && oi < col_best_i)) { col_best = ob; col_best_i = oi; }
+                }
+                row_best = s_red[0][2]; row_best_j = s_red[0][3]; corner = s_red[0][4];
+            }
+        }
+        if (mode == 1) {  // SMX_MODE_SG_QE_DE
+            int best = SMX_NEG_INF, bi = m - 1, bj = n - 1;
+            if (col_best > best) { best = col_best; bi = col_best_i; bj = n - 1; }
+            if (row_best > best) { best = row_best; bi = m - 1; bj = row_best_j; }
+            r.score = best; r.end_q = bi; r.end_r = bj;
+        } else {
+            r.score = corner; r.end_q = m - 1; r.end_r = n - 1;
+        }
+        if (TEAM ? (threadIdx.x == 0) : (lane == 0)) a.results[pid] = r;
+    }
+}
