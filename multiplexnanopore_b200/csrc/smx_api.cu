@@ -46,8 +46,9 @@ struct smx_handle {
     bool owns_stream = false;
     int sm_count = 148;
     std::string err;
-    int64_t trace_budget = (int64_t)40 << 30;  // clamped to a quarter of the free device memory at creation
+    int64_t trace_budget = (int64_t)24 << 30;  // clamped to a sixth of the free device memory at creation
     bool use_s16 = true;  // SMX_S16=0 forces the int32 kernels (cross-check)
+    int s16_min_rows = 128;  // the diagonal-frame kernel takes problems of more rows than this (SMX_S16_MINROWS overrides)
     bool use_s16h = true;  // diagonal-frame u16x2 kernel (smx_dp16h.cuh) when the scoring allows it; SMX_S16H=0 keeps smx_dp16.cuh
     int s16_max_wsel = 1;  // warps per problem of the s16 kernel are capped at 2 (measured best); SMX_S16_MAXW=1|2|4|8 overrides
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -199,7 +200,7 @@ extern "C" int smx_create(smx_handle **out, int device_ordinal, void *stream)
     cudaEventCreate(&h->ev1);
     {
         size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) h->trace_budget = std::max<int64_t>((int64_t)2 << 30, std::min<int64_t>(h->trace_budget, (int64_t)(free_b / 4)));
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) h->trace_budget = std::max<int64_t>((int64_t)2 << 30, std::min<int64_t>(h->trace_budget, (int64_t)(free_b / 6)));
     }
     if (const char *tb = getenv("SMX_TRACE_BUDGET_GB")) { const long v = atol(tb); if (v >= 1 && v <= 160) h->trace_budget = (int64_t)v << 30; }
     *out = h;
@@ -311,7 +312,7 @@ static bool s16h_scoring_ok(const SmxScoring &sc)
 
 static bool s16_eligible(const smx_handle *h, int64_t s2_off, int m, int n, int mode)
 {
-    if (mode == SMX_MODE_SW || m <= 256) return false;
+    if (mode == SMX_MODE_SW || m <= (h->use_s16h ? h->s16_min_rows : 256)) return false;
     const SmxScoring &sc = h->sc;
     if (h->use_s16h) {
         // biased unsigned halves: BIAS + H^ <= BIAS + max(match, 0) * min(rows, cols) + ge * (rows + cols), with the
@@ -364,6 +365,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
     {
         const char *env = getenv("SMX_S16");
         h->use_s16 = !(env && env[0] == '0');
+        if (const char *mr = getenv("SMX_S16_MINROWS")) { const int v = atoi(mr); if (v >= 32 && v <= 4096) h->s16_min_rows = v; }
         const char *envh = getenv("SMX_S16H");
         h->use_s16h = !(envh && envh[0] == '0') && s16h_scoring_ok(h->sc);
         const char *mw = getenv("SMX_S16_MAXW");

@@ -22,22 +22,40 @@
 
 // max.u16x2 with both "a won or tied" predicates (ptxas fuses this into one VIMNMX.U16x2 with two predicate
 // outputs); when b won strictly the flag IMM is added to the direction word of the low / high band.
-template <uint32_t IMM>
+// FMA = true: the flag is dropped by a predicated IMAD (w = one * IMM + w, FMA pipe); false: by a predicated OR (ALU
+// pipe).  The cell uses both so that neither integer pipe carries all 64 flag updates of a column step.
+template <uint32_t IMM, bool FMA>
 __device__ __forceinline__ uint32_t smx16h_max_tr(uint32_t a, uint32_t b, uint32_t &w_lo, uint32_t &w_hi, uint32_t one)
 {
     uint32_t r;
-    asm("{.reg .pred pu, pv; .reg .u16 r0, r1, r2, r3;\n\t"
-        "mov.b32 {r2, r3}, %3;\n\t"  // read a before %0 is written: the output may share its register
-        "max.u16x2 %0, %3, %4;\n\t"
-        "mov.b32 {r0, r1}, %0;\n\t"
-        "setp.eq.u16 pv, r0, r2;\n\t"
-        "setp.eq.u16 pu, r1, r3;\n\t"
-        "@!pv mad.lo.u32 %1, %6, %5, %1;\n\t"
-        "@!pu mad.lo.u32 %2, %6, %5, %2;}\n\t"
-        : "=r"(r), "+r"(w_lo), "+r"(w_hi)
-        : "r"(a), "r"(b), "n"(IMM), "r"(one));
+    if (FMA) {
+        asm("{.reg .pred pu, pv; .reg .u16 r0, r1, r2, r3;\n\t"
+            "mov.b32 {r2, r3}, %3;\n\t"  // read a before %0 is written: the output may share its register
+            "max.u16x2 %0, %3, %4;\n\t"
+            "mov.b32 {r0, r1}, %0;\n\t"
+            "setp.eq.u16 pv, r0, r2;\n\t"
+            "setp.eq.u16 pu, r1, r3;\n\t"
+            "@!pv mad.lo.u32 %1, %6, %5, %1;\n\t"
+            "@!pu mad.lo.u32 %2, %6, %5, %2;}\n\t"
+            : "=r"(r), "+r"(w_lo), "+r"(w_hi)
+            : "r"(a), "r"(b), "n"(IMM), "r"(one));
+    } else {
+        asm("{.reg .pred pu, pv; .reg .u16 r0, r1, r2, r3;\n\t"
+            "mov.b32 {r2, r3}, %3;\n\t"
+            "max.u16x2 %0, %3, %4;\n\t"
+            "mov.b32 {r0, r1}, %0;\n\t"
+            "setp.eq.u16 pv, r0, r2;\n\t"
+            "setp.eq.u16 pu, r1, r3;\n\t"
+            "@!pv or.b32 %1, %1, %5;\n\t"
+            "@!pu or.b32 %2, %2, %5;}\n\t"
+            : "=r"(r), "+r"(w_lo), "+r"(w_hi)
+            : "r"(a), "r"(b), "n"(IMM));
+    }
     return r;
 }
+#ifndef SMX16H_ALU_FLAGS
+#define SMX16H_ALU_FLAGS 1  // how many of the four flag kinds of a cell go through the ALU pipe
+#endif
 
 struct Smx16hCol {  // per-column scalars threaded through the K cells of a lane
     uint32_t hd;    // Hc(i-1, j-1): diagonal input of the current row
@@ -56,11 +74,11 @@ struct Smx16hCell {
         constexpr int SH = 4 * (k & 7);
         uint32_t &n_lo = c.w_lo[A];
         uint32_t &n_hi = c.w_hi[A];
-        const uint32_t e = smx16h_max_tr<(4u << SH)>(El[k], Hc[k], n_lo, n_hi, c.one);   // extend | open
-        const uint32_t f = smx16h_max_tr<(8u << SH)>(c.fu, c.hcu, n_lo, n_hi, c.one);
+        const uint32_t e = smx16h_max_tr<(4u << SH), (SMX16H_ALU_FLAGS < 1)>(El[k], Hc[k], n_lo, n_hi, c.one);   // extend | open
+        const uint32_t f = smx16h_max_tr<(8u << SH), (SMX16H_ALU_FLAGS < 3)>(c.fu, c.hcu, n_lo, n_hi, c.one);
         const uint32_t hdiag = c.hd + smx_subst_u(plo[k], phi[k], sel);  // no carry between the halves: s'' >= 0, no wrap
-        const uint32_t t = smx16h_max_tr<(2u << SH)>(f, e, n_lo, n_hi, c.one);
-        const uint32_t h = smx16h_max_tr<(1u << SH)>(hdiag, t, n_lo, n_hi, c.one);
+        const uint32_t t = smx16h_max_tr<(2u << SH), (SMX16H_ALU_FLAGS < 2)>(f, e, n_lo, n_hi, c.one);
+        const uint32_t h = smx16h_max_tr<(1u << SH), (SMX16H_ALU_FLAGS < 4)>(hdiag, t, n_lo, n_hi, c.one);
         const uint32_t hc = h + negc2;  // - (go - ge) in both halves; the low half never borrows (bias)
         c.hd = Hc[k];
         Hc[k] = hc;
@@ -188,7 +206,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
         const int nbands = (m + 32 * K - 1) / (32 * K);
         const int npairs = (nbands + 1) >> 1;
         const int steps = n + 31;          // steps of one band (trace layout)
-        const int psteps = steps + LAG;    // steps of a band pair
+        const int psteps = nbands > 1 ? steps + LAG : steps;  // steps of a band pair (a single band has no trailing half)
         const int nchunks = (psteps + 31) >> 5;
         // H(i, j) = half - BIAS + cc - ge * (i + j)
         const int hconst = cc - BIAS;

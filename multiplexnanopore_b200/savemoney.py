@@ -107,8 +107,9 @@ _engine_pools = {}
 
 
 def _engines_for(engine, n):
-    """`n` engines on the device of `engine`: the caller's engine plus lazily created siblings.  Two handles
-    let the host stages (chain search, stitching) of one batch overlap the GPU stages of the next one."""
+    """`n` engines on the device of `engine`: the caller's engine plus lazily created siblings.  Several handles
+    in flight let the host stages (planning, stitching) of one batch overlap the GPU stages of the others, and
+    let kernels of different batches fill each other's tails (measured best on B200: 4 x 1000 reads)."""
     key = id(engine)
     pool = _engine_pools.setdefault(key, [engine])
     while len(pool) < n:
@@ -117,7 +118,7 @@ def _engines_for(engine, n):
 
 
 def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None, n_threads=0, batch_queries=1000,
-              overlap=2):
+              overlap=4):
     """The alignment stage for every (query, reference) pair and both strands (or the explicit `pairs`).
     Queries are processed in batches of `batch_queries` so that device workspaces stay bounded; `overlap`
     batches are in flight at once (one engine handle and one Python thread each; ctypes drops the GIL)."""

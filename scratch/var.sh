@@ -1,5 +1,5 @@
 #!/bin/bash
 for v in "$@"; do
 echo "== $v"
-SMX_LIB_PATH=scratch/var/$v.so python scratch/dpbench.py 3000x4000x2400 600x3000x12000 2>&1 | grep -v "W<=4\|W<=8"
+SMX_LIB_PATH=scratch/var/$v.so python scratch/dpbench.py 3000x4000x4736 2000x3000x9472 2>&1 | grep -v "W<=8" | sed 's/; tb.*//'
 done
