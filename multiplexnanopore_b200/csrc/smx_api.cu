@@ -406,21 +406,35 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         h->nmax = std::max(h->nmax, nn);
     }
     h->runs_scratch = runs_off;
-    // size-sorted order, then greedy chunking under the trace budget
+    // class-major order (largest kernel class first; counting sort), the large classes size-sorted inside so
+    // that their longest problems start first; then greedy chunking under the trace budget.  The small classes
+    // (86 % of the problems, 1 % of the cells) are left in input order.
     std::vector<int32_t> order((size_t)n);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
-        return (int64_t)h->probs[x].m * h->probs[x].n > (int64_t)h->probs[y].m * h->probs[y].n;
-    });
+    {
+        int cnt[kNumFwdClasses + 1] = {0};
+        for (int p = 0; p < n; ++p) cnt[kNumFwdClasses - 1 - h->probs[(size_t)p].cls + 1]++;
+        for (int c = 0; c < kNumFwdClasses; ++c) cnt[c + 1] += cnt[c];
+        int pos_c[kNumFwdClasses];
+        for (int c = 0; c < kNumFwdClasses; ++c) pos_c[c] = cnt[c];
+        for (int p = 0; p < n; ++p) order[(size_t)pos_c[kNumFwdClasses - 1 - h->probs[(size_t)p].cls]++] = p;
+        for (int c = 0; c < kNumFwdClasses; ++c) {
+            const int cls = kNumFwdClasses - 1 - c;
+            if (cls < 6) continue;  // K <= 4 rows per lane: tiny problems
+            std::stable_sort(order.begin() + cnt[c], order.begin() + cnt[c + 1], [&](int32_t x, int32_t y) {
+                return (int64_t)h->probs[x].m * h->probs[x].n > (int64_t)h->probs[y].m * h->probs[y].n;
+            });
+        }
+    }
     h->chunks.clear();
     h->order_all = order;
-    h->order_cls.assign((size_t)n, 0);
+    h->order_cls = order;  // already grouped by class inside every chunk (a chunk is a contiguous range of `order`)
     h->max_chunk_trace = 0;
     int pos = 0;
     while (pos < n) {
         Chunk c;
         c.first = pos;
         size_t bytes = 0;
+        for (int cls = 0; cls < kNumFwdClasses; ++cls) { c.cls_first[cls] = pos; c.cls_count[cls] = 0; }
         while (pos < n) {
             SmxProblem &q = h->probs[(size_t)order[pos]];
             size_t tb = (size_t)smx_trace_bytes(q.m, q.n, 1 << q.kshift);
@@ -428,20 +442,12 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
             if (c.count > 0 && bytes + tb > (size_t)h->trace_budget) break;
             q.trace_off = (int64_t)bytes;
             bytes += tb;
+            if (c.cls_count[q.cls] == 0) c.cls_first[q.cls] = pos;
+            ++c.cls_count[q.cls];
             ++c.count; ++pos;
         }
         c.trace_bytes = bytes;
         h->max_chunk_trace = std::max(h->max_chunk_trace, bytes);
-        // class lists (stable: keeps largest-first inside each class)
-        int w = c.first;
-        for (int cls = kNumFwdClasses - 1; cls >= 0; --cls) {
-            c.cls_first[cls] = w;
-            for (int x = c.first; x < c.first + c.count; ++x) {
-                const SmxProblem &q = h->probs[(size_t)order[x]];
-                if (q.cls == cls) h->order_cls[(size_t)w++] = order[x];
-            }
-            c.cls_count[cls] = w - c.cls_first[cls];
-        }
         h->chunks.push_back(c);
     }
     if (n == 0) { h->n = 0; return 0; }
