@@ -48,7 +48,7 @@ struct smx_handle {
     std::string err;
     int64_t trace_budget = (int64_t)24 << 30;  // clamped to a sixth of the free device memory at creation
     bool use_s16 = true;  // SMX_S16=0 forces the int32 kernels (cross-check)
-    int s16_min_rows = 128;  // the diagonal-frame kernel takes problems of more rows than this (SMX_S16_MINROWS overrides)
+    int s16_min_rows = 32;   // the diagonal-frame kernel takes problems of more rows than this (SMX_S16_MINROWS overrides)
     bool use_s16h = true;  // diagonal-frame u16x2 kernel (smx_dp16h.cuh) when the scoring allows it; SMX_S16H=0 keeps smx_dp16.cuh
     int s16_max_wsel = 1;  // warps per problem of the s16 kernel are capped at 2 (measured best); SMX_S16_MAXW=1|2|4|8 overrides
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -4,13 +4,13 @@ run() { # label, env, args
   python - <<'PY'
 import json
 d=json.loads(open('/tmp/line.json').read())
-print(round(d["ms_per_step"]), "ms/step", round(d["e2e"]["reads_per_s"]), "reads/s; dev GCUPS", round(d["value"]), "e2e GCUPS", round(d["e2e"]["value"]), "dev ms", round(d["device_ms_per_step"]))
+k=d["kernel_ms_per_step_rank0"]
+print(round(d["ms_per_step"]), "ms/step", round(d["e2e"]["reads_per_s"]), "reads/s; dev GCUPS", round(d["value"]), "e2e GCUPS", round(d["e2e"]["value"]), "dev ms", round(d["device_ms_per_step"]), "util", d["clocks"].get("gpu_util_pct_mean"), "W", d["clocks"].get("power_w_mean"))
+print("   w2", round(k["dp_forward16_w2"]), "w1", round(k["dp_forward16_w1"]), "k4", round(k["dp_forward_k4"]), "k2", round(k["dp_forward_k2"]), "k1", round(k["dp_forward_k1"]), "tb", round(k["traceback"]))
 PY
 }
-run "overlap4 batch1000 24G" "SMX_TRACE_BUDGET_GB=24" "--overlap 4 --batch 1000"
-run "overlap4 batch1000 36G" "SMX_TRACE_BUDGET_GB=36" "--overlap 4 --batch 1000"
-run "overlap6 batch500 16G" "SMX_TRACE_BUDGET_GB=16" "--overlap 6 --batch 500"
-run "overlap6 batch500 20G" "SMX_TRACE_BUDGET_GB=20" "--overlap 6 --batch 500"
-run "overlap8 batch250 10G" "SMX_TRACE_BUDGET_GB=10" "--overlap 8 --batch 250"
-run "overlap4 batch500 20G thr8" "SMX_TRACE_BUDGET_GB=20" "--overlap 4 --batch 500 --threads 8"
-run "overlap4 batch500 20G thr4" "SMX_TRACE_BUDGET_GB=20" "--overlap 4 --batch 500 --threads 4"
+run "default" "A=1" ""
+run "minrows 64" "SMX_S16_MINROWS=64" ""
+run "minrows 32" "SMX_S16_MINROWS=32" ""
+run "maxw 4" "SMX_S16_MAXW=4" ""
+run "overlap 5" "A=1" "--overlap 5"
