@@ -62,7 +62,7 @@ struct smx_handle {
     int kernel_launches[16] = {0};
     int64_t class_cells[14] = {0};
 
-    DevBuf pool, pool2, pool_special;  // ASCII pool, its 2-bit packing and per-word non-ACGT flags (smx_scan.cuh)
+    DevBuf pool, pool2, pool_special;  // ASCII pool, its two bit planes and per-word non-ACGT flags (smx_scan.cuh)
     int64_t pool_len = 0;
     std::vector<int32_t> pool_nonacgt;  // prefix count of bytes other than A/C/G/T (s16 kernel eligibility)
 
@@ -242,12 +242,12 @@ extern "C" int smx_pool_upload(smx_handle *h, const uint8_t *seqs, int64_t n)
     if (int rc = ensure(h, h->pool, (size_t)n + 64)) return rc;
     SMX_CUDA(h, cudaMemcpyAsync(h->pool.p, seqs, (size_t)n, cudaMemcpyHostToDevice, h->stream));
     {
-        const int64_t n_words = (n + 15) / 16;
-        if (int rc = ensure(h, h->pool2, sizeof(uint32_t) * (size_t)(n_words + 4))) return rc;
+        const int64_t n_words = (n + 31) / 32;  // bit planes: one uint2 per 32 bases
+        if (int rc = ensure(h, h->pool2, sizeof(uint2) * (size_t)(n_words + 4))) return rc;
         if (int rc = ensure(h, h->pool_special, (size_t)(n_words + 4))) return rc;
-        SMX_CUDA(h, cudaMemsetAsync(h->pool2.p, 0, sizeof(uint32_t) * (size_t)(n_words + 4), h->stream));
+        SMX_CUDA(h, cudaMemsetAsync(h->pool2.p, 0, sizeof(uint2) * (size_t)(n_words + 4), h->stream));
         SMX_CUDA(h, cudaMemsetAsync(h->pool_special.p, 0, (size_t)(n_words + 4), h->stream));
-        smx_pack_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, h->stream>>>((const uint8_t *)h->pool.p, n, (uint32_t *)h->pool2.p,
+        smx_pack_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, h->stream>>>((const uint8_t *)h->pool.p, n, (uint2 *)h->pool2.p,
                                                                                  (uint8_t *)h->pool_special.p, n_words);
         SMX_CUDA(h, cudaGetLastError());
     }
@@ -397,6 +397,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
             int wsel = pairs >= 8 ? 3 : pairs >= 4 ? 2 : pairs >= 2 ? 1 : 0;
             if (wsel > h->s16_max_wsel) wsel = h->s16_max_wsel;
             q.cls = (int16_t)(kClsS16 + wsel);
+            q.kshift = 3;  // the packed kernels always run 8 rows per lane (trace layout and traceback follow kshift)
         }
         h->class_cells[q.cls] += (int64_t)m * nn;
         q.trace_off = 0;
@@ -712,9 +713,9 @@ extern "C" int smx_scan_run(smx_handle *h)
     h->last_ms = 0.f;
     if (h->scan_n == 0) return 0;
     SMX_CUDA(h, cudaSetDevice(h->device));
-    const int qwords = (h->scan_nq_max + 15) / 16;
-    const int rwords = SMX_SCAN_TILE / 16 + qwords + 2;
-    const size_t smem = sizeof(uint32_t) * (size_t)(qwords + rwords + 4);
+    const int qwords = (h->scan_nq_max + 31) / 32;
+    const int rwords = qwords + 34;
+    const size_t smem = sizeof(uint2) * (size_t)(qwords + rwords) + sizeof(uint32_t) * (size_t)(rwords + 2);
     if (smem > 48 * 1024) SMX_CUDA(h, cudaFuncSetAttribute(smx_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SmxScanArgs a;
     a.pool = (const uint8_t *)h->pool.p;
@@ -722,7 +723,7 @@ extern "C" int smx_scan_run(smx_handle *h)
     a.tile_pair = (const int32_t *)h->d_scan_tile_pair.p;
     a.counts = (int32_t *)h->d_counts.p;
     a.topology = h->scan_topology;
-    a.pool2 = (const uint32_t *)h->pool2.p;
+    a.pool2 = (const uint2 *)h->pool2.p;
     a.special = (const uint8_t *)h->pool_special.p;
     SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     smx_scan_kernel<<<h->scan_tiles, SMX_SCAN_THREADS, smem, h->stream>>>(a);

@@ -4,11 +4,17 @@
 //   circular: ref_ext = reference tiled, k in [0, Nr)
 //   linear  : ref_ext = reference zero-padded by Nq-1 on both sides, k in [0, Nr+Nq-1)
 //
-// The sequence pool is packed once per upload to 2 bit/base (smx_pack_kernel, 16 bases per 32-bit word, plus one
-// flag byte per word for bytes other than A/C/G/T).  One CTA = 1024 consecutive diagonals of one (reference, query)
-// pair: the packed query and the reference window the tile touches are staged in shared memory with two word loads
-// and one funnel shift per word; every thread owns 4 diagonals that are 16 apart (same shift, neighbouring words),
-// so one query word and one new reference word per step feed 64 cells: funnel shift, XOR, fold, POPC.
+// The sequence pool is packed once per upload into two BIT PLANES (smx_pack_kernel: for every 32 bases one word
+// with the low bits and one with the high bits of the 2-bit codes, plus one flag byte for bytes other than
+// A/C/G/T), so that one 32-bit word compares 32 bases:  mismatch = (r_lo ^ q_lo) | (r_hi ^ q_hi).
+//
+// One CTA = 1024 consecutive diagonals of one (reference, query) pair.  The packed query and the reference window
+// the tile touches are staged in shared memory.  Diagonal k needs the window shifted by k mod 32 bits; the 32
+// diagonals k = k0 + s + 32 y (y = 0..31) share ONE shifted stream S_s, each reading it one word further.  A group
+// of 8 lanes owns the shift s: lane t holds S_s[4t .. 4t+3] (+ the step) in registers for its 4 diagonals; stepping
+// to the next 32 query bases renames three registers and takes the fourth from lane t+1 with one warp shuffle per
+// plane (the last lane of the group builds the fresh word with a funnel shift).  Per 128 cells a lane spends
+// 8 LOP3 + 4 POPC + 4 adds + ~8 instructions of stream upkeep, 2.5 x fewer than a 16-bases-per-word formulation.
 // Tiles that touch a flagged word fall back to an exact byte-compare loop in the same kernel (equality in the
 // reference is on raw characters).
 #pragma once
@@ -26,64 +32,61 @@ struct SmxScanPair {
 
 struct SmxScanArgs {
     const uint8_t *pool;
-    const uint32_t *pool2;   // 2-bit packed pool
-    const uint8_t *special;  // per packed word: holds a byte other than A/C/G/T
+    const uint2 *pool2;      // bit planes of the pool: .x = low bits, .y = high bits of 32 bases
+    const uint8_t *special;  // per 32-base word: holds a byte other than A/C/G/T
     const SmxScanPair *pairs;
     const int32_t *tile_pair;  // tile -> pair index
     int32_t *counts;
     int32_t topology;  // 0 circular, 1 linear
 };
 
-// one thread per 16 bases of the pool
-__global__ void __launch_bounds__(256) smx_pack_kernel(const uint8_t *pool, int64_t n, uint32_t *pool2, uint8_t *special, int64_t n_words)
+// one thread per 32 bases of the pool
+__global__ void __launch_bounds__(256) smx_pack_kernel(const uint8_t *pool, int64_t n, uint2 *pool2, uint8_t *special, int64_t n_words)
 {
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words) return;
-    uint32_t v = 0;
+    uint32_t lo = 0, hi = 0;
     int sp = 0;
-    const int64_t base = w * 16;
-    if (base + 16 <= n) {
-        const uint4 raw = *reinterpret_cast<const uint4 *>(pool + base);
-        const uint32_t words[4] = {raw.x, raw.y, raw.z, raw.w};
+    const int64_t base = w * 32;
+    if (base + 32 <= n) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(pool + base);  // the pool allocation is 16-byte aligned
+        const uint4 raw0 = src[0], raw1 = src[1];
+        const uint32_t words[8] = {raw0.x, raw0.y, raw0.z, raw0.w, raw1.x, raw1.y, raw1.z, raw1.w};
 #pragma unroll
-        for (int b = 0; b < 16; ++b) {
+        for (int b = 0; b < 32; ++b) {
             const int c = smx_code((words[b >> 2] >> (8 * (b & 3))) & 0xffu);
             sp |= c > 3;
-            v |= (uint32_t)(c & 3) << (2 * b);
+            lo |= (uint32_t)(c & 1) << b;
+            hi |= (uint32_t)((c >> 1) & 1) << b;
         }
     } else {
-        for (int b = 0; b < 16 && base + b < n; ++b) {
+        for (int b = 0; b < 32 && base + b < n; ++b) {
             const int c = smx_code(pool[base + b]);
             sp |= c > 3;
-            v |= (uint32_t)(c & 3) << (2 * b);
+            lo |= (uint32_t)(c & 1) << b;
+            hi |= (uint32_t)((c >> 1) & 1) << b;
         }
     }
-    pool2[w] = v;
+    pool2[w] = make_uint2(lo, hi);
     special[w] = (uint8_t)sp;
 }
 
-// 16 bases starting at pool position p (any alignment)
-__device__ __forceinline__ uint32_t smx_fetch16(const uint32_t *pool2, const uint8_t *special, int64_t p, int &sp)
+// bit planes of the 32 bases starting at pool position p (any alignment)
+__device__ __forceinline__ uint2 smx_fetch32(const uint2 *pool2, const uint8_t *special, int64_t p, int &sp)
 {
-    const int64_t w = p >> 4;
-    const int sh = 2 * (int)(p & 15);
+    const int64_t w = p >> 5;
+    const int sh = (int)(p & 31);
+    const uint2 a = pool2[w], b = pool2[w + 1];
     sp |= special[w] | special[w + 1];
-    return __funnelshift_r(pool2[w], pool2[w + 1], sh);
+    return make_uint2(__funnelshift_r(a.x, b.x, sh), __funnelshift_r(a.y, b.y, sh));
 }
 
-__device__ __forceinline__ int smx_scan_word(uint32_t q, uint32_t s, int base, int i_lo, int i_hi)
-{
-    const uint32_t x = q ^ s;
-    uint32_t mis = (x | (x >> 1)) & 0x55555555u;
-    if (base < i_lo) mis |= (1u << (2 * (i_lo - base))) - 1u;
-    if (base + 16 > i_hi) mis |= ~((1u << (2 * (i_hi - base))) - 1u);
-    return 16 - __popc(mis & 0x55555555u);
-}
+__device__ __forceinline__ uint32_t smx_lowmask(int nbits) { return nbits >= 32 ? 0xffffffffu : ((1u << nbits) - 1u); }
 
-// smem layout: [packed query words | packed reference window words]
+// smem layout: [query planes (uint2 per 32 bases) | reference window planes | reference window validity (linear)]
 __global__ void __launch_bounds__(SMX_SCAN_THREADS) smx_scan_kernel(const SmxScanArgs a)
 {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ uint2 smem2[];
     const int tile = blockIdx.x;
     const int pi = a.tile_pair[tile];
     const SmxScanPair pr = a.pairs[pi];
@@ -92,84 +95,119 @@ __global__ void __launch_bounds__(SMX_SCAN_THREADS) smx_scan_kernel(const SmxSca
     const int tid = threadIdx.x;
     const bool linear = a.topology == 1;
     const int shift0 = linear ? (nq - 1) : 0;  // ref_ext[x] = reference[x - shift0] (linear) or reference[x mod nr]
-    const int wlen = SMX_SCAN_TILE + nq - 1;   // window of ref_ext positions touched by the tile: [k0, k0 + wlen)
-    const int qwords = (nq + 15) >> 4;
-    const int rwords = SMX_SCAN_TILE / 16 + qwords + 2;
-    (void)wlen;
-    uint32_t *qpk = smem;
-    uint32_t *rpk = smem + qwords;
+    const int qwords = (nq + 31) >> 5;
+    const int rwords = qwords + 34;            // window words [0, 32 + qwords] plus one for the funnel shift
+    uint2 *qpk = smem2;
+    uint2 *rpk = smem2 + qwords;
+    uint32_t *rvalid = reinterpret_cast<uint32_t *>(rpk + rwords);  // linear only
 
     // ---- stage the packed query and reference window ----
     int special = 0;
-    for (int w = tid; w < qwords; w += SMX_SCAN_THREADS) qpk[w] = smx_fetch16(a.pool2, a.special, pr.qry_off + 16 * w, special);
+    for (int w = tid; w < qwords; w += SMX_SCAN_THREADS) qpk[w] = smx_fetch32(a.pool2, a.special, pr.qry_off + 32 * w, special);
     for (int w = tid; w < rwords; w += SMX_SCAN_THREADS) {
-        const int x = k0 + w * 16;
-        uint32_t v = 0;
+        const int x = k0 + w * 32;
+        uint2 v = make_uint2(0u, 0u);
         if (!linear) {
-            if (nr >= 16) {
-                // 16 bases from position x mod nr; a word that crosses the end continues at position 0
+            if (nr >= 64) {
+                // 32 bases from position x mod nr; a word that crosses the end continues at position 0
                 const int p0 = x % nr;
-                v = smx_fetch16(a.pool2, a.special, pr.ref_off + p0, special);
+                v = smx_fetch32(a.pool2, a.special, pr.ref_off + p0, special);
                 const int left = nr - p0;  // bases before the wrap
-                if (left < 16) v = (v & ((1u << (2 * left)) - 1u)) | (smx_fetch16(a.pool2, a.special, pr.ref_off, special) << (2 * left));
+                if (left < 32) {
+                    const uint2 h = smx_fetch32(a.pool2, a.special, pr.ref_off, special);
+                    const uint32_t m = smx_lowmask(left);
+                    v.x = (v.x & m) | (h.x << left);
+                    v.y = (v.y & m) | (h.y << left);
+                }
             } else {
-                for (int b = 0; b < 16; ++b) { const int c = smx_code(a.pool[pr.ref_off + (x + b) % nr]); special |= c > 3; v |= (uint32_t)(c & 3) << (2 * b); }
+                for (int b = 0; b < 32; ++b) {
+                    const int c = smx_code(a.pool[pr.ref_off + (x + b) % nr]);
+                    special |= c > 3;
+                    v.x |= (uint32_t)(c & 1) << b;
+                    v.y |= (uint32_t)((c >> 1) & 1) << b;
+                }
             }
         } else {
-            const int pos = x - shift0;  // positions outside [0, nr) are padding: masked by the per-diagonal range below
-            if (pos >= 0 && pos < nr) v = smx_fetch16(a.pool2, a.special, pr.ref_off + pos, special);
-            else if (pos < 0 && pos > -16) v = smx_fetch16(a.pool2, a.special, pr.ref_off, special) << (2 * (-pos));
+            // ref_ext positions outside [shift0, shift0 + nr) are padding that never matches (validity plane)
+            const int pos = x - shift0;
+            uint32_t valid = 0u;
+            if (pos >= 0 && pos < nr) {
+                v = smx_fetch32(a.pool2, a.special, pr.ref_off + pos, special);
+                valid = smx_lowmask(nr - pos);
+            } else if (pos < 0 && pos > -32) {
+                const uint2 h = smx_fetch32(a.pool2, a.special, pr.ref_off, special);
+                v.x = h.x << (-pos);
+                v.y = h.y << (-pos);
+                valid = smx_lowmask(nr) << (-pos);
+            }
+            rvalid[w] = valid;
         }
         rpk[w] = v;
     }
     special = __syncthreads_or(special);
 
-    const int sh = 2 * (tid & 15);
-    const int xb = SMX_SCAN_DPT * (tid >> 4);
-    const int kb = k0 + (tid & 15) + 16 * xb;  // diagonals kb + 16 d, d = 0..3
-    int cnt[SMX_SCAN_DPT], i_lo[SMX_SCAN_DPT], i_hi[SMX_SCAN_DPT];
-    int w_a = 0, w_b = nq >> 4;  // interior words [w_a, w_b) are complete for all four diagonals
+    const int s = tid >> 3;   // shift of this group of 8 lanes
+    const int t = tid & 7;    // lane in the group: stream words 4t .. 4t+3
+    const int kb = k0 + s + 32 * SMX_SCAN_DPT * t;  // diagonals kb + 32 d, d = 0..3
+    int mism[SMX_SCAN_DPT];
 #pragma unroll
-    for (int d = 0; d < SMX_SCAN_DPT; ++d) {
-        cnt[d] = 0;
-        i_lo[d] = 0; i_hi[d] = nq;
-        if (linear) {
-            const int dd = kb + 16 * d - (nq - 1);
-            i_lo[d] = max(0, -dd);
-            i_hi[d] = max(i_lo[d], min(nq, nr - dd));
-        }
-        w_a = max(w_a, (i_lo[d] + 15) >> 4);
-        w_b = min(w_b, i_hi[d] >> 4);
-    }
+    for (int d = 0; d < SMX_SCAN_DPT; ++d) mism[d] = 0;
+
     if (!special) {
-        if (w_b > w_a) {
-            uint32_t r[SMX_SCAN_DPT + 1];
+        // S_s[y] = window bits [32 y + s, 32 y + s + 32)
+        uint32_t alo[SMX_SCAN_DPT], ahi[SMX_SCAN_DPT], av[SMX_SCAN_DPT];
+        {
+            uint2 r0 = rpk[SMX_SCAN_DPT * t];
+            uint32_t v0 = linear ? rvalid[SMX_SCAN_DPT * t] : 0xffffffffu;
 #pragma unroll
-            for (int d = 0; d <= SMX_SCAN_DPT; ++d) r[d] = rpk[xb + w_a + d];
-            for (int w = w_a; w < w_b; ++w) {
-                const uint32_t q = qpk[w];
-#pragma unroll
-                for (int d = 0; d < SMX_SCAN_DPT; ++d) {
-                    const uint32_t x = q ^ __funnelshift_r(r[d], r[d + 1], sh);
-                    cnt[d] += 16 - __popc((x | (x >> 1)) & 0x55555555u);
-                }
-#pragma unroll
-                for (int d = 0; d < SMX_SCAN_DPT; ++d) r[d] = r[d + 1];
-                r[SMX_SCAN_DPT] = rpk[xb + w + SMX_SCAN_DPT + 1];
+            for (int d = 0; d < SMX_SCAN_DPT; ++d) {
+                const uint2 r1 = rpk[SMX_SCAN_DPT * t + d + 1];
+                const uint32_t v1 = linear ? rvalid[SMX_SCAN_DPT * t + d + 1] : 0xffffffffu;
+                alo[d] = __funnelshift_r(r0.x, r1.x, s);
+                ahi[d] = __funnelshift_r(r0.y, r1.y, s);
+                av[d] = __funnelshift_r(v0, v1, s);
+                r0 = r1; v0 = v1;
             }
-        } else {
-            w_b = w_a;
         }
-        // edge words (partial, or outside the common interior), per diagonal
+        uint2 rprev = rpk[32];  // window word 32 + w of the step
+        uint32_t vprev = linear ? rvalid[32] : 0xffffffffu;
+        const bool last_lane = t == 7;
+        const uint32_t qmask_last = (nq & 31) ? smx_lowmask(nq & 31) : 0xffffffffu;
+        for (int w = 0; w < qwords; ++w) {
+            const uint2 q = qpk[w];
+            const uint32_t qm = w == qwords - 1 ? qmask_last : 0xffffffffu;
+#pragma unroll
+            for (int d = 0; d < SMX_SCAN_DPT; ++d) {
+                uint32_t mis = (alo[d] ^ q.x) | (ahi[d] ^ q.y);
+                if (linear) mis |= ~av[d];
+                mism[d] += __popc(mis & qm);
+            }
+            // slide the stream by one word: lane t takes S_s[4t + 4 + w] from lane t+1, the last lane of the group builds it
+            const uint2 rnext = rpk[33 + w];
+            uint32_t nlo = __shfl_down_sync(SMX_FULL_MASK, alo[0], 1, 8);
+            uint32_t nhi = __shfl_down_sync(SMX_FULL_MASK, ahi[0], 1, 8);
+            const uint32_t flo = __funnelshift_r(rprev.x, rnext.x, s);
+            const uint32_t fhi = __funnelshift_r(rprev.y, rnext.y, s);
+            if (last_lane) { nlo = flo; nhi = fhi; }
+            rprev = rnext;
+#pragma unroll
+            for (int d = 0; d + 1 < SMX_SCAN_DPT; ++d) { alo[d] = alo[d + 1]; ahi[d] = ahi[d + 1]; }
+            alo[SMX_SCAN_DPT - 1] = nlo; ahi[SMX_SCAN_DPT - 1] = nhi;
+            if (linear) {
+                const uint32_t vnext = rvalid[33 + w];
+                uint32_t nv = __shfl_down_sync(SMX_FULL_MASK, av[0], 1, 8);
+                const uint32_t fv = __funnelshift_r(vprev, vnext, s);
+                if (last_lane) nv = fv;
+                vprev = vnext;
+#pragma unroll
+                for (int d = 0; d + 1 < SMX_SCAN_DPT; ++d) av[d] = av[d + 1];
+                av[SMX_SCAN_DPT - 1] = nv;
+            }
+        }
 #pragma unroll
         for (int d = 0; d < SMX_SCAN_DPT; ++d) {
-            if (i_hi[d] <= i_lo[d]) continue;
-            const int first = i_lo[d] >> 4, last = (i_hi[d] - 1) >> 4;
-            for (int w = first; w <= last; ++w) {
-                if (w >= w_a && w < w_b) { w = w_b - 1; continue; }
-                const uint32_t s = __funnelshift_r(rpk[xb + d + w], rpk[xb + d + w + 1], sh);
-                cnt[d] += smx_scan_word(qpk[w], s, w << 4, i_lo[d], i_hi[d]);
-            }
+            const int k = kb + 32 * d;
+            if (k < pr.max_k) a.counts[pr.counts_off + k] = nq - mism[d];
         }
     } else {
         // exact byte path (rare): raw character equality
@@ -177,20 +215,17 @@ __global__ void __launch_bounds__(SMX_SCAN_THREADS) smx_scan_kernel(const SmxSca
         const uint8_t *qry = a.pool + pr.qry_off;
 #pragma unroll
         for (int d = 0; d < SMX_SCAN_DPT; ++d) {
-            const int k = kb + 16 * d;
+            const int k = kb + 32 * d;
             if (k >= pr.max_k) continue;
             int c = 0;
-            for (int i = i_lo[d]; i < i_hi[d]; ++i) {
-                const int x = k + i;
-                const int pos = linear ? x - shift0 : x % nr;
-                c += (ref[pos] == qry[i]);
+            if (!linear) {
+                for (int i = 0; i < nq; ++i) c += (ref[(k + i) % nr] == qry[i]);
+            } else {
+                const int dd = k - shift0;
+                const int i_lo = max(0, -dd), i_hi = min(nq, nr - dd);
+                for (int i = i_lo; i < i_hi; ++i) c += (ref[dd + i] == qry[i]);
             }
-            cnt[d] = c;
+            a.counts[pr.counts_off + k] = c;
         }
-    }
-#pragma unroll
-    for (int d = 0; d < SMX_SCAN_DPT; ++d) {
-        const int k = kb + 16 * d;
-        if (k < pr.max_k) a.counts[pr.counts_off + k] = cnt[d];
     }
 }
