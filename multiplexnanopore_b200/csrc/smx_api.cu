@@ -713,10 +713,11 @@ extern "C" int smx_scan_run(smx_handle *h)
     h->last_ms = 0.f;
     if (h->scan_n == 0) return 0;
     SMX_CUDA(h, cudaSetDevice(h->device));
-    const int qwords = (h->scan_nq_max + 31) / 32;
-    const int rwords = qwords + 34;
-    const size_t smem = sizeof(uint2) * (size_t)(qwords + rwords) + sizeof(uint32_t) * (size_t)(rwords + 2);
-    if (smem > 48 * 1024) SMX_CUDA(h, cudaFuncSetAttribute(smx_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int qwords4 = (((h->scan_nq_max + 31) / 32) + 3) & ~3;
+    const int rwords = qwords4 + 34;
+    const size_t smem = sizeof(uint2) * (size_t)(qwords4 + rwords) + sizeof(uint32_t) * (size_t)(rwords + 2);
+    void (*scan_kern)(const SmxScanArgs) = h->scan_topology == 1 ? smx_scan_kernel<true> : smx_scan_kernel<false>;
+    if (smem > 48 * 1024) SMX_CUDA(h, cudaFuncSetAttribute(scan_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SmxScanArgs a;
     a.pool = (const uint8_t *)h->pool.p;
     a.pairs = (const SmxScanPair *)h->d_scan_pairs.p;
@@ -726,7 +727,7 @@ extern "C" int smx_scan_run(smx_handle *h)
     a.pool2 = (const uint2 *)h->pool2.p;
     a.special = (const uint8_t *)h->pool_special.p;
     SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    smx_scan_kernel<<<h->scan_tiles, SMX_SCAN_THREADS, smem, h->stream>>>(a);
+    scan_kern<<<h->scan_tiles, SMX_SCAN_THREADS, smem, h->stream>>>(a);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches = 1;
     SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));

@@ -83,7 +83,42 @@ __device__ __forceinline__ uint2 smx_fetch32(const uint2 *pool2, const uint8_t *
 
 __device__ __forceinline__ uint32_t smx_lowmask(int nbits) { return nbits >= 32 ? 0xffffffffu : ((1u << nbits) - 1u); }
 
-// smem layout: [query planes (uint2 per 32 bases) | reference window planes | reference window validity (linear)]
+// one step of a lane: 32 query bases against its four stream words, then slide the stream by one word.
+// U = sub-step inside a group of four (compile time): logical stream word d lives in register slot (d + U) & 3, so
+// sliding renames registers instead of moving them.
+template <bool LINEAR, int U, bool MASKED>
+__device__ __forceinline__ void smx_scan_step(uint32_t (&alo)[4], uint32_t (&ahi)[4], uint32_t (&av)[4], int (&mism)[4], const uint2 q,
+                                              const uint32_t qm, const uint2 rnext, const uint32_t vnext, uint2 &rprev, uint32_t &vprev,
+                                              const int s, const bool last_lane)
+{
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        const int slot = (d + U) & 3;
+        uint32_t mis = (alo[slot] ^ q.x) | (ahi[slot] ^ q.y);
+        if (LINEAR) mis |= ~av[slot];
+        if (MASKED) mis &= qm;
+        mism[d] += __popc(mis);
+    }
+    // lane t takes S_s[4t + 4 + w] from lane t+1 (its logical word 0); the last lane of the group builds it
+    const int s0 = U & 3;
+    uint32_t nlo = __shfl_down_sync(SMX_FULL_MASK, alo[s0], 1, 8);
+    uint32_t nhi = __shfl_down_sync(SMX_FULL_MASK, ahi[s0], 1, 8);
+    const uint32_t flo = __funnelshift_r(rprev.x, rnext.x, s);
+    const uint32_t fhi = __funnelshift_r(rprev.y, rnext.y, s);
+    alo[s0] = last_lane ? flo : nlo;
+    ahi[s0] = last_lane ? fhi : nhi;
+    rprev = rnext;
+    if (LINEAR) {
+        const uint32_t nv = __shfl_down_sync(SMX_FULL_MASK, av[s0], 1, 8);
+        const uint32_t fv = __funnelshift_r(vprev, vnext, s);
+        av[s0] = last_lane ? fv : nv;
+        vprev = vnext;
+    }
+}
+
+// smem layout: [query planes (uint2 per 32 bases, padded to a multiple of 4 words) | reference window planes |
+//               reference window validity (linear)]
+template <bool LINEAR>
 __global__ void __launch_bounds__(SMX_SCAN_THREADS) smx_scan_kernel(const SmxScanArgs a)
 {
     extern __shared__ uint2 smem2[];
@@ -93,21 +128,22 @@ __global__ void __launch_bounds__(SMX_SCAN_THREADS) smx_scan_kernel(const SmxSca
     const int nr = pr.nr, nq = pr.nq;
     const int k0 = (tile - pr.tile0) * SMX_SCAN_TILE;
     const int tid = threadIdx.x;
-    const bool linear = a.topology == 1;
-    const int shift0 = linear ? (nq - 1) : 0;  // ref_ext[x] = reference[x - shift0] (linear) or reference[x mod nr]
+    const int shift0 = LINEAR ? (nq - 1) : 0;  // ref_ext[x] = reference[x - shift0] (linear) or reference[x mod nr]
     const int qwords = (nq + 31) >> 5;
-    const int rwords = qwords + 34;            // window words [0, 32 + qwords] plus one for the funnel shift
+    const int qwords4 = (qwords + 3) & ~3;
+    const int rwords = qwords4 + 34;           // window words [0, 32 + qwords4] plus one for the funnel shift
     uint2 *qpk = smem2;
-    uint2 *rpk = smem2 + qwords;
+    uint2 *rpk = smem2 + qwords4;
     uint32_t *rvalid = reinterpret_cast<uint32_t *>(rpk + rwords);  // linear only
 
     // ---- stage the packed query and reference window ----
     int special = 0;
-    for (int w = tid; w < qwords; w += SMX_SCAN_THREADS) qpk[w] = smx_fetch32(a.pool2, a.special, pr.qry_off + 32 * w, special);
+    for (int w = tid; w < qwords4; w += SMX_SCAN_THREADS)
+        qpk[w] = w < qwords ? smx_fetch32(a.pool2, a.special, pr.qry_off + 32 * w, special) : make_uint2(0u, 0u);
     for (int w = tid; w < rwords; w += SMX_SCAN_THREADS) {
         const int x = k0 + w * 32;
         uint2 v = make_uint2(0u, 0u);
-        if (!linear) {
+        if (!LINEAR) {
             if (nr >= 64) {
                 // 32 bases from position x mod nr; a word that crosses the end continues at position 0
                 const int p0 = x % nr;
@@ -155,14 +191,14 @@ __global__ void __launch_bounds__(SMX_SCAN_THREADS) smx_scan_kernel(const SmxSca
 
     if (!special) {
         // S_s[y] = window bits [32 y + s, 32 y + s + 32)
-        uint32_t alo[SMX_SCAN_DPT], ahi[SMX_SCAN_DPT], av[SMX_SCAN_DPT];
+        uint32_t alo[4], ahi[4], av[4];
         {
-            uint2 r0 = rpk[SMX_SCAN_DPT * t];
-            uint32_t v0 = linear ? rvalid[SMX_SCAN_DPT * t] : 0xffffffffu;
+            uint2 r0 = rpk[4 * t];
+            uint32_t v0 = LINEAR ? rvalid[4 * t] : 0xffffffffu;
 #pragma unroll
-            for (int d = 0; d < SMX_SCAN_DPT; ++d) {
-                const uint2 r1 = rpk[SMX_SCAN_DPT * t + d + 1];
-                const uint32_t v1 = linear ? rvalid[SMX_SCAN_DPT * t + d + 1] : 0xffffffffu;
+            for (int d = 0; d < 4; ++d) {
+                const uint2 r1 = rpk[4 * t + d + 1];
+                const uint32_t v1 = LINEAR ? rvalid[4 * t + d + 1] : 0xffffffffu;
                 alo[d] = __funnelshift_r(r0.x, r1.x, s);
                 ahi[d] = __funnelshift_r(r0.y, r1.y, s);
                 av[d] = __funnelshift_r(v0, v1, s);
@@ -170,39 +206,29 @@ __global__ void __launch_bounds__(SMX_SCAN_THREADS) smx_scan_kernel(const SmxSca
             }
         }
         uint2 rprev = rpk[32];  // window word 32 + w of the step
-        uint32_t vprev = linear ? rvalid[32] : 0xffffffffu;
+        uint32_t vprev = LINEAR ? rvalid[32] : 0xffffffffu;
         const bool last_lane = t == 7;
         const uint32_t qmask_last = (nq & 31) ? smx_lowmask(nq & 31) : 0xffffffffu;
-        for (int w = 0; w < qwords; ++w) {
-            const uint2 q = qpk[w];
-            const uint32_t qm = w == qwords - 1 ? qmask_last : 0xffffffffu;
-#pragma unroll
-            for (int d = 0; d < SMX_SCAN_DPT; ++d) {
-                uint32_t mis = (alo[d] ^ q.x) | (ahi[d] ^ q.y);
-                if (linear) mis |= ~av[d];
-                mism[d] += __popc(mis & qm);
-            }
-            // slide the stream by one word: lane t takes S_s[4t + 4 + w] from lane t+1, the last lane of the group builds it
-            const uint2 rnext = rpk[33 + w];
-            uint32_t nlo = __shfl_down_sync(SMX_FULL_MASK, alo[0], 1, 8);
-            uint32_t nhi = __shfl_down_sync(SMX_FULL_MASK, ahi[0], 1, 8);
-            const uint32_t flo = __funnelshift_r(rprev.x, rnext.x, s);
-            const uint32_t fhi = __funnelshift_r(rprev.y, rnext.y, s);
-            if (last_lane) { nlo = flo; nhi = fhi; }
-            rprev = rnext;
-#pragma unroll
-            for (int d = 0; d + 1 < SMX_SCAN_DPT; ++d) { alo[d] = alo[d + 1]; ahi[d] = ahi[d + 1]; }
-            alo[SMX_SCAN_DPT - 1] = nlo; ahi[SMX_SCAN_DPT - 1] = nhi;
-            if (linear) {
-                const uint32_t vnext = rvalid[33 + w];
-                uint32_t nv = __shfl_down_sync(SMX_FULL_MASK, av[0], 1, 8);
-                const uint32_t fv = __funnelshift_r(vprev, vnext, s);
-                if (last_lane) nv = fv;
-                vprev = vnext;
-#pragma unroll
-                for (int d = 0; d + 1 < SMX_SCAN_DPT; ++d) av[d] = av[d + 1];
-                av[SMX_SCAN_DPT - 1] = nv;
-            }
+        // groups of four words that lie completely inside the query run unmasked
+        const int full = (qwords - 1) & ~3;  // words [0, full) are complete and not the last word
+        int w = 0;
+        for (; w < full; w += 4) {
+            smx_scan_step<LINEAR, 0, false>(alo, ahi, av, mism, qpk[w + 0], 0u, rpk[33 + w + 0], LINEAR ? rvalid[33 + w + 0] : 0u, rprev, vprev, s, last_lane);
+            smx_scan_step<LINEAR, 1, false>(alo, ahi, av, mism, qpk[w + 1], 0u, rpk[33 + w + 1], LINEAR ? rvalid[33 + w + 1] : 0u, rprev, vprev, s, last_lane);
+            smx_scan_step<LINEAR, 2, false>(alo, ahi, av, mism, qpk[w + 2], 0u, rpk[33 + w + 2], LINEAR ? rvalid[33 + w + 2] : 0u, rprev, vprev, s, last_lane);
+            smx_scan_step<LINEAR, 3, false>(alo, ahi, av, mism, qpk[w + 3], 0u, rpk[33 + w + 3], LINEAR ? rvalid[33 + w + 3] : 0u, rprev, vprev, s, last_lane);
+        }
+        // last group: the final (possibly partial) word is masked, words beyond the query count nothing
+        {
+            const int last = qwords - 1;
+            const uint32_t m0 = w + 0 < last ? 0xffffffffu : (w + 0 == last ? qmask_last : 0u);
+            const uint32_t m1 = w + 1 < last ? 0xffffffffu : (w + 1 == last ? qmask_last : 0u);
+            const uint32_t m2 = w + 2 < last ? 0xffffffffu : (w + 2 == last ? qmask_last : 0u);
+            const uint32_t m3 = w + 3 < last ? 0xffffffffu : (w + 3 == last ? qmask_last : 0u);
+            smx_scan_step<LINEAR, 0, true>(alo, ahi, av, mism, qpk[w + 0], m0, rpk[33 + w + 0], LINEAR ? rvalid[33 + w + 0] : 0u, rprev, vprev, s, last_lane);
+            smx_scan_step<LINEAR, 1, true>(alo, ahi, av, mism, qpk[w + 1], m1, rpk[33 + w + 1], LINEAR ? rvalid[33 + w + 1] : 0u, rprev, vprev, s, last_lane);
+            smx_scan_step<LINEAR, 2, true>(alo, ahi, av, mism, qpk[w + 2], m2, rpk[33 + w + 2], LINEAR ? rvalid[33 + w + 2] : 0u, rprev, vprev, s, last_lane);
+            smx_scan_step<LINEAR, 3, true>(alo, ahi, av, mism, qpk[w + 3], m3, rpk[33 + w + 3], LINEAR ? rvalid[33 + w + 3] : 0u, rprev, vprev, s, last_lane);
         }
 #pragma unroll
         for (int d = 0; d < SMX_SCAN_DPT; ++d) {
@@ -218,7 +244,7 @@ __global__ void __launch_bounds__(SMX_SCAN_THREADS) smx_scan_kernel(const SmxSca
             const int k = kb + 32 * d;
             if (k >= pr.max_k) continue;
             int c = 0;
-            if (!linear) {
+            if (!LINEAR) {
                 for (int i = 0; i < nq; ++i) c += (ref[(k + i) % nr] == qry[i]);
             } else {
                 const int dd = k - shift0;
