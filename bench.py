@@ -176,7 +176,8 @@ def run_engine(args, rank, world, local_rank):
     eng = Engine(local_rank)
     plasmids, reads, _ = workload(rank, args.reads)
     cores = os.cpu_count() or 1
-    n_threads = args.threads or max(1, cores // max(world, 1))
+    # host stages need about three cores per GPU (measured); more threads per handle only add scheduling noise
+    n_threads = args.threads or max(1, min(4, cores // max(world, 1)))
     refs = [p.upper() for p in plasmids]
     reads = [r.upper() for r in reads]
     in_bytes = sum(len(p) for p in refs) + sum(len(r) for r in reads)
@@ -285,7 +286,7 @@ def run_engine(args, rank, world, local_rank):
         "device_timing": "CUDA events on the engine stream, one extra serialised pass" if args.overlap > 1 else "CUDA events on the engine stream, timed steps",
         "stage_seconds_per_step_rank0": {k: agg[k] / args.steps for k in ("t_pool", "t_scan", "t_select", "t_chain", "t_dp", "t_stitch", "t_total")},
         "stage_seconds_per_step_rank0_overlapped": {k: timed_stats[k] / args.steps for k in ("t_pool", "t_scan", "t_select", "t_chain", "t_dp", "t_stitch", "t_total")},
-        "kernel_ms_per_step_rank0": {"scan": agg["gpu_scan_ms"] / args.steps, "select_and_chain": agg["gpu_select_ms"] / args.steps,
+        "kernel_ms_per_step_rank0": {"scan": agg["gpu_scan_ms"] / args.steps, "select_and_chain": agg["gpu_select_ms"] / args.steps, "select": agg["gpu_select_only_ms"] / args.steps, "chain": agg["gpu_chain_ms"] / args.steps,
                                      "dp_all": agg["gpu_dp_ms"] / args.steps, "dp_forward16_w8": agg["dp_ms_class13"] / args.steps, "dp_forward16_w4": agg["dp_ms_class12"] / args.steps,
                                      "dp_forward16_w2": agg["dp_ms_class11"] / args.steps, "dp_forward16_w1": agg["dp_ms_class10"] / args.steps,
                                      "dp_forward_k8_team": agg["dp_ms_class8"] / args.steps,

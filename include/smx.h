@@ -149,7 +149,8 @@ int smx_pipeline_fetch(smx_handle *h, int32_t *score, int32_t *new_query_seq_off
 /* out[0..16]: t_total, t_pool, t_scan, t_select, t_chain, t_dp, t_stitch (host seconds), gpu_scan_ms,
  * gpu_select_ms, gpu_dp_ms, scan_cells, dp_cells, n_dp_problems, n_host_redecisions, n_failed,
  * kernel_launches, n_pair_strands, then out[17..32] = smx_align_kernel_ms ms16 of the DP run,
- * out[33..46] = its cells14, out[47..62] = launches per kernel (same order as ms16) */
+ * out[33..46] = its cells14, out[47..62] = launches per kernel (same order as ms16), out[63] = select kernel ms,
+ * out[64] = chain kernel ms */
 int smx_pipeline_stats(smx_handle *h, double *out, int32_t n);
 
 /* ---- measurement helper: dependency-free int32 / DPX issue-rate microbenchmark ---------------

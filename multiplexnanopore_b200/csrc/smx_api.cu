@@ -34,6 +34,7 @@ struct PinBuf {
 
 struct Chunk {
     int first = 0, count = 0;            // range in the size-sorted order
+    int n_big = 0;                       // traceback: the first n_big problems of the chunk's order_all range get a warp each
     int cls_first[14] = {0}, cls_count[14] = {0};  // per kernel class ranges inside order_cls (see problem_class)
     size_t trace_bytes = 0;
 };
@@ -284,6 +285,7 @@ extern "C" int smx_pool_upload(smx_handle *h, const uint8_t *seqs, int64_t n)
 // 10..13 for the packed s16x2 kernel with 1, 2, 4, 8 warps per problem
 enum { kClsS16 = 10, kNumFwdClasses = 14, kSlotTraceback = 14, kSlotCompact = 15, kNumSlots = 16 };
 static const int kTeamMinRows = 513;
+static const int kTbBigWalk = 768;  // m + n from which a traceback walk gets its own warp
 static int problem_class(int m, int mode);
 static int pick_kshift(int m)
 {
@@ -449,6 +451,12 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         }
         c.trace_bytes = bytes;
         h->max_chunk_trace = std::max(h->max_chunk_trace, bytes);
+        // traceback order of the chunk: long walks first (one warp each, see smx_traceback), the rest one thread each
+        {
+            auto big = [&](int32_t p) { return h->probs[(size_t)p].m + h->probs[(size_t)p].n >= kTbBigWalk; };
+            auto mid = std::stable_partition(h->order_all.begin() + c.first, h->order_all.begin() + c.first + c.count, big);
+            c.n_big = (int)(mid - (h->order_all.begin() + c.first));
+        }
         h->chunks.push_back(c);
     }
     if (n == 0) { h->n = 0; return 0; }
@@ -574,11 +582,13 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
         t.probs = (const SmxProblem *)h->d_probs.p;
         t.order = (const int32_t *)h->d_order_all.p + c.first;
         t.n_order = c.count;
+        t.n_big = c.n_big;
         t.trace = (const uint8_t *)h->d_trace.p;
         t.results = (SmxResult *)h->d_results.p;
         t.runs = (uint32_t *)h->d_runs.p;
         t.sc = h->sc;
-        smx_traceback<<<(c.count + 127) / 128, 128, 0, h->stream>>>(t);
+        const long long tb_threads = 32ll * c.n_big + (c.count - c.n_big);
+        smx_traceback<<<(unsigned)((tb_threads + 127) / 128), 128, 0, h->stream>>>(t);
         SMX_CUDA(h, cudaGetLastError());
         h->last_launches++;
         if (int rc2 = mark(h, kSlotTraceback)) return rc2;
@@ -1296,6 +1306,8 @@ extern "C" int smx_pipeline_stats(smx_handle *h, double *out, int32_t n)
         else if (i < m + 16) out[i] = st.dp_kernel_ms[i - m];
         else if (i < m + 30) out[i] = (double)st.dp_class_cells[i - m - 16];
         else if (i < m + 46) out[i] = (double)st.dp_kernel_launches[i - m - 30];
+        else if (i == m + 46) out[i] = st.gpu_select_ms;
+        else if (i == m + 47) out[i] = st.gpu_chain_ms;
         else out[i] = 0.0;
     }
     return 0;

@@ -17,6 +17,7 @@ struct SmxTbArgs {
     const SmxProblem *probs;
     const int32_t *order;  // problems of this chunk
     int32_t n_order;
+    int32_t n_big;  // the first n_big problems of `order` are long walks: one warp each (lane 0 walks), the rest one thread each
     const uint8_t *trace;
     SmxResult *results;
     uint32_t *runs;  // scratch, reversed order per problem
@@ -86,10 +87,19 @@ struct SmxWalk {
     }
 };
 
-// one thread per problem; runs are emitted while walking back, i.e. in reverse order
+// One walker per problem; runs are emitted while walking back, i.e. in reverse order.  A walk is a chain of
+// dependent loads: 32 long walks in one warp would advance at the pace of the slowest load of every step and
+// serialise on their divergent branches, so the long walks (m + n >= kTbBigWalk on the host) get a warp each.
 __global__ void __launch_bounds__(128) smx_traceback(const SmxTbArgs a)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int t;
+    if (gt < 32ll * a.n_big) {
+        if (threadIdx.x & 31) return;
+        t = (int)(gt >> 5);
+    } else {
+        t = (int)(gt - 32ll * a.n_big) + a.n_big;
+    }
     if (t >= a.n_order) return;
     const int pid = a.order[t];
     const SmxProblem pr = a.probs[pid];

@@ -138,6 +138,9 @@ def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None,
     from concurrent.futures import ThreadPoolExecutor
     import queue
     engines = _engines_for(eng, min(overlap, len(starts)))
+    if n_threads <= 0:  # host stages need about three cores per GPU; every handle in flight runs its own pool
+        import os
+        n_threads = max(1, min(4, (os.cpu_count() or 4) // len(engines)))
     free = queue.SimpleQueue()
     for e in engines:
         free.put(e)
