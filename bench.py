@@ -177,7 +177,7 @@ def run_engine(args, rank, world, local_rank):
     plasmids, reads, _ = workload(rank, args.reads)
     cores = os.cpu_count() or 1
     # host stages need about three cores per GPU (measured); more threads per handle only add scheduling noise
-    n_threads = args.threads or max(1, min(4, cores // max(world, 1)))
+    n_threads = args.threads or max(1, min(4, (cores // max(world, 1)) // 2))
     refs = [p.upper() for p in plasmids]
     reads = [r.upper() for r in reads]
     in_bytes = sum(len(p) for p in refs) + sum(len(r) for r in reads)
@@ -214,7 +214,7 @@ def run_engine(args, rank, world, local_rank):
         # chunk per batch).  Serialised kernels cannot fill each other's tails, so `value` can be BELOW e2e.
         eng.set_trace_budget(40 << 30)
         one = step(overlap=1)
-        eng.set_trace_budget(24 << 30)
+        eng.set_trace_budget(16 << 30)
         agg = {k: v * args.steps for k, v in one.stats.items()}
     dev_s = (agg["gpu_scan_ms"] + agg["gpu_select_ms"] + agg["gpu_dp_ms"]) * 1e-3
     if dist is not None:
@@ -310,7 +310,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--reads", type=int, default=20000, help="reads per rank (C2 = 20000)")
     ap.add_argument("--batch", type=int, default=1000, help="reads per smx_pipeline_run call")
-    ap.add_argument("--overlap", type=int, default=4, help="batches in flight per rank (engine handles)")
+    ap.add_argument("--overlap", type=int, default=6, help="batches in flight per rank (engine handles)")
     ap.add_argument("--cpu-reads", type=int, default=0, help="reads of the CPU sample (default: max(cores, 8))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--threads", type=int, default=0, help="host threads per rank (default: cores / ranks)")

@@ -59,7 +59,7 @@ void smx_destroy(smx_handle *h);
 /* message of the last failing call on this handle ("" if none); h may be NULL for create errors */
 const char *smx_last_error(const smx_handle *h);
 
-/* Upper bound for the device bytes of packed traceback kept in flight at once (default min(24 GiB, a sixth of
+/* Upper bound for the device bytes of packed traceback kept in flight at once (default min(16 GiB, an eighth of
  * the free device memory at creation); SMX_TRACE_BUDGET_GB in the environment overrides);
  * larger batches are cut into chunks that are processed back to back. */
 int smx_set_trace_budget(smx_handle *h, int64_t bytes);

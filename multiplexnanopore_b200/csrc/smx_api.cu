@@ -4,6 +4,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <new>
 #include <numeric>
 #include <string>
@@ -43,16 +45,18 @@ struct Chunk {
 
 struct smx_handle {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     // forward DP + traceback (lowest priority: long launches)
+    cudaStream_t stream_hi = nullptr;  // everything short: pool upload, scan, select, chain, compaction, copies (highest priority)
     bool owns_stream = false;
     int sm_count = 148;
     std::string err;
-    int64_t trace_budget = (int64_t)24 << 30;  // clamped to a sixth of the free device memory at creation
+    int64_t trace_budget = (int64_t)16 << 30;  // clamped to an eighth of the free device memory at creation
     bool use_s16 = true;  // SMX_S16=0 forces the int32 kernels (cross-check)
     int s16_min_rows = 32;   // the diagonal-frame kernel takes problems of more rows than this (SMX_S16_MINROWS overrides)
+    bool persistent_fwd = false;  // SMX_PERSISTENT=1: launch smx_dp16h.cuh as a persistent grid (A/B switch)
     bool use_s16h = true;  // diagonal-frame u16x2 kernel (smx_dp16h.cuh) when the scoring allows it; SMX_S16H=0 keeps smx_dp16.cuh
     int s16_max_wsel = 1;  // warps per problem of the s16 kernel are capped at 2 (measured best); SMX_S16_MAXW=1|2|4|8 overrides
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fwd = nullptr;
     float last_ms = 0.f;
     int last_launches = 0;
     // per-kernel timing of the last smx_align_run: [0..13] forward classes (problem_class), [14] traceback, [15] compaction
@@ -79,7 +83,7 @@ struct smx_handle {
     size_t max_chunk_trace = 0;
     int64_t runs_scratch = 0;
     int64_t total_runs = -1;
-    DevBuf d_probs, d_order_cls, d_order_all, d_results, d_trace, d_boundary, d_runs, d_dense, d_dense_off, d_tickets;
+    DevBuf d_probs, d_order_cls, d_order_all, d_results, d_trace, d_boundary, d_runs, d_dense, d_dense_off, d_tickets, d_slots;
     std::vector<SmxResult> h_results;
     std::vector<int64_t> h_dense_off;
 
@@ -97,6 +101,7 @@ struct smx_handle {
     struct SmxPipelineState *pipe = nullptr;
 };
 
+static const int kLineSlots = 4096;  // boundary-line pairs of the non-persistent forward launches (> resident workers of any class)
 static thread_local std::string g_create_error;
 
 static int fail(smx_handle *h, int code, const char *fmt, ...)
@@ -152,8 +157,9 @@ static void release(DevBuf &b)
 static void smx_pipeline_free(smx_handle *h);
 
 // records an event after the launch just issued and tags the interval that ends here
-static int mark(smx_handle *h, int tag)
+static int mark(smx_handle *h, int tag, cudaStream_t stream = nullptr)
 {
+    if (!stream) stream = h->stream;
     if (h->ev_used == h->ev_pool.size()) {
         cudaEvent_t e;
         if (cudaEventCreate(&e) != cudaSuccess) return fail(h, -2, "cudaEventCreate failed");
@@ -161,7 +167,7 @@ static int mark(smx_handle *h, int tag)
         h->ev_tag.push_back(0);
     }
     h->ev_tag[h->ev_used] = tag;
-    cudaError_t e = cudaEventRecord(h->ev_pool[h->ev_used], h->stream);
+    cudaError_t e = cudaEventRecord(h->ev_pool[h->ev_used], stream);
     if (e != cudaSuccess) return fail(h, -2, "cudaEventRecord failed: %s", cudaGetErrorString(e));
     h->ev_used++;
     return 0;
@@ -192,16 +198,29 @@ extern "C" int smx_create(smx_handle **out, int device_ordinal, void *stream)
     h->device = device_ordinal;
     h->sm_count = prop.multiProcessorCount;
     if ((e = cudaSetDevice(device_ordinal)) != cudaSuccess) { delete h; return fail(nullptr, -2, "cudaSetDevice: %s", cudaGetErrorString(e)); }
-    if (stream) { h->stream = (cudaStream_t)stream; h->owns_stream = false; }
+    if (stream) { h->stream = (cudaStream_t)stream; h->stream_hi = h->stream; h->owns_stream = false; }
     else {
-        if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete h; return fail(nullptr, -2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        // Several handles share a GPU (batches in flight).  The short kernels of a batch's front end must not queue
+        // behind the long forward-DP launches of the other handles, or all handles end up in their host phases
+        // at the same time (measured: GPU idle 22 % of the wall clock): they run on a high-priority stream, and the
+        // forward kernels are launched non-persistent so that SM slots free up continuously.
+        int prio_least = 0, prio_greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+        if ((e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_least)) != cudaSuccess) { delete h; return fail(nullptr, -2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        if ((e = cudaStreamCreateWithPriority(&h->stream_hi, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return fail(nullptr, -2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         h->owns_stream = true;
     }
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
+    cudaEventCreateWithFlags(&h->ev_fwd, cudaEventDisableTiming);
+    if (ensure(h, h->d_slots, sizeof(int32_t) * kLineSlots) != 0 || cudaMemset(h->d_slots.p, 0, sizeof(int32_t) * kLineSlots) != cudaSuccess) {
+        g_create_error = "smx_create: cannot allocate the boundary-line slot table";
+        smx_destroy(h);
+        return -3;
+    }
     {
         size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) h->trace_budget = std::max<int64_t>((int64_t)2 << 30, std::min<int64_t>(h->trace_budget, (int64_t)(free_b / 6)));
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) h->trace_budget = std::max<int64_t>((int64_t)2 << 30, std::min<int64_t>(h->trace_budget, (int64_t)(free_b / 8)));
     }
     if (const char *tb = getenv("SMX_TRACE_BUDGET_GB")) { const long v = atol(tb); if (v >= 1 && v <= 160) h->trace_budget = (int64_t)v << 30; }
     *out = h;
@@ -213,8 +232,9 @@ extern "C" void smx_destroy(smx_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    cudaStreamSynchronize(h->stream_hi);
     DevBuf *bufs[] = {&h->pool, &h->pool2, &h->pool_special, &h->d_probs, &h->d_order_cls, &h->d_order_all, &h->d_results, &h->d_trace, &h->d_boundary,
-                      &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts,
+                      &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_slots, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts,
                       &h->d_sel_pairs, &h->d_sel_out, &h->d_regions, &h->d_chain_tasks, &h->d_chain_regions, &h->d_chain_traces,
                       &h->d_chain_out, &h->d_chain_scratch};
     smx_pipeline_free(h);
@@ -223,7 +243,8 @@ extern "C" void smx_destroy(smx_handle *h)
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->owns_stream) cudaStreamDestroy(h->stream);
+    if (h->ev_fwd) cudaEventDestroy(h->ev_fwd);
+    if (h->owns_stream) { cudaStreamDestroy(h->stream); cudaStreamDestroy(h->stream_hi); }
     delete h;
 }
 
@@ -241,18 +262,18 @@ extern "C" int smx_pool_upload(smx_handle *h, const uint8_t *seqs, int64_t n)
     if (!seqs || n <= 0) return fail(h, -1, "smx_pool_upload: empty pool");
     SMX_CUDA(h, cudaSetDevice(h->device));
     if (int rc = ensure(h, h->pool, (size_t)n + 64)) return rc;
-    SMX_CUDA(h, cudaMemcpyAsync(h->pool.p, seqs, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    SMX_CUDA(h, cudaMemcpyAsync(h->pool.p, seqs, (size_t)n, cudaMemcpyHostToDevice, h->stream_hi));
     {
         const int64_t n_words = (n + 31) / 32;  // bit planes: one uint2 per 32 bases
         if (int rc = ensure(h, h->pool2, sizeof(uint2) * (size_t)(n_words + 4))) return rc;
         if (int rc = ensure(h, h->pool_special, (size_t)(n_words + 4))) return rc;
-        SMX_CUDA(h, cudaMemsetAsync(h->pool2.p, 0, sizeof(uint2) * (size_t)(n_words + 4), h->stream));
-        SMX_CUDA(h, cudaMemsetAsync(h->pool_special.p, 0, (size_t)(n_words + 4), h->stream));
-        smx_pack_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, h->stream>>>((const uint8_t *)h->pool.p, n, (uint2 *)h->pool2.p,
+        SMX_CUDA(h, cudaMemsetAsync(h->pool2.p, 0, sizeof(uint2) * (size_t)(n_words + 4), h->stream_hi));
+        SMX_CUDA(h, cudaMemsetAsync(h->pool_special.p, 0, (size_t)(n_words + 4), h->stream_hi));
+        smx_pack_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, h->stream_hi>>>((const uint8_t *)h->pool.p, n, (uint2 *)h->pool2.p,
                                                                                  (uint8_t *)h->pool_special.p, n_words);
         SMX_CUDA(h, cudaGetLastError());
     }
-    SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
     h->pool_len = n;
     // per 64-byte block: does it hold a byte other than A/C/G/T?  prefix over blocks (s16 kernel eligibility)
     {
@@ -368,6 +389,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         const char *env = getenv("SMX_S16");
         h->use_s16 = !(env && env[0] == '0');
         if (const char *mr = getenv("SMX_S16_MINROWS")) { const int v = atoi(mr); if (v >= 32 && v <= 4096) h->s16_min_rows = v; }
+        { const char *pe = getenv("SMX_PERSISTENT"); h->persistent_fwd = pe && pe[0] == '1'; }
         const char *envh = getenv("SMX_S16H");
         h->use_s16h = !(envh && envh[0] == '0') && s16h_scoring_ok(h->sc);
         const char *mw = getenv("SMX_S16_MAXW");
@@ -468,13 +490,44 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
     if (int rc = ensure(h, h->d_runs, sizeof(uint32_t) * (size_t)h->runs_scratch)) return rc;
     if (int rc = ensure(h, h->d_dense_off, sizeof(int64_t) * ((size_t)n + 1))) return rc;
     if (int rc = ensure(h, h->d_tickets, sizeof(int32_t) * kNumFwdClasses * h->chunks.size())) return rc;
-    SMX_CUDA(h, cudaMemcpyAsync(h->d_probs.p, h->probs.data(), sizeof(SmxProblem) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    SMX_CUDA(h, cudaMemcpyAsync(h->d_order_cls.p, h->order_cls.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    SMX_CUDA(h, cudaMemcpyAsync(h->d_order_all.p, h->order_all.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    SMX_CUDA(h, cudaMemcpyAsync(h->d_probs.p, h->probs.data(), sizeof(SmxProblem) * (size_t)n, cudaMemcpyHostToDevice, h->stream_hi));
+    SMX_CUDA(h, cudaMemcpyAsync(h->d_order_cls.p, h->order_cls.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream_hi));
+    SMX_CUDA(h, cudaMemcpyAsync(h->d_order_all.p, h->order_all.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream_hi));
+    SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
     h->n = n;
     return 0;
 }
+
+// Handles that share a GPU submit their forward-DP phase through this gate: at most `permits` DP phases are on the
+// device at a time (FIFO between handles), while the short front-end kernels of the other handles cut in on their
+// high-priority streams.  Without it all handles in flight submit their DP phases together, the GPU time-slices
+// them, they all finish at the same moment, and every handle is in its host phase at once (measured: GPU idle 22 %).
+struct DpGate {
+    std::mutex mu;
+    std::condition_variable cv;
+    int in_flight = 0;
+    unsigned long long next_ticket = 0, serving = 0;
+    int permits()
+    {
+        static const int p = [] { const char *e = getenv("SMX_DP_INFLIGHT"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+        return p;
+    }
+    void enter()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        const unsigned long long my = next_ticket++;
+        cv.wait(lk, [&] { return my == serving && in_flight < permits(); });
+        ++serving;
+        ++in_flight;
+        cv.notify_all();
+    }
+    void leave()
+    {
+        { std::lock_guard<std::mutex> lk(mu); --in_flight; }
+        cv.notify_all();
+    }
+};
+static DpGate g_dp_gate[16];
 
 template <int K, bool LOCAL, bool TEAM>
 static int launch_forward(smx_handle *h, const Chunk &c, int cls, int chunk_idx)
@@ -502,6 +555,7 @@ static int launch_forward(smx_handle *h, const Chunk &c, int cls, int chunk_idx)
     a.results = (SmxResult *)h->d_results.p;
     a.sc = h->sc;
     a.one = 1u;
+    a.max_tickets = INT32_MAX; a.n_slots = 0; a.slot_flags = nullptr;
     smx_dp_forward<K, LOCAL, TEAM><<<blocks, threads, 0, h->stream>>>(a);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
@@ -520,9 +574,12 @@ static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_id
     SMX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
     if (occ < 1) occ = 1;
     const int per_block = TEAM ? 1 : threads / 32;
-    int blocks = std::min(h->sm_count * occ, (count + per_block - 1) / per_block);
+    // smx_dp16h.cuh is launched non-persistent (one problem per worker, boundary lines claimed from a slot pool)
+    const bool persistent = !h->use_s16h || h->persistent_fwd;
+    int blocks = (count + per_block - 1) / per_block;
+    if (persistent) blocks = std::min(h->sm_count * occ, blocks);
     if (blocks < 1) blocks = 1;
-    const size_t workers = TEAM ? (size_t)blocks : (size_t)blocks * (threads / 32);
+    const size_t workers = !persistent ? (size_t)kLineSlots : TEAM ? (size_t)blocks : (size_t)blocks * (threads / 32);
     if (int rc = ensure(h, h->d_boundary, sizeof(int2) * 2 * (size_t)h->nmax * workers)) return rc;
     SmxFwdArgs a;
     a.pool = (const uint8_t *)h->pool.p;
@@ -536,13 +593,22 @@ static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_id
     a.results = (SmxResult *)h->d_results.p;
     a.sc = h->sc;
     a.one = 1u;
+    a.max_tickets = persistent ? INT32_MAX : 1;
+    a.n_slots = kLineSlots;
+    a.slot_flags = persistent ? nullptr : (int32_t *)h->d_slots.p;
     kern<<<blocks, threads, 0, h->stream>>>(a);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
     return mark(h, cls);
 }
 
-extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
+static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate);
+
+extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs) { return align_run_impl(h, total_runs, nullptr); }
+
+// gate != nullptr (pipeline): the launches wait for admission, and the gate is handed on as soon as the last forward
+// kernel has finished -- the latency-bound tail of the traceback overlaps the next handle's forward launch
+static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
 {
     if (!h) return -1;
     if (total_runs) *total_runs = 0;
@@ -552,9 +618,15 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
     SMX_CUDA(h, cudaSetDevice(h->device));
     // boundary lines must be sized before the timed region (no allocation between launches)
     {
-        const size_t line_bytes = sizeof(int2) * 2 * (size_t)h->nmax * (size_t)h->sm_count * 16 * 4;  // >= workers of any class
+        const size_t line_bytes = sizeof(int2) * 2 * (size_t)h->nmax * (size_t)std::max(h->sm_count * 16 * 4, kLineSlots);  // >= workers of any class
         if (int rc = ensure(h, h->d_boundary, line_bytes)) return rc;
     }
+    struct GateGuard {  // leaves the gate on every exit path
+        DpGate *g;
+        ~GateGuard() { if (g) g->leave(); }
+        void release() { if (g) { g->leave(); g = nullptr; } }
+    } guard{gate};
+    if (gate) gate->enter();
     SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     SMX_CUDA(h, cudaMemsetAsync(h->d_tickets.p, 0, sizeof(int32_t) * kNumFwdClasses * h->chunks.size(), h->stream));
     h->ev_used = 0;
@@ -577,6 +649,7 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
         if ((rc = launch_forward<2, true, false>(h, c, 3, (int)ci))) return rc;
         if ((rc = launch_forward<1, false, false>(h, c, 0, (int)ci))) return rc;
         if ((rc = launch_forward<1, true, false>(h, c, 1, (int)ci))) return rc;
+        if (gate && ci + 1 == h->chunks.size()) SMX_CUDA(h, cudaEventRecord(h->ev_fwd, h->stream));  // last forward kernel is in
         SmxTbArgs t;
         t.pool = (const uint8_t *)h->pool.p;
         t.probs = (const SmxProblem *)h->d_probs.p;
@@ -597,6 +670,7 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
     // results header to host: run counts -> dense offsets -> compaction
     h->h_results.resize((size_t)h->n);
     SMX_CUDA(h, cudaMemcpyAsync(h->h_results.data(), h->d_results.p, sizeof(SmxResult) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    if (gate) { SMX_CUDA(h, cudaEventSynchronize(h->ev_fwd)); guard.release(); }
     SMX_CUDA(h, cudaStreamSynchronize(h->stream));
     SMX_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     h->h_dense_off.resize((size_t)h->n + 1);
@@ -605,15 +679,15 @@ extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs)
     h->h_dense_off[(size_t)h->n] = acc;
     h->total_runs = acc;
     if (int rc = ensure(h, h->d_dense, sizeof(uint32_t) * (size_t)std::max<int64_t>(acc, 1))) return rc;
-    SMX_CUDA(h, cudaMemcpyAsync(h->d_dense_off.p, h->h_dense_off.data(), sizeof(int64_t) * ((size_t)h->n + 1), cudaMemcpyHostToDevice, h->stream));
+    SMX_CUDA(h, cudaMemcpyAsync(h->d_dense_off.p, h->h_dense_off.data(), sizeof(int64_t) * ((size_t)h->n + 1), cudaMemcpyHostToDevice, h->stream_hi));
     const int threads = 256, wpb = threads / 32;
-    smx_compact_runs<<<(h->n + wpb - 1) / wpb, threads, 0, h->stream>>>((const SmxProblem *)h->d_probs.p, (const SmxResult *)h->d_results.p,
+    smx_compact_runs<<<(h->n + wpb - 1) / wpb, threads, 0, h->stream_hi>>>((const SmxProblem *)h->d_probs.p, (const SmxResult *)h->d_results.p,
                                                                         (const int64_t *)h->d_dense_off.p, (const uint32_t *)h->d_runs.p,
                                                                         (uint32_t *)h->d_dense.p, h->n);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
-    if (int rc = mark(h, kSlotCompact)) return rc;
-    SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (int rc = mark(h, kSlotCompact, h->stream_hi)) return rc;
+    SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
     for (size_t i = 1; i < h->ev_used; ++i) {
         if (h->ev_tag[i] < 0) continue;
         float ms = 0.f;
@@ -641,8 +715,8 @@ extern "C" int smx_align_fetch(smx_handle *h, int32_t *score, int32_t *end_query
     if (cigar_off) memcpy(cigar_off, h->h_dense_off.data(), sizeof(int64_t) * ((size_t)h->n + 1));
     if (cigar_rle && h->total_runs > 0) {
         SMX_CUDA(h, cudaSetDevice(h->device));
-        SMX_CUDA(h, cudaMemcpyAsync(cigar_rle, h->d_dense.p, sizeof(uint32_t) * (size_t)h->total_runs, cudaMemcpyDeviceToHost, h->stream));
-        SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+        SMX_CUDA(h, cudaMemcpyAsync(cigar_rle, h->d_dense.p, sizeof(uint32_t) * (size_t)h->total_runs, cudaMemcpyDeviceToHost, h->stream_hi));
+        SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
     }
     return 0;
 }
@@ -709,9 +783,9 @@ extern "C" int smx_scan_prepare(smx_handle *h, const int64_t *ref_off, const int
     if (int rc = ensure(h, h->d_scan_pairs, sizeof(SmxScanPair) * (size_t)n)) return rc;
     if (int rc = ensure(h, h->d_scan_tile_pair, sizeof(int32_t) * (size_t)tiles)) return rc;
     if (int rc = ensure(h, h->d_counts, sizeof(int32_t) * (size_t)total)) return rc;
-    SMX_CUDA(h, cudaMemcpyAsync(h->d_scan_pairs.p, pairs.data(), sizeof(SmxScanPair) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-    SMX_CUDA(h, cudaMemcpyAsync(h->d_scan_tile_pair.p, tile_pair.data(), sizeof(int32_t) * (size_t)tiles, cudaMemcpyHostToDevice, h->stream));
-    SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    SMX_CUDA(h, cudaMemcpyAsync(h->d_scan_pairs.p, pairs.data(), sizeof(SmxScanPair) * (size_t)n, cudaMemcpyHostToDevice, h->stream_hi));
+    SMX_CUDA(h, cudaMemcpyAsync(h->d_scan_tile_pair.p, tile_pair.data(), sizeof(int32_t) * (size_t)tiles, cudaMemcpyHostToDevice, h->stream_hi));
+    SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
     h->scan_n = n;
     return 0;
 }
@@ -736,12 +810,12 @@ extern "C" int smx_scan_run(smx_handle *h)
     a.topology = h->scan_topology;
     a.pool2 = (const uint2 *)h->pool2.p;
     a.special = (const uint8_t *)h->pool_special.p;
-    SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    scan_kern<<<h->scan_tiles, SMX_SCAN_THREADS, smem, h->stream>>>(a);
+    SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream_hi));
+    scan_kern<<<h->scan_tiles, SMX_SCAN_THREADS, smem, h->stream_hi>>>(a);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches = 1;
-    SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-    SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream_hi));
+    SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
     SMX_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     return 0;
 }
@@ -752,8 +826,8 @@ extern "C" int smx_scan_fetch(smx_handle *h, int32_t *counts, int64_t counts_cap
     if (!counts || counts_capacity < h->scan_total) return fail(h, -1, "smx_scan_fetch: counts buffer too small");
     if (h->scan_n == 0) return 0;
     SMX_CUDA(h, cudaSetDevice(h->device));
-    SMX_CUDA(h, cudaMemcpyAsync(counts, h->d_counts.p, sizeof(int32_t) * (size_t)h->scan_total, cudaMemcpyDeviceToHost, h->stream));
-    SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    SMX_CUDA(h, cudaMemcpyAsync(counts, h->d_counts.p, sizeof(int32_t) * (size_t)h->scan_total, cudaMemcpyDeviceToHost, h->stream_hi));
+    SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
     return 0;
 }
 
@@ -796,13 +870,13 @@ extern "C" int smx_measure_int_peak(smx_handle *h, int32_t iters, double *out_go
     for (int which = 0; which < 3; ++which) {
         float best = 1e30f;
         for (int rep = 0; rep < 3; ++rep) {
-            SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-            if (which == 0) smx_int_peak_kernel<0><<<blocks, threads, 0, h->stream>>>((int *)h->d_tickets.p, iters, 12345 + rep);
-            else if (which == 1) smx_int_peak_kernel<1><<<blocks, threads, 0, h->stream>>>((int *)h->d_tickets.p, iters, 12345 + rep);
-            else smx_int_peak_kernel<2><<<blocks, threads, 0, h->stream>>>((int *)h->d_tickets.p, iters, 12345 + rep);
+            SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream_hi));
+            if (which == 0) smx_int_peak_kernel<0><<<blocks, threads, 0, h->stream_hi>>>((int *)h->d_tickets.p, iters, 12345 + rep);
+            else if (which == 1) smx_int_peak_kernel<1><<<blocks, threads, 0, h->stream_hi>>>((int *)h->d_tickets.p, iters, 12345 + rep);
+            else smx_int_peak_kernel<2><<<blocks, threads, 0, h->stream_hi>>>((int *)h->d_tickets.p, iters, 12345 + rep);
             SMX_CUDA(h, cudaGetLastError());
-            SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-            SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+            SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream_hi));
+            SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
             float ms = 0.f;
             SMX_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
             best = std::min(best, ms);
@@ -841,6 +915,20 @@ void init_comp()
 
 static SmxPipelineState *pipeline_state(smx_handle *h);
 
+// SMX_PHASE_LOG=1: one stderr line per GPU phase of a pipeline call ("PH handle label t0 t1", steady-clock seconds)
+struct PhaseLog {
+    bool on = getenv("SMX_PHASE_LOG") != nullptr;
+    std::vector<std::string> lines;
+    void add(const void *h, const char *label, double t0, double t1)
+    {
+        if (!on) return;
+        char buf[160];
+        snprintf(buf, sizeof buf, "PH %p %s %.6f %.6f\n", h, label, t0, t1);
+        lines.emplace_back(buf);
+    }
+    ~PhaseLog() { for (const std::string &l : lines) fputs(l.c_str(), stderr); }
+};
+
 extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const int64_t *ref_off, const int32_t *ref_len, int32_t n_refs,
                                 const double *ref_sigma, const uint8_t *qry_seqs, const int64_t *qry_off, const int32_t *qry_len,
                                 int32_t n_qrys, const int32_t *pair_ref, const int32_t *pair_qry, int32_t n_pairs, int32_t open,
@@ -857,6 +945,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     if ((pair_ref == nullptr) != (pair_qry == nullptr)) return fail(h, -1, "pair_ref and pair_qry must both be given or both be NULL");
     if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
     init_comp();
+    PhaseLog plog;
     const double t_begin = now_s();
     SMX_CUDA(h, cudaSetDevice(h->device));
     const Scoring sc{open, extend, match, mismatch};
@@ -936,7 +1025,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         }
         double t0 = now_s();
         if (int rc = smx_scan_prepare(h, s_roff.data(), s_rlen.data(), s_qoff.data(), s_qlen.data(), n, topology, c_off.data())) return rc;
-        if (int rc = smx_scan_run(h)) return rc;
+        { const double p0 = now_s(); if (int rc = smx_scan_run(h)) return rc; plog.add(h, "scan", p0, now_s()); }
         st.gpu_scan_ms += h->last_ms; st.scan_cells += h->scan_cells; st.launches += 1;
         st.t_scan += now_s() - t0;
         t0 = now_s();
@@ -956,27 +1045,29 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         if (int rc = ensure(h, h->d_sel_out, sizeof(SmxSelOut) * (size_t)n)) return rc;
         if (int rc = ensure(h, h->d_regions, sizeof(SmxRegion) * (size_t)n * kRegionCap + 64)) return rc;
         int32_t *d_region_counter = (int32_t *)((char *)h->d_regions.p + sizeof(SmxRegion) * (size_t)n * kRegionCap);
-        SMX_CUDA(h, cudaMemsetAsync(d_region_counter, 0, sizeof(int32_t), h->stream));
-        SMX_CUDA(h, cudaMemcpyAsync(h->d_sel_pairs.p, sel_pairs.data(), sizeof(SmxSelPair) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+        SMX_CUDA(h, cudaMemsetAsync(d_region_counter, 0, sizeof(int32_t), h->stream_hi));
+        SMX_CUDA(h, cudaMemcpyAsync(h->d_sel_pairs.p, sel_pairs.data(), sizeof(SmxSelPair) * (size_t)n, cudaMemcpyHostToDevice, h->stream_hi));
         SmxSelArgs sa;
         sa.pool = (const uint8_t *)h->pool.p; sa.pairs = (const SmxSelPair *)h->d_sel_pairs.p; sa.counts = (const int32_t *)h->d_counts.p;
         sa.regions = (SmxRegion *)h->d_regions.p; sa.out = (SmxSelOut *)h->d_sel_out.p; sa.region_counter = d_region_counter; sa.topology = topology;
-        SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-        smx_select_kernel<<<n, SMX_SEL_THREADS, 0, h->stream>>>(sa);
+        const double p_sel0 = now_s();
+        SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream_hi));
+        smx_select_kernel<<<n, SMX_SEL_THREADS, 0, h->stream_hi>>>(sa);
         SMX_CUDA(h, cudaGetLastError());
-        SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream_hi));
         st.launches += 1;
         int32_t n_regions_total = 0;
-        SMX_CUDA(h, cudaMemcpyAsync(sel_out.data(), h->d_sel_out.p, sizeof(SmxSelOut) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
-        SMX_CUDA(h, cudaMemcpyAsync(&n_regions_total, d_region_counter, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-        SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+        SMX_CUDA(h, cudaMemcpyAsync(sel_out.data(), h->d_sel_out.p, sizeof(SmxSelOut) * (size_t)n, cudaMemcpyDeviceToHost, h->stream_hi));
+        SMX_CUDA(h, cudaMemcpyAsync(&n_regions_total, d_region_counter, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream_hi));
+        SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
         if (int rc = ensure_pinned(h, h->pin_regions, sizeof(SmxRegion) * (size_t)std::max(n_regions_total, 1))) return rc;
         SmxRegion *reg_host = (SmxRegion *)h->pin_regions.p;
         if (n_regions_total > 0) {
-            SMX_CUDA(h, cudaMemcpyAsync(reg_host, h->d_regions.p, sizeof(SmxRegion) * (size_t)n_regions_total, cudaMemcpyDeviceToHost, h->stream));
-            SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+            SMX_CUDA(h, cudaMemcpyAsync(reg_host, h->d_regions.p, sizeof(SmxRegion) * (size_t)n_regions_total, cudaMemcpyDeviceToHost, h->stream_hi));
+            SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
         }
         { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1); st.gpu_select_ms += ms; }
+        plog.add(h, "select", p_sel0, now_s());
         for (int i = 0; i < n; ++i) {
             PairStrand &x = st.ps[(size_t)active[pos + i]];
             const SmxSelOut &o = sel_out[i];
@@ -1053,9 +1144,10 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
             if (int rc = ensure(h, h->d_chain_traces, sizeof(int32_t) * (size_t)std::max<int64_t>(trace_total, 1))) return rc;
             if (int rc = ensure(h, h->d_chain_out, sizeof(SmxChainOut) * tasks.size())) return rc;
             if (int rc = ensure(h, h->d_chain_scratch, sizeof(int32_t) * 3 * regs.size())) return rc;
-            SMX_CUDA(h, cudaMemcpyAsync(h->d_chain_tasks.p, tasks.data(), sizeof(SmxChainTask) * tasks.size(), cudaMemcpyHostToDevice, h->stream));
-            SMX_CUDA(h, cudaMemcpyAsync(h->d_chain_regions.p, regs.data(), sizeof(int4) * regs.size(), cudaMemcpyHostToDevice, h->stream));
-            SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+            const double p_ch0 = now_s();
+            SMX_CUDA(h, cudaMemcpyAsync(h->d_chain_tasks.p, tasks.data(), sizeof(SmxChainTask) * tasks.size(), cudaMemcpyHostToDevice, h->stream_hi));
+            SMX_CUDA(h, cudaMemcpyAsync(h->d_chain_regions.p, regs.data(), sizeof(int4) * regs.size(), cudaMemcpyHostToDevice, h->stream_hi));
+            SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream_hi));
             for (int c = 0; c < 4; ++c) {
                 const int cnt = cls_first[c + 1] - cls_first[c];
                 if (cnt == 0) continue;
@@ -1074,23 +1166,24 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
                 int slices = 1;
                 if (topology == 0 && cnt < 2 * h->sm_count) slices = std::max(1, std::min(nmax / SMX_CHAIN_WARPS, (2 * h->sm_count + cnt - 1) / cnt));
                 ca.n_slices = slices; ca.phase = 0;
-                smx_chain_kernel<<<cnt * slices, SMX_CHAIN_WARPS * 32, smem, h->stream>>>(ca);
+                smx_chain_kernel<<<cnt * slices, SMX_CHAIN_WARPS * 32, smem, h->stream_hi>>>(ca);
                 SMX_CUDA(h, cudaGetLastError());
                 st.launches += 1;
                 if (slices > 1) {
                     ca.n_slices = 1; ca.phase = 1;
-                    smx_chain_kernel<<<cnt, SMX_CHAIN_WARPS * 32, smem, h->stream>>>(ca);
+                    smx_chain_kernel<<<cnt, SMX_CHAIN_WARPS * 32, smem, h->stream_hi>>>(ca);
                     SMX_CUDA(h, cudaGetLastError());
                     st.launches += 1;
                 }
             }
-            SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+            SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream_hi));
             std::vector<SmxChainOut> couts(tasks.size());
             std::vector<int32_t> tr((size_t)std::max<int64_t>(trace_total, 1));
-            SMX_CUDA(h, cudaMemcpyAsync(couts.data(), h->d_chain_out.p, sizeof(SmxChainOut) * tasks.size(), cudaMemcpyDeviceToHost, h->stream));
-            SMX_CUDA(h, cudaMemcpyAsync(tr.data(), h->d_chain_traces.p, sizeof(int32_t) * (size_t)std::max<int64_t>(trace_total, 1), cudaMemcpyDeviceToHost, h->stream));
-            SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+            SMX_CUDA(h, cudaMemcpyAsync(couts.data(), h->d_chain_out.p, sizeof(SmxChainOut) * tasks.size(), cudaMemcpyDeviceToHost, h->stream_hi));
+            SMX_CUDA(h, cudaMemcpyAsync(tr.data(), h->d_chain_traces.p, sizeof(int32_t) * (size_t)std::max<int64_t>(trace_total, 1), cudaMemcpyDeviceToHost, h->stream_hi));
+            SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
             { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1); st.gpu_chain_ms += ms; }
+            plog.add(h, "chain", p_ch0, now_s());
             for (size_t k = 0; k < tasks.size(); ++k) {
                 std::vector<int> &t = traces[(size_t)task_ti[k]];
                 t.assign(tr.begin() + tasks[k].trace_off, tr.begin() + tasks[k].trace_off + couts[k].trace_len);
@@ -1207,16 +1300,21 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     if (n_prob > 0) {
         if (int rc = align_prepare_impl(h, p_s1.data(), p_m.data(), p_s2.data(), p_n.data(), p_mode.data(), p_clip.data(), n_prob, open, extend, match, mismatch)) return rc;
         int64_t truns = 0;
-        if (int rc = smx_align_run(h, &truns)) return rc;
+        {
+            const double p0 = now_s();
+            if (int rc = align_run_impl(h, &truns, &g_dp_gate[h->device & 15])) return rc;
+            plog.add(h, "dp", p0, now_s());
+        }
         st.gpu_dp_ms = h->last_ms; st.dp_cells = h->cells; st.launches += h->last_launches;
         for (int c = 0; c < 16; ++c) st.dp_kernel_ms[c] = h->kernel_ms[c];
         for (int c = 0; c < 14; ++c) st.dp_class_cells[c] = h->class_cells[c];
         for (int c = 0; c < 16; ++c) st.dp_kernel_launches[c] = h->kernel_launches[c];
         if (int rc = ensure_pinned(h, h->pin_cigar, sizeof(uint32_t) * (size_t)std::max<int64_t>(truns, 1))) return rc;
         cg = (uint32_t *)h->pin_cigar.p;
-        if (int rc = smx_align_fetch(h, nullptr, nullptr, nullptr, nullptr, nullptr, cg_off.data(), cg, std::max<int64_t>(truns, 1))) return rc;
+        { const double p0 = now_s(); if (int rc = smx_align_fetch(h, nullptr, nullptr, nullptr, nullptr, nullptr, cg_off.data(), cg, std::max<int64_t>(truns, 1))) return rc; plog.add(h, "fetch", p0, now_s()); }
     }
     st.t_dp = now_s() - t0;
+    plog.add(h, "call", t_begin, now_s());
 
     // ---- A9-A11 on host threads (run-length domain; re-clipping already happened in the traceback kernel) ----
     t0 = now_s();

@@ -81,6 +81,13 @@ struct SmxFwdArgs {
     SmxResult *results;
     SmxScoring sc;
     uint32_t one;  // always 1 (a kernel parameter so that ptxas cannot fold the IMAD it feeds, smx_dp16.cuh)
+    // smx_dp16h.cuh only: non-persistent launch.  Every worker (warp, or CTA in team mode) takes `max_tickets` problems
+    // and leaves, so that blocks retire all the time and short kernels of other streams (scan / select / chain of the
+    // next batch, on a high-priority stream) get SM slots while a long forward launch is running.  Boundary lines are
+    // then claimed from `n_slots` line pairs through `slot_flags` (0 = free) instead of being indexed by the worker.
+    int32_t max_tickets;
+    int32_t n_slots;
+    int32_t *slot_flags;
 };
 
 #define SMX_TEAM_WARPS 8  // warps of a CTA that share one large problem (bands interleaved)

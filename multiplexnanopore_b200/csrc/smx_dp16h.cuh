@@ -164,7 +164,20 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
     constexpr int LAG = SMX16_LAG;
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int worker = TEAM ? blockIdx.x : ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    __shared__ int s_slot[W == 1 ? 4 : 1];
+    // claim a pair of boundary lines (see SmxFwdArgs::slot_flags); released when the worker leaves
+    int worker = TEAM ? blockIdx.x : ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (a.slot_flags) {
+        if (TEAM ? threadIdx.x == 0 : lane == 0) {
+            unsigned smid;
+            asm("mov.u32 %0, %%smid;" : "=r"(smid));
+            int sl = (int)((smid * 61u + (unsigned)worker * 17u) % (unsigned)a.n_slots);
+            while (atomicCAS(&a.slot_flags[sl], 0, 1) != 0) sl = sl + 1 == a.n_slots ? 0 : sl + 1;
+            s_slot[TEAM ? 0 : wib] = sl;
+        }
+        if (TEAM) __syncthreads(); else __syncwarp();
+        worker = s_slot[TEAM ? 0 : wib];
+    }
     uint32_t *line0 = reinterpret_cast<uint32_t *>(a.boundary + (size_t)worker * 2 * (size_t)a.nmax);
     uint32_t *line1 = line0 + a.nmax;
     const int go = a.sc.go, ge = a.sc.ge;
@@ -183,7 +196,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
     __shared__ int s_red[W][6];
     __shared__ uint4 s_top[W == 1 ? 4 : W][32];
 
-    for (;;) {
+    for (int served = 0; served < a.max_tickets; ++served) {
         int ticket = 0;
         if (TEAM) {
             __syncthreads();
@@ -416,5 +429,9 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
             r.score = corner; r.end_q = m - 1; r.end_r = n - 1;
         }
         if (TEAM ? (threadIdx.x == 0) : (lane == 0)) a.results[pid] = r;
+    }
+    if (a.slot_flags) {
+        if (TEAM) __syncthreads(); else __syncwarp();
+        if (TEAM ? threadIdx.x == 0 : lane == 0) atomicExch(&a.slot_flags[worker], 0);
     }
 }

@@ -237,6 +237,14 @@ _STAT_KEYS = ("t_total", "t_pool", "t_scan", "t_select", "t_chain", "t_dp", "t_s
     + ("gpu_select_only_ms", "gpu_chain_ms")
 
 
+def pack_slice(packed, lo, hi):
+    """the sub-batch [lo, hi) of sequences packed by `_pack`, without copying the bases"""
+    buf, offs, lens = packed
+    base = int(offs[lo])
+    end = int(offs[hi - 1]) + int(lens[hi - 1])
+    return buf[base:end], offs[lo:hi] - base, lens[lo:hi]
+
+
 def _pack(seqs):
     enc = [s.encode("ascii") if isinstance(s, str) else bytes(s) for s in seqs]
     lens = np.array([len(e) for e in enc], dtype=np.int32)
@@ -251,19 +259,20 @@ def pipeline_run(self, refs, queries, sigmas, open_: int, extend: int, match: in
     """A1: scan -> select -> chain -> DP -> stitch for every (query, reference) pair and both strands.
     refs/queries: upper-case str (or bytes); sigmas: float64 per reference; pairs: optional int array [P, 2]
     of (ref_idx, query_idx); default = all combinations, query-major."""
-    rb, ro, rl = _pack(refs)
-    qb, qo, ql = _pack(queries)
+    rb, ro, rl = refs if isinstance(refs, tuple) else _pack(refs)
+    qb, qo, ql = queries if isinstance(queries, tuple) else _pack(queries)   # tuples: already packed (bytes, offsets, lengths)
+    n_refs, n_queries = len(rl), len(ql)
     sig = np.ascontiguousarray(sigmas, dtype=np.float64)
-    if sig.size != len(refs):
+    if sig.size != n_refs:
         raise ValueError("one sigma per reference")
     if pairs is not None:
         pairs = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
         pr = np.ascontiguousarray(pairs[:, 0]); pq = np.ascontiguousarray(pairs[:, 1]); n_pairs = pairs.shape[0]
     else:
-        pr = pq = None; n_pairs = len(refs) * len(queries)
+        pr = pq = None; n_pairs = n_refs * n_queries
     total = ctypes.c_int64(0)
-    self._check(self._lib.smx_pipeline_run(self._h, _ptr(rb), _ptr(ro), _ptr(rl), len(refs), _ptr(sig), _ptr(qb), _ptr(qo), _ptr(ql),
-                                           len(queries), _ptr(pr), _ptr(pq), n_pairs, open_, extend, match, mismatch, int(topology),
+    self._check(self._lib.smx_pipeline_run(self._h, _ptr(rb), _ptr(ro), _ptr(rl), n_refs, _ptr(sig), _ptr(qb), _ptr(qo), _ptr(ql),
+                                           n_queries, _ptr(pr), _ptr(pq), n_pairs, open_, extend, match, mismatch, int(topology),
                                            int(bool(omit_too_long)), int(n_threads), ctypes.byref(total)), "smx_pipeline_run")
     n = 2 * n_pairs
     score = np.empty(n, np.int32); off = np.empty(n, np.int32); status = np.empty(n, np.uint8)

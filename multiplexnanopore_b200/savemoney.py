@@ -118,7 +118,7 @@ def _engines_for(engine, n):
 
 
 def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None, n_threads=0, batch_queries=1000,
-              overlap=4):
+              overlap=6):
     """The alignment stage for every (query, reference) pair and both strands (or the explicit `pairs`).
     Queries are processed in batches of `batch_queries` so that device workspaces stay bounded; `overlap`
     batches are in flight at once (one engine handle and one Python thread each; ctypes drops the GIL)."""
@@ -132,8 +132,13 @@ def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None,
     if pairs is not None or len(queries) <= batch_queries:
         return eng.pipeline_run(refs, queries, sig, *args, pairs=pairs, n_threads=n_threads)
     starts = list(range(0, len(queries), batch_queries))
+    # pack once: the batches below are zero-copy views (per-batch packing would run under the GIL of every worker)
+    from .engine import _pack, pack_slice
+    n_q = len(queries)
+    refs = _pack(refs)
+    queries = _pack(queries)
     if overlap <= 1:
-        parts = [eng.pipeline_run(refs, queries[b:b + batch_queries], sig, *args, n_threads=n_threads) for b in starts]
+        parts = [eng.pipeline_run(refs, pack_slice(queries, b, min(b + batch_queries, n_q)), sig, *args, n_threads=n_threads) for b in starts]
         return _merge(parts)
     from concurrent.futures import ThreadPoolExecutor
     import queue
@@ -148,7 +153,7 @@ def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None,
     def work(b):
         e = free.get()
         try:
-            return e.pipeline_run(refs, queries[b:b + batch_queries], sig, *args, n_threads=n_threads)
+            return e.pipeline_run(refs, pack_slice(queries, b, min(b + batch_queries, n_q)), sig, *args, n_threads=n_threads)
         finally:
             free.put(e)
 

@@ -93,7 +93,7 @@ def test_trace_budget_chunking(engine):
     try:
         run_and_compare(engine, probs, modes, (3, 1, 1, -2))
     finally:
-        engine.set_trace_budget(24 << 30)
+        engine.set_trace_budget(16 << 30)
 
 
 def test_rejects_bad_input(engine):
