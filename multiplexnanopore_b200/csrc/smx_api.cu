@@ -53,6 +53,7 @@ struct smx_handle {
     int64_t trace_budget = (int64_t)16 << 30;  // clamped to an eighth of the free device memory at creation
     bool use_s16 = true;  // SMX_S16=0 forces the int32 kernels (cross-check)
     int s16_min_rows = 32;   // the diagonal-frame kernel takes problems of more rows than this (SMX_S16_MINROWS overrides)
+    int64_t team_min_cells = 0;  // SMX_TEAM_MIN_MCELLS (in Mi cells): below it one warp per problem (measured: no gain on C2)
     bool persistent_fwd = false;  // SMX_PERSISTENT=1: launch smx_dp16h.cuh as a persistent grid (A/B switch)
     bool use_s16h = true;  // diagonal-frame u16x2 kernel (smx_dp16h.cuh) when the scoring allows it; SMX_S16H=0 keeps smx_dp16.cuh
     int s16_max_wsel = 1;  // warps per problem of the s16 kernel are capped at 2 (measured best); SMX_S16_MAXW=1|2|4|8 overrides
@@ -389,6 +390,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         const char *env = getenv("SMX_S16");
         h->use_s16 = !(env && env[0] == '0');
         if (const char *mr = getenv("SMX_S16_MINROWS")) { const int v = atoi(mr); if (v >= 32 && v <= 4096) h->s16_min_rows = v; }
+        if (const char *tm = getenv("SMX_TEAM_MIN_MCELLS")) h->team_min_cells = (int64_t)atol(tm) << 20;
         { const char *pe = getenv("SMX_PERSISTENT"); h->persistent_fwd = pe && pe[0] == '1'; }
         const char *envh = getenv("SMX_S16H");
         h->use_s16h = !(envh && envh[0] == '0') && s16h_scoring_ok(h->sc);
@@ -420,6 +422,9 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
             const int pairs = ((m + 255) / 256 + 1) / 2;
             int wsel = pairs >= 8 ? 3 : pairs >= 4 ? 2 : pairs >= 2 ? 1 : 0;
             if (wsel > h->s16_max_wsel) wsel = h->s16_max_wsel;
+            // teams shorten the critical path of the largest problems (launch tail) but idle a warp whenever the band pairs
+            // do not divide evenly: everything below the threshold runs one warp per problem
+            if ((int64_t)m * nn < h->team_min_cells) wsel = 0;
             q.cls = (int16_t)(kClsS16 + wsel);
             q.kshift = 3;  // the packed kernels always run 8 rows per lane (trace layout and traceback follow kshift)
         }

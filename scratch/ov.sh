@@ -5,12 +5,12 @@ run() { # label, env, args
 import json
 d=json.loads(open('/tmp/line.json').read())
 k=d["kernel_ms_per_step_rank0"]
-print(round(d["ms_per_step"]), "ms/step", round(d["e2e"]["reads_per_s"]), "reads/s; dev GCUPS", round(d["value"]), "e2e GCUPS", round(d["e2e"]["value"]), "dev ms", round(d["device_ms_per_step"]), "util", d["clocks"].get("gpu_util_pct_mean"), "W", d["clocks"].get("power_w_mean"))
-print("   w2", round(k["dp_forward16_w2"]), "w1", round(k["dp_forward16_w1"]), "k4", round(k["dp_forward_k4"]), "k2", round(k["dp_forward_k2"]), "k1", round(k["dp_forward_k1"]), "tb", round(k["traceback"]))
+print(round(d["ms_per_step"]), "ms/step", round(d["e2e"]["reads_per_s"]), "reads/s; dev GCUPS", round(d["value"]), "e2e GCUPS", round(d["e2e"]["value"]), "dev ms", round(d["device_ms_per_step"]), "util", round(d["clocks"].get("gpu_util_pct_mean") or 0))
+print("   w2", round(k["dp_forward16_w2"]), "w1", round(k["dp_forward16_w1"]), "k1", round(k["dp_forward_k1"]), "tb", round(k["traceback"]))
 PY
 }
-run "default" "A=1" ""
-run "minrows 64" "SMX_S16_MINROWS=64" ""
-run "minrows 32" "SMX_S16_MINROWS=32" ""
-run "maxw 4" "SMX_S16_MAXW=4" ""
-run "overlap 5" "A=1" "--overlap 5"
+run "team min 0" "SMX_TEAM_MIN_MCELLS=0" ""
+run "team min 8" "SMX_TEAM_MIN_MCELLS=8" ""
+run "team min 16" "SMX_TEAM_MIN_MCELLS=16" ""
+run "team min 32" "SMX_TEAM_MIN_MCELLS=32" ""
+run "team min 1000 (W=1 only)" "SMX_TEAM_MIN_MCELLS=1000" ""
