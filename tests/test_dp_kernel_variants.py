@@ -1,0 +1,71 @@
+"""The three forward-DP kernel families must agree with the oracle (and therefore with each other) on the same
+problems: smx_dp_forward16h (u16x2 diagonal frame, default), smx_dp_forward16 (s16x2, SMX_S16H=0 or scorings the
+diagonal frame cannot take) and smx_dp_forward (int32, SMX_S16=0).  Plus the ends of the packed kernel's value range
+(long, highly similar and completely dissimilar pairs) and its launch modes."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import util
+from tests.test_dp_parity import run_and_compare
+
+pytestmark = pytest.mark.gpu
+
+
+class _Env:
+    def __init__(self, **kv):
+        self.kv, self.old = kv, {}
+
+    def __enter__(self):
+        for k, v in self.kv.items():
+            self.old[k] = os.environ.get(k)
+            os.environ[k] = v
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _mixed_problems(seed, n=40, max_len=1400):
+    rng = np.random.default_rng(seed)
+    probs = util.make_problems(rng, n, max_len, related=0.75)
+    modes = rng.integers(0, 3, size=len(probs))
+    return probs, modes
+
+
+@pytest.mark.parametrize("env", [dict(SMX_S16H="0"), dict(SMX_S16="0"), dict(SMX_PERSISTENT="1"), dict(SMX_S16_MINROWS="256"),
+                                 dict(SMX_S16_MAXW="1"), dict(SMX_S16_MAXW="8"), dict(SMX_TEAM_MIN_MCELLS="1")])
+def test_kernel_families_and_launch_modes(engine, env):
+    probs, modes = _mixed_problems(61)
+    with _Env(**env):
+        run_and_compare(engine, probs, modes, (3, 1, 1, -2))
+        run_and_compare(engine, probs[:12], modes[:12], (5, 2, 2, -3))
+
+
+@pytest.mark.parametrize("scoring", [(1, 3, 1, -2),      # go < ge: the constant of the diagonal frame changes sign
+                                     (3, 1, 1, -5),      # mismatch + 2 ge < 0: falls back to the s16x2 kernel
+                                     (40, 20, 60, -30),  # match + go + ge = 120: profile bytes near their limit
+                                     (60, 30, 40, -50),  # 130 > 127: s16x2 kernel
+                                     (2, 1, 0, -1)])     # match 0
+def test_scorings_around_the_packed_kernel_conditions(engine, scoring):
+    probs, modes = _mixed_problems(62, n=24, max_len=900)
+    run_and_compare(engine, probs, modes, scoring)
+
+
+def test_value_range_ends(engine):
+    """12 000 x 13 000: scores near +12 000 (similar pair) and near -(go + 25 000 ge) along the borders (dissimilar pair);
+    with (5, 2, 2, -3) the biased diagonal-frame values pass 65 000 and the problem must leave the packed kernel."""
+    rng = np.random.default_rng(63)
+    ref = util.rand_seq(rng, 13000)
+    similar = util.mutate(rng, ref, 0.01, 0.005, 0.005)[:12000]
+    other = util.rand_seq(rng, 12000)
+    low = "AC" * 6000  # tie-heavy against itself shifted
+    probs = [(similar, ref), (other, ref), (similar, ref), (other, ref), (low, low[1:] + "A")]
+    modes = [0, 0, 1, 2, 0]
+    run_and_compare(engine, probs, modes, (3, 1, 1, -2))
+    run_and_compare(engine, probs[:2], modes[:2], (5, 2, 2, -3))
