@@ -99,6 +99,7 @@ struct smx_handle {
     DevBuf d_chain_tasks, d_chain_regions, d_chain_traces, d_chain_out, d_chain_scratch;
     std::vector<uint8_t> host_pool;
     PinBuf pin_regions, pin_cigar, pin_pool;
+    PinBuf pin_stage[16];  // page-locked staging of the small descriptor / result copies (PinSlot)
     struct SmxPipelineState *pipe = nullptr;
 };
 
@@ -146,6 +147,32 @@ static int ensure_pinned(smx_handle *h, PinBuf &b, size_t bytes)
     cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocDefault);
     if (e != cudaSuccess) { b.p = nullptr; return fail(h, -3, "cudaHostAlloc(%zu bytes) failed: %s", want, cudaGetErrorString(e)); }
     b.cap = want;
+    return 0;
+}
+
+// Every host<->device copy of the path goes through page-locked memory: a cudaMemcpyAsync on pageable memory is staged
+// by the driver under locks shared by all streams of the context, and with several handles in flight the small
+// descriptor / result copies of a batch's front end were measured to wait 30 ms and more behind the other handles'
+// work (the select phase took 41 ms of which the kernel 9 ms).
+enum PinSlot { PIN_PROBS, PIN_ORDER_CLS, PIN_ORDER_ALL, PIN_RESULTS, PIN_DENSE_OFF, PIN_SCAN_PAIRS, PIN_SCAN_TILES, PIN_SEL_PAIRS,
+               PIN_SEL_OUT, PIN_NREG, PIN_CHAIN_TASKS, PIN_CHAIN_REGS, PIN_CHAIN_OUT, PIN_CHAIN_TR };
+
+// host -> device through staging slot `slot`; the slot must not be reused before `stream` has been synchronised
+static int h2d(smx_handle *h, int slot, void *dst_dev, const void *src, size_t bytes, cudaStream_t stream)
+{
+    if (bytes == 0) return 0;
+    if (int rc = ensure_pinned(h, h->pin_stage[slot], bytes)) return rc;
+    memcpy(h->pin_stage[slot].p, src, bytes);
+    SMX_CUDA(h, cudaMemcpyAsync(dst_dev, h->pin_stage[slot].p, bytes, cudaMemcpyHostToDevice, stream));
+    return 0;
+}
+
+// device -> staging slot `slot` (asynchronous); read h->pin_stage[slot].p after synchronising `stream`
+static int d2h(smx_handle *h, int slot, const void *src_dev, size_t bytes, cudaStream_t stream)
+{
+    if (bytes == 0) return 0;
+    if (int rc = ensure_pinned(h, h->pin_stage[slot], bytes)) return rc;
+    SMX_CUDA(h, cudaMemcpyAsync(h->pin_stage[slot].p, src_dev, bytes, cudaMemcpyDeviceToHost, stream));
     return 0;
 }
 
@@ -240,6 +267,7 @@ extern "C" void smx_destroy(smx_handle *h)
                       &h->d_chain_out, &h->d_chain_scratch};
     smx_pipeline_free(h);
     for (PinBuf *b : {&h->pin_regions, &h->pin_cigar, &h->pin_pool}) if (b->p) cudaFreeHost(b->p);
+    for (PinBuf &b : h->pin_stage) if (b.p) cudaFreeHost(b.p);
     for (DevBuf *b : bufs) release(*b);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -495,9 +523,9 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
     if (int rc = ensure(h, h->d_runs, sizeof(uint32_t) * (size_t)h->runs_scratch)) return rc;
     if (int rc = ensure(h, h->d_dense_off, sizeof(int64_t) * ((size_t)n + 1))) return rc;
     if (int rc = ensure(h, h->d_tickets, sizeof(int32_t) * kNumFwdClasses * h->chunks.size())) return rc;
-    SMX_CUDA(h, cudaMemcpyAsync(h->d_probs.p, h->probs.data(), sizeof(SmxProblem) * (size_t)n, cudaMemcpyHostToDevice, h->stream_hi));
-    SMX_CUDA(h, cudaMemcpyAsync(h->d_order_cls.p, h->order_cls.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream_hi));
-    SMX_CUDA(h, cudaMemcpyAsync(h->d_order_all.p, h->order_all.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream_hi));
+    if (int rc = h2d(h, PIN_PROBS, h->d_probs.p, h->probs.data(), sizeof(SmxProblem) * (size_t)n, h->stream_hi)) return rc;
+    if (int rc = h2d(h, PIN_ORDER_CLS, h->d_order_cls.p, h->order_cls.data(), sizeof(int32_t) * (size_t)n, h->stream_hi)) return rc;
+    if (int rc = h2d(h, PIN_ORDER_ALL, h->d_order_all.p, h->order_all.data(), sizeof(int32_t) * (size_t)n, h->stream_hi)) return rc;
     SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
     h->n = n;
     return 0;
@@ -674,9 +702,10 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
     SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     // results header to host: run counts -> dense offsets -> compaction
     h->h_results.resize((size_t)h->n);
-    SMX_CUDA(h, cudaMemcpyAsync(h->h_results.data(), h->d_results.p, sizeof(SmxResult) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    if (int rc = d2h(h, PIN_RESULTS, h->d_results.p, sizeof(SmxResult) * (size_t)h->n, h->stream)) return rc;
     if (gate) { SMX_CUDA(h, cudaEventSynchronize(h->ev_fwd)); guard.release(); }
     SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    memcpy(h->h_results.data(), h->pin_stage[PIN_RESULTS].p, sizeof(SmxResult) * (size_t)h->n);
     SMX_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     h->h_dense_off.resize((size_t)h->n + 1);
     int64_t acc = 0;
@@ -684,7 +713,7 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
     h->h_dense_off[(size_t)h->n] = acc;
     h->total_runs = acc;
     if (int rc = ensure(h, h->d_dense, sizeof(uint32_t) * (size_t)std::max<int64_t>(acc, 1))) return rc;
-    SMX_CUDA(h, cudaMemcpyAsync(h->d_dense_off.p, h->h_dense_off.data(), sizeof(int64_t) * ((size_t)h->n + 1), cudaMemcpyHostToDevice, h->stream_hi));
+    if (int rc = h2d(h, PIN_DENSE_OFF, h->d_dense_off.p, h->h_dense_off.data(), sizeof(int64_t) * ((size_t)h->n + 1), h->stream_hi)) return rc;
     const int threads = 256, wpb = threads / 32;
     smx_compact_runs<<<(h->n + wpb - 1) / wpb, threads, 0, h->stream_hi>>>((const SmxProblem *)h->d_probs.p, (const SmxResult *)h->d_results.p,
                                                                         (const int64_t *)h->d_dense_off.p, (const uint32_t *)h->d_runs.p,
@@ -788,8 +817,8 @@ extern "C" int smx_scan_prepare(smx_handle *h, const int64_t *ref_off, const int
     if (int rc = ensure(h, h->d_scan_pairs, sizeof(SmxScanPair) * (size_t)n)) return rc;
     if (int rc = ensure(h, h->d_scan_tile_pair, sizeof(int32_t) * (size_t)tiles)) return rc;
     if (int rc = ensure(h, h->d_counts, sizeof(int32_t) * (size_t)total)) return rc;
-    SMX_CUDA(h, cudaMemcpyAsync(h->d_scan_pairs.p, pairs.data(), sizeof(SmxScanPair) * (size_t)n, cudaMemcpyHostToDevice, h->stream_hi));
-    SMX_CUDA(h, cudaMemcpyAsync(h->d_scan_tile_pair.p, tile_pair.data(), sizeof(int32_t) * (size_t)tiles, cudaMemcpyHostToDevice, h->stream_hi));
+    if (int rc = h2d(h, PIN_SCAN_PAIRS, h->d_scan_pairs.p, pairs.data(), sizeof(SmxScanPair) * (size_t)n, h->stream_hi)) return rc;
+    if (int rc = h2d(h, PIN_SCAN_TILES, h->d_scan_tile_pair.p, tile_pair.data(), sizeof(int32_t) * (size_t)tiles, h->stream_hi)) return rc;
     SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
     h->scan_n = n;
     return 0;
@@ -1051,7 +1080,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         if (int rc = ensure(h, h->d_regions, sizeof(SmxRegion) * (size_t)n * kRegionCap + 64)) return rc;
         int32_t *d_region_counter = (int32_t *)((char *)h->d_regions.p + sizeof(SmxRegion) * (size_t)n * kRegionCap);
         SMX_CUDA(h, cudaMemsetAsync(d_region_counter, 0, sizeof(int32_t), h->stream_hi));
-        SMX_CUDA(h, cudaMemcpyAsync(h->d_sel_pairs.p, sel_pairs.data(), sizeof(SmxSelPair) * (size_t)n, cudaMemcpyHostToDevice, h->stream_hi));
+        if (int rc = h2d(h, PIN_SEL_PAIRS, h->d_sel_pairs.p, sel_pairs.data(), sizeof(SmxSelPair) * (size_t)n, h->stream_hi)) return rc;
         SmxSelArgs sa;
         sa.pool = (const uint8_t *)h->pool.p; sa.pairs = (const SmxSelPair *)h->d_sel_pairs.p; sa.counts = (const int32_t *)h->d_counts.p;
         sa.regions = (SmxRegion *)h->d_regions.p; sa.out = (SmxSelOut *)h->d_sel_out.p; sa.region_counter = d_region_counter; sa.topology = topology;
@@ -1061,10 +1090,13 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         SMX_CUDA(h, cudaGetLastError());
         SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream_hi));
         st.launches += 1;
+        if (plog.on) { cudaEventSynchronize(h->ev1); plog.add(h, "selk", p_sel0, now_s()); }
         int32_t n_regions_total = 0;
-        SMX_CUDA(h, cudaMemcpyAsync(sel_out.data(), h->d_sel_out.p, sizeof(SmxSelOut) * (size_t)n, cudaMemcpyDeviceToHost, h->stream_hi));
-        SMX_CUDA(h, cudaMemcpyAsync(&n_regions_total, d_region_counter, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream_hi));
+        if (int rc = d2h(h, PIN_SEL_OUT, h->d_sel_out.p, sizeof(SmxSelOut) * (size_t)n, h->stream_hi)) return rc;
+        if (int rc = d2h(h, PIN_NREG, d_region_counter, sizeof(int32_t), h->stream_hi)) return rc;
         SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
+        memcpy(sel_out.data(), h->pin_stage[PIN_SEL_OUT].p, sizeof(SmxSelOut) * (size_t)n);
+        n_regions_total = *(const int32_t *)h->pin_stage[PIN_NREG].p;
         if (int rc = ensure_pinned(h, h->pin_regions, sizeof(SmxRegion) * (size_t)std::max(n_regions_total, 1))) return rc;
         SmxRegion *reg_host = (SmxRegion *)h->pin_regions.p;
         if (n_regions_total > 0) {
@@ -1150,8 +1182,8 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
             if (int rc = ensure(h, h->d_chain_out, sizeof(SmxChainOut) * tasks.size())) return rc;
             if (int rc = ensure(h, h->d_chain_scratch, sizeof(int32_t) * 3 * regs.size())) return rc;
             const double p_ch0 = now_s();
-            SMX_CUDA(h, cudaMemcpyAsync(h->d_chain_tasks.p, tasks.data(), sizeof(SmxChainTask) * tasks.size(), cudaMemcpyHostToDevice, h->stream_hi));
-            SMX_CUDA(h, cudaMemcpyAsync(h->d_chain_regions.p, regs.data(), sizeof(int4) * regs.size(), cudaMemcpyHostToDevice, h->stream_hi));
+            if (int rc = h2d(h, PIN_CHAIN_TASKS, h->d_chain_tasks.p, tasks.data(), sizeof(SmxChainTask) * tasks.size(), h->stream_hi)) return rc;
+            if (int rc = h2d(h, PIN_CHAIN_REGS, h->d_chain_regions.p, regs.data(), sizeof(int4) * regs.size(), h->stream_hi)) return rc;
             SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream_hi));
             for (int c = 0; c < 4; ++c) {
                 const int cnt = cls_first[c + 1] - cls_first[c];
@@ -1184,9 +1216,11 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
             SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream_hi));
             std::vector<SmxChainOut> couts(tasks.size());
             std::vector<int32_t> tr((size_t)std::max<int64_t>(trace_total, 1));
-            SMX_CUDA(h, cudaMemcpyAsync(couts.data(), h->d_chain_out.p, sizeof(SmxChainOut) * tasks.size(), cudaMemcpyDeviceToHost, h->stream_hi));
-            SMX_CUDA(h, cudaMemcpyAsync(tr.data(), h->d_chain_traces.p, sizeof(int32_t) * (size_t)std::max<int64_t>(trace_total, 1), cudaMemcpyDeviceToHost, h->stream_hi));
+            if (int rc = d2h(h, PIN_CHAIN_OUT, h->d_chain_out.p, sizeof(SmxChainOut) * tasks.size(), h->stream_hi)) return rc;
+            if (int rc = d2h(h, PIN_CHAIN_TR, h->d_chain_traces.p, sizeof(int32_t) * (size_t)std::max<int64_t>(trace_total, 1), h->stream_hi)) return rc;
             SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
+            memcpy(couts.data(), h->pin_stage[PIN_CHAIN_OUT].p, sizeof(SmxChainOut) * tasks.size());
+            memcpy(tr.data(), h->pin_stage[PIN_CHAIN_TR].p, sizeof(int32_t) * (size_t)std::max<int64_t>(trace_total, 1));
             { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1); st.gpu_chain_ms += ms; }
             plog.add(h, "chain", p_ch0, now_s());
             for (size_t k = 0; k < tasks.size(); ++k) {
