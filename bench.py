@@ -198,7 +198,7 @@ def run_engine(args, rank, world, local_rank):
     out_bytes = 0
     for _ in range(args.steps):
         res = step()
-        out_bytes = res.cigar_rle.nbytes + res.score.nbytes + res.new_query_seq_offset.nbytes + res.status.nbytes + res.cigar_off.nbytes
+        out_bytes = res.nbytes
         agg = dict(res.stats) if agg is None else {k: agg[k] + res.stats[k] for k in agg}
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0

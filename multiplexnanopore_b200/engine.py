@@ -197,20 +197,12 @@ class Engine:
         return {"viaddmax_gops": out[0], "vimax3_gops": out[1], "iadd_lop_gops": out[2]}
 
 
-@dataclass
-class PipelineResult:
-    """Output of the alignment stage for P pairs x 2 strands, index = 2 * pair + strand."""
-    score: np.ndarray                  # int32[2P]   MyResult.score (0 for empty results)
-    new_query_seq_offset: np.ndarray   # int32[2P]   INT32_MIN encodes None
-    status: np.ndarray                 # uint8[2P]   0 aligned, 1 empty MyResult(), 2 reference would raise
-    cigar_off: np.ndarray              # int64[2P+1]
-    cigar_rle: np.ndarray              # uint32[total]
-    stats: dict
-
+class _PipelineResultOps:
+    """accessors shared by the one-batch and the segmented result (both provide runs(i), score, new_query_seq_offset)"""
     _OPS = {1: "I", 2: "D", 4: "S", 5: "H", 7: "=", 8: "X"}
-
-    def runs(self, i: int) -> np.ndarray:
-        return self.cigar_rle[self.cigar_off[i]: self.cigar_off[i + 1]]
+    _LUT = np.zeros(16, dtype="S1")
+    for _k, _v in _OPS.items():
+        _LUT[_k] = _v.encode()
 
     def cigar_string(self, i: int) -> str:
         """RLE text as MyResult.cigar renders it (ref_query_alignment.py:449-451)."""
@@ -220,14 +212,63 @@ class PipelineResult:
         r = self.runs(i)
         if r.size == 0:
             return ""
-        lut = np.zeros(16, dtype="S1")
-        for k, v in self._OPS.items():
-            lut[k] = v.encode()
-        return np.repeat(lut[r & 15], r >> 4).tobytes().decode("ascii")
+        return np.repeat(self._LUT[r & 15], r >> 4).tobytes().decode("ascii")
 
     def offset(self, i: int):
         v = int(self.new_query_seq_offset[i])
         return None if v == -2147483648 else v
+
+
+@dataclass
+class PipelineResult(_PipelineResultOps):
+    """Output of the alignment stage for P pairs x 2 strands, index = 2 * pair + strand."""
+    score: np.ndarray                  # int32[2P]   MyResult.score (0 for empty results)
+    new_query_seq_offset: np.ndarray   # int32[2P]   INT32_MIN encodes None
+    status: np.ndarray                 # uint8[2P]   0 aligned, 1 empty MyResult(), 2 reference would raise
+    cigar_off: np.ndarray              # int64[2P+1]
+    cigar_rle: np.ndarray              # uint32[total]
+    stats: dict
+
+    def runs(self, i: int) -> np.ndarray:
+        return self.cigar_rle[self.cigar_off[i]: self.cigar_off[i + 1]]
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.score.nbytes + self.new_query_seq_offset.nbytes + self.status.nbytes + self.cigar_off.nbytes + self.cigar_rle.nbytes)
+
+
+class SegmentedPipelineResult(_PipelineResultOps):
+    """The batches of one align_all call, in order.  score / new_query_seq_offset / status / cigar_off are flat arrays
+    over all pair-strands; the CIGAR runs stay in their per-batch arrays (runs(i) slices the right one) and are only
+    concatenated if somebody asks for the flat `cigar_rle` (hundreds of MB for 20 000 reads)."""
+
+    def __init__(self, parts):
+        self.parts = list(parts)
+        self.score = np.concatenate([p.score for p in self.parts])
+        self.new_query_seq_offset = np.concatenate([p.new_query_seq_offset for p in self.parts])
+        self.status = np.concatenate([p.status for p in self.parts])
+        self._first = np.cumsum([0] + [len(p.score) for p in self.parts])          # first pair-strand of every batch
+        self._run_base = np.cumsum([0] + [int(p.cigar_off[-1]) for p in self.parts])  # first run of every batch
+        self.cigar_off = np.concatenate([self.parts[0].cigar_off] + [p.cigar_off[1:] + b for p, b in zip(self.parts[1:], self._run_base[1:])])
+        self.stats = {k: sum(p.stats[k] for p in self.parts) for k in self.parts[0].stats}
+        self._flat = None
+
+    def runs(self, i: int) -> np.ndarray:
+        k = int(np.searchsorted(self._first, i, side="right")) - 1
+        p = self.parts[k]
+        j = i - int(self._first[k])
+        return p.cigar_rle[p.cigar_off[j]: p.cigar_off[j + 1]]
+
+    @property
+    def cigar_rle(self) -> np.ndarray:
+        if self._flat is None:
+            self._flat = np.concatenate([p.cigar_rle for p in self.parts])
+        return self._flat
+
+    @property
+    def nbytes(self) -> int:
+        return int(self.score.nbytes + self.new_query_seq_offset.nbytes + self.status.nbytes + self.cigar_off.nbytes
+                   + sum(p.cigar_rle.nbytes for p in self.parts))
 
 
 _STAT_KEYS = ("t_total", "t_pool", "t_scan", "t_select", "t_chain", "t_dp", "t_stitch", "gpu_scan_ms", "gpu_select_ms",

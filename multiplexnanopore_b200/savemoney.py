@@ -89,18 +89,8 @@ def default_engine() -> Engine:
 
 
 def _merge(parts):
-    from .engine import PipelineResult
-    if len(parts) == 1:
-        return parts[0]
-    offs = [parts[0].cigar_off]
-    base = int(parts[0].cigar_off[-1])
-    for p in parts[1:]:
-        offs.append(p.cigar_off[1:] + base)
-        base += int(p.cigar_off[-1])
-    stats = {k: sum(p.stats[k] for p in parts) for k in parts[0].stats}
-    return PipelineResult(np.concatenate([p.score for p in parts]), np.concatenate([p.new_query_seq_offset for p in parts]),
-                          np.concatenate([p.status for p in parts]), np.concatenate(offs),
-                          np.concatenate([p.cigar_rle for p in parts]), stats)
+    from .engine import SegmentedPipelineResult
+    return parts[0] if len(parts) == 1 else SegmentedPipelineResult(parts)
 
 
 _engine_pools = {}
@@ -132,16 +122,14 @@ def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None,
     if pairs is not None or len(queries) <= batch_queries:
         return eng.pipeline_run(refs, queries, sig, *args, pairs=pairs, n_threads=n_threads)
     starts = list(range(0, len(queries), batch_queries))
-    # pack once: the batches below are zero-copy views (per-batch packing would run under the GIL of every worker)
-    from .engine import _pack, pack_slice
-    n_q = len(queries)
+    from .engine import _pack
     refs = _pack(refs)
-    queries = _pack(queries)
     if overlap <= 1:
-        parts = [eng.pipeline_run(refs, pack_slice(queries, b, min(b + batch_queries, n_q)), sig, *args, n_threads=n_threads) for b in starts]
+        parts = [eng.pipeline_run(refs, _pack(queries[b:b + batch_queries]), sig, *args, n_threads=n_threads) for b in starts]
         return _merge(parts)
-    from concurrent.futures import ThreadPoolExecutor
     import queue
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
     engines = _engines_for(eng, min(overlap, len(starts)))
     if n_threads <= 0:  # host stages need about three cores per GPU; every handle in flight runs its own pool
         import os
@@ -149,16 +137,33 @@ def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None,
     free = queue.SimpleQueue()
     for e in engines:
         free.put(e)
+    # the batches are packed (str -> bytes + offsets) by one producer thread while the first ones are already on the GPU
+    packed = [None] * len(starts)
+    ready = [threading.Event() for _ in starts]
 
-    def work(b):
+    def producer():
+        for k, b in enumerate(starts):
+            try:
+                packed[k] = _pack(queries[b:b + batch_queries])
+            except Exception as exc:  # surfaces in the worker that waits for this batch
+                packed[k] = exc
+            ready[k].set()
+
+    threading.Thread(target=producer, daemon=True).start()
+
+    def work(k):
+        ready[k].wait()
+        if isinstance(packed[k], Exception):
+            raise packed[k]
         e = free.get()
         try:
-            return e.pipeline_run(refs, pack_slice(queries, b, min(b + batch_queries, n_q)), sig, *args, n_threads=n_threads)
+            return e.pipeline_run(refs, packed[k], sig, *args, n_threads=n_threads)
         finally:
+            packed[k] = None
             free.put(e)
 
     with ThreadPoolExecutor(max_workers=len(engines)) as ex:
-        parts = list(ex.map(work, starts))
+        parts = list(ex.map(work, range(len(starts))))
     return _merge(parts)
 
 
