@@ -56,7 +56,8 @@ struct smx_handle {
     int64_t team_min_cells = 0;  // SMX_TEAM_MIN_MCELLS (in Mi cells): below it one warp per problem (measured: no gain on C2)
     bool persistent_fwd = false;  // SMX_PERSISTENT=1: launch smx_dp16h.cuh as a persistent grid (A/B switch)
     bool use_s16h = true;  // diagonal-frame u16x2 kernel (smx_dp16h.cuh) when the scoring allows it; SMX_S16H=0 keeps smx_dp16.cuh
-    int s16_max_wsel = 1;  // warps per problem of the s16 kernel are capped at 2 (measured best); SMX_S16_MAXW=1|2|4|8 overrides
+    int s16_max_wsel = 0;  // warps per problem of the packed kernels: 1 (measured best with several DP phases in flight, whose
+                           // launches fill each other's tails); SMX_S16_MAXW=2|4|8 turns the teams on (latency of few huge problems)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fwd = nullptr;
     float last_ms = 0.f;
     int last_launches = 0;
@@ -423,7 +424,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         const char *envh = getenv("SMX_S16H");
         h->use_s16h = !(envh && envh[0] == '0') && s16h_scoring_ok(h->sc);
         const char *mw = getenv("SMX_S16_MAXW");
-        h->s16_max_wsel = 1;
+        h->s16_max_wsel = 0;
         if (mw) { const int v = atoi(mw); h->s16_max_wsel = v >= 8 ? 3 : v >= 4 ? 2 : v >= 2 ? 1 : 0; }
     }
     h->nmax = 1;
@@ -542,7 +543,7 @@ struct DpGate {
     unsigned long long next_ticket = 0, serving = 0;
     int permits()
     {
-        static const int p = [] { const char *e = getenv("SMX_DP_INFLIGHT"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+        static const int p = [] { const char *e = getenv("SMX_DP_INFLIGHT"); const int v = e ? atoi(e) : 3; return v < 1 ? 1 : v; }();
         return p;
     }
     void enter()
