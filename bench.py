@@ -129,7 +129,7 @@ def run_reference(args, rank, world):
         return
     plasmids, reads, _ = workload(0, args.reads)
     cores = os.cpu_count() or 1
-    n_sample = args.cpu_reads or max(cores, 8)
+    n_sample = args.cpu_reads or max(4 * cores, 16)   # four reads per worker process: ~10 s of CPU work per step
     for _ in range(args.warmup):
         cpu_sample(plasmids, reads, min(2, n_sample), min(2, cores))
     vals, walls = [], []
@@ -272,7 +272,7 @@ def run_engine(args, rank, world, local_rank):
             pass
     cpu = None
     if world >= 1 and not args.no_cpu_baseline:
-        cpu = cpu_sample(plasmids, reads, args.cpu_reads or max(cores, 8), cores)
+        cpu = cpu_sample(plasmids, reads, args.cpu_reads or max(4 * cores, 16), cores)
     line = {
         "metric": "alignment-stage DP throughput (post_analysis, C2)", "value": cells_all / dev_s / 1e9, "unit": "GCUPS",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
@@ -311,7 +311,7 @@ def main():
     ap.add_argument("--reads", type=int, default=20000, help="reads per rank (C2 = 20000)")
     ap.add_argument("--batch", type=int, default=1000, help="reads per smx_pipeline_run call")
     ap.add_argument("--overlap", type=int, default=6, help="batches in flight per rank (engine handles)")
-    ap.add_argument("--cpu-reads", type=int, default=0, help="reads of the CPU sample (default: max(cores, 8))")
+    ap.add_argument("--cpu-reads", type=int, default=0, help="reads of the CPU sample (default: max(4 * cores, 16))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--threads", type=int, default=0, help="host threads per rank (default: cores / ranks)")
     args = ap.parse_args()
