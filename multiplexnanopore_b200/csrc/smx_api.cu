@@ -58,7 +58,7 @@ struct smx_handle {
     bool use_s16h = true;  // diagonal-frame u16x2 kernel (smx_dp16h.cuh) when the scoring allows it; SMX_S16H=0 keeps smx_dp16.cuh
     int s16_max_wsel = 0;  // warps per problem of the packed kernels: 1 (measured best with several DP phases in flight, whose
                            // launches fill each other's tails); SMX_S16_MAXW=2|4|8 turns the teams on (latency of few huge problems)
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fwd = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fwd = nullptr, ev_sync_lo = nullptr, ev_sync_hi = nullptr;
     float last_ms = 0.f;
     int last_launches = 0;
     // per-kernel timing of the last smx_align_run: [0..13] forward classes (problem_class), [14] traceback, [15] compaction
@@ -202,6 +202,18 @@ static int mark(smx_handle *h, int tag, cudaStream_t stream = nullptr)
     return 0;
 }
 
+// Host waits sleep instead of spinning: with several handles per GPU and one process per GPU a spinning
+// cudaStreamSynchronize per waiting thread eats the host cores the pipeline's own stages need (8 GPUs x 6 handles on 32
+// cores).  A blocking-sync event is recorded behind the work and waited for.
+static cudaError_t smx_sync(smx_handle *h, cudaStream_t stream)
+{
+    cudaEvent_t ev = stream == h->stream ? h->ev_sync_lo : h->ev_sync_hi;
+    if (!ev) return cudaStreamSynchronize(stream);
+    cudaError_t e = cudaEventRecord(ev, stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ev);
+}
+
 extern "C" int smx_version(void) { return 100; }
 
 extern "C" const char *smx_last_error(const smx_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -241,7 +253,9 @@ extern "C" int smx_create(smx_handle **out, int device_ordinal, void *stream)
     }
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
-    cudaEventCreateWithFlags(&h->ev_fwd, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_fwd, cudaEventDisableTiming | cudaEventBlockingSync);
+    cudaEventCreateWithFlags(&h->ev_sync_lo, cudaEventDisableTiming | cudaEventBlockingSync);
+    cudaEventCreateWithFlags(&h->ev_sync_hi, cudaEventDisableTiming | cudaEventBlockingSync);
     if (ensure(h, h->d_slots, sizeof(int32_t) * kLineSlots) != 0 || cudaMemset(h->d_slots.p, 0, sizeof(int32_t) * kLineSlots) != cudaSuccess) {
         g_create_error = "smx_create: cannot allocate the boundary-line slot table";
         smx_destroy(h);
@@ -274,6 +288,8 @@ extern "C" void smx_destroy(smx_handle *h)
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_fwd) cudaEventDestroy(h->ev_fwd);
+    if (h->ev_sync_lo) cudaEventDestroy(h->ev_sync_lo);
+    if (h->ev_sync_hi) cudaEventDestroy(h->ev_sync_hi);
     if (h->owns_stream) { cudaStreamDestroy(h->stream); cudaStreamDestroy(h->stream_hi); }
     delete h;
 }
@@ -303,7 +319,7 @@ extern "C" int smx_pool_upload(smx_handle *h, const uint8_t *seqs, int64_t n)
                                                                                  (uint8_t *)h->pool_special.p, n_words);
         SMX_CUDA(h, cudaGetLastError());
     }
-    SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
+    SMX_CUDA(h, smx_sync(h, h->stream_hi));
     h->pool_len = n;
     // per 64-byte block: does it hold a byte other than A/C/G/T?  prefix over blocks (s16 kernel eligibility)
     {
@@ -527,7 +543,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
     if (int rc = h2d(h, PIN_PROBS, h->d_probs.p, h->probs.data(), sizeof(SmxProblem) * (size_t)n, h->stream_hi)) return rc;
     if (int rc = h2d(h, PIN_ORDER_CLS, h->d_order_cls.p, h->order_cls.data(), sizeof(int32_t) * (size_t)n, h->stream_hi)) return rc;
     if (int rc = h2d(h, PIN_ORDER_ALL, h->d_order_all.p, h->order_all.data(), sizeof(int32_t) * (size_t)n, h->stream_hi)) return rc;
-    SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
+    SMX_CUDA(h, smx_sync(h, h->stream_hi));
     h->n = n;
     return 0;
 }
@@ -705,7 +721,7 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
     h->h_results.resize((size_t)h->n);
     if (int rc = d2h(h, PIN_RESULTS, h->d_results.p, sizeof(SmxResult) * (size_t)h->n, h->stream)) return rc;
     if (gate) { SMX_CUDA(h, cudaEventSynchronize(h->ev_fwd)); guard.release(); }
-    SMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    SMX_CUDA(h, smx_sync(h, h->stream));
     memcpy(h->h_results.data(), h->pin_stage[PIN_RESULTS].p, sizeof(SmxResult) * (size_t)h->n);
     SMX_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     h->h_dense_off.resize((size_t)h->n + 1);
@@ -722,7 +738,7 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
     if (int rc = mark(h, kSlotCompact, h->stream_hi)) return rc;
-    SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
+    SMX_CUDA(h, smx_sync(h, h->stream_hi));
     for (size_t i = 1; i < h->ev_used; ++i) {
         if (h->ev_tag[i] < 0) continue;
         float ms = 0.f;
@@ -751,7 +767,7 @@ extern "C" int smx_align_fetch(smx_handle *h, int32_t *score, int32_t *end_query
     if (cigar_rle && h->total_runs > 0) {
         SMX_CUDA(h, cudaSetDevice(h->device));
         SMX_CUDA(h, cudaMemcpyAsync(cigar_rle, h->d_dense.p, sizeof(uint32_t) * (size_t)h->total_runs, cudaMemcpyDeviceToHost, h->stream_hi));
-        SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
+        SMX_CUDA(h, smx_sync(h, h->stream_hi));
     }
     return 0;
 }
@@ -820,7 +836,7 @@ extern "C" int smx_scan_prepare(smx_handle *h, const int64_t *ref_off, const int
     if (int rc = ensure(h, h->d_counts, sizeof(int32_t) * (size_t)total)) return rc;
     if (int rc = h2d(h, PIN_SCAN_PAIRS, h->d_scan_pairs.p, pairs.data(), sizeof(SmxScanPair) * (size_t)n, h->stream_hi)) return rc;
     if (int rc = h2d(h, PIN_SCAN_TILES, h->d_scan_tile_pair.p, tile_pair.data(), sizeof(int32_t) * (size_t)tiles, h->stream_hi)) return rc;
-    SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
+    SMX_CUDA(h, smx_sync(h, h->stream_hi));
     h->scan_n = n;
     return 0;
 }
@@ -850,7 +866,7 @@ extern "C" int smx_scan_run(smx_handle *h)
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches = 1;
     SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream_hi));
-    SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
+    SMX_CUDA(h, smx_sync(h, h->stream_hi));
     SMX_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     return 0;
 }
@@ -862,7 +878,7 @@ extern "C" int smx_scan_fetch(smx_handle *h, int32_t *counts, int64_t counts_cap
     if (h->scan_n == 0) return 0;
     SMX_CUDA(h, cudaSetDevice(h->device));
     SMX_CUDA(h, cudaMemcpyAsync(counts, h->d_counts.p, sizeof(int32_t) * (size_t)h->scan_total, cudaMemcpyDeviceToHost, h->stream_hi));
-    SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
+    SMX_CUDA(h, smx_sync(h, h->stream_hi));
     return 0;
 }
 
@@ -911,7 +927,7 @@ extern "C" int smx_measure_int_peak(smx_handle *h, int32_t iters, double *out_go
             else smx_int_peak_kernel<2><<<blocks, threads, 0, h->stream_hi>>>((int *)h->d_tickets.p, iters, 12345 + rep);
             SMX_CUDA(h, cudaGetLastError());
             SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream_hi));
-            SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
+            SMX_CUDA(h, smx_sync(h, h->stream_hi));
             float ms = 0.f;
             SMX_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
             best = std::min(best, ms);
@@ -1095,14 +1111,14 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         int32_t n_regions_total = 0;
         if (int rc = d2h(h, PIN_SEL_OUT, h->d_sel_out.p, sizeof(SmxSelOut) * (size_t)n, h->stream_hi)) return rc;
         if (int rc = d2h(h, PIN_NREG, d_region_counter, sizeof(int32_t), h->stream_hi)) return rc;
-        SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
+        SMX_CUDA(h, smx_sync(h, h->stream_hi));
         memcpy(sel_out.data(), h->pin_stage[PIN_SEL_OUT].p, sizeof(SmxSelOut) * (size_t)n);
         n_regions_total = *(const int32_t *)h->pin_stage[PIN_NREG].p;
         if (int rc = ensure_pinned(h, h->pin_regions, sizeof(SmxRegion) * (size_t)std::max(n_regions_total, 1))) return rc;
         SmxRegion *reg_host = (SmxRegion *)h->pin_regions.p;
         if (n_regions_total > 0) {
             SMX_CUDA(h, cudaMemcpyAsync(reg_host, h->d_regions.p, sizeof(SmxRegion) * (size_t)n_regions_total, cudaMemcpyDeviceToHost, h->stream_hi));
-            SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
+            SMX_CUDA(h, smx_sync(h, h->stream_hi));
         }
         { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1); st.gpu_select_ms += ms; }
         plog.add(h, "select", p_sel0, now_s());
@@ -1219,7 +1235,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
             std::vector<int32_t> tr((size_t)std::max<int64_t>(trace_total, 1));
             if (int rc = d2h(h, PIN_CHAIN_OUT, h->d_chain_out.p, sizeof(SmxChainOut) * tasks.size(), h->stream_hi)) return rc;
             if (int rc = d2h(h, PIN_CHAIN_TR, h->d_chain_traces.p, sizeof(int32_t) * (size_t)std::max<int64_t>(trace_total, 1), h->stream_hi)) return rc;
-            SMX_CUDA(h, cudaStreamSynchronize(h->stream_hi));
+            SMX_CUDA(h, smx_sync(h, h->stream_hi));
             memcpy(couts.data(), h->pin_stage[PIN_CHAIN_OUT].p, sizeof(SmxChainOut) * tasks.size());
             memcpy(tr.data(), h->pin_stage[PIN_CHAIN_TR].p, sizeof(int32_t) * (size_t)std::max<int64_t>(trace_total, 1));
             { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev0, h->ev1); st.gpu_chain_ms += ms; }
