@@ -9,8 +9,12 @@ read x plasmid x strand) over the whole read set of the rank.  Metric = GCUPS: g
 per second, cells counted as the reference algorithm counts them (sum of len(s1) * len(s2) over every
 parasail call it would make) -- both arms count the same cells for the same reads.
 
-  value        device-resident throughput: cells / (CUDA-event time of the path's kernels)
-  e2e.value    through the C-ABI call with HOST buffers, host<->device copies and host stages inside
+  value        device-resident throughput: cells / (CUDA-event time of the path's kernels), measured in one extra
+               pass with the batches serialised (with several batches in flight the event intervals of one handle
+               contain the other handles' kernels); serialised launches cannot fill each other's tails, so value
+               can come out BELOW e2e
+  e2e.value    through the C-ABI call with HOST buffers (six 1000-read batches in flight), host<->device copies
+               and host stages inside
   ms_per_step  wall clock per step (the e2e path), max over ranks
 Multi-GPU: one process per GPU, every rank aligns its own 20k-read mixture (reads shard with no
 data-path collective) => weak scaling.
