@@ -1206,7 +1206,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
                 const int cnt = cls_first[c + 1] - cls_first[c];
                 if (cnt == 0) continue;
                 const int nmax = cls_n[c];
-                const size_t smem = sizeof(int) * (size_t)(4 * nmax + SMX_CHAIN_WARPS * (15 * nmax + nmax * (nmax / 32)));
+                const size_t smem = sizeof(int) * (size_t)(4 * nmax + SMX_CHAIN_WARPS * (17 * nmax + nmax * (nmax / 32)));
                 if (smem > 48 * 1024) SMX_CUDA(h, cudaFuncSetAttribute(smx_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 SmxChainArgs ca;
                 ca.tasks = (const SmxChainTask *)h->d_chain_tasks.p + cls_first[c];

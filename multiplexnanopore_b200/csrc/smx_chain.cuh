@@ -41,13 +41,14 @@ struct SmxChainArgs {
 
 struct SmxChainScratch {
     int *rs, *re, *qs, *qe, *keep;        // shifted rows that survive the removal, and their original index
-    int *op_r, *cl_r, *op_q, *cl_q;       // composite event keys
+    int4 *nodej;                          // per node j, packed for the adjacency loop: {open_r, open_q, rs (INT_MIN if j is ignored), qs}
+    int2 *close;                          // per node: {close_r, close_q}
     uint32_t *adj;                        // n x nw bit matrix
     int *score, *parent, *indeg, *list0, *list1, *trace;
     int nw;
 };
 
-__device__ __forceinline__ int smx_chain_scratch_ints(int nmax) { return 15 * nmax + nmax * (nmax / 32); }
+__device__ __forceinline__ int smx_chain_scratch_ints(int nmax) { return 17 * nmax + nmax * (nmax / 32); }
 
 // One search (search_longest_path) by one warp.  origin < 0: rows are used as they are (linear mode passes
 // rows already shifted).  Returns trace length (0 on failure) with the trace (original row indices) in
@@ -85,43 +86,46 @@ __device__ int smx_chain_search(const SmxChainScratch &sc, const int4 *R, int N,
     if (n_init != 1) return 0;  // assert at :878-879
     __syncwarp();
     const int nw = (n + 31) >> 5;
-    // ---- B: composite event keys ----
+    // ---- B: composite event keys, packed per node so that the adjacency loop reads one 16-byte word per candidate ----
     for (int c = lane; c < n; c += 32) {
         const int a0 = (10 * sc.rs[c] - 1) * 512 + 2 * c, b0 = (10 * sc.re[c]) * 512 + 2 * c + 1;
-        sc.op_r[c] = min(a0, b0); sc.cl_r[c] = max(a0, b0);
         const int a1 = (10 * sc.qs[c] - 1) * 512 + 2 * c, b1 = (10 * sc.qe[c]) * 512 + 2 * c + 1;
-        sc.op_q[c] = min(a1, b1); sc.cl_q[c] = max(a1, b1);
+        // a target j needs weight > 0 and a well-formed query interval (:891-894); INT_MIN makes `re_i < rs_j` fail
+        const bool usable = (sc.re[c] - sc.rs[c]) > 0 && (sc.qe[c] - sc.qs[c]) >= 0;
+        sc.nodej[c] = make_int4(min(a0, b0), min(a1, b1), usable ? sc.rs[c] : INT32_MIN, sc.qs[c]);
+        sc.close[c] = make_int2(max(a0, b0), max(a1, b1));
     }
     __syncwarp();
     // ---- C: adjacency = (1-D ref | 1-D query) & strictly-after-in-both & valid nodes (:882-894, :943-948) ----
     for (int i = lane; i < ((n + 31) & ~31); i += 32) {
         if (i < n) {
-            const int cr = sc.cl_r[i], cq = sc.cl_q[i];
+            const int2 ci = sc.close[i];
+            const int cr = ci.x, cq = ci.y;
             int fr = 0x7fffffff, fq = 0x7fffffff;
             for (int x = 0; x < n; ++x) {
-                const int a = sc.op_r[x], b = sc.op_q[x];
-                if (a > cr && a < fr) fr = a;
-                if (b > cq && b < fq) fq = b;
+                const int4 v = sc.nodej[x];
+                if (v.x > cr && v.x < fr) fr = v.x;
+                if (v.y > cq && v.y < fq) fq = v.y;
             }
             int kr = 0x7fffffff, kq = 0x7fffffff;
             for (int y = 0; y < n; ++y) {
-                const int a = sc.cl_r[y], b = sc.cl_q[y];
-                if (a > fr && a < kr) kr = a;
-                if (b > fq && b < kq) kq = b;
+                const int2 v = sc.close[y];
+                if (v.x > fr && v.x < kr) kr = v.x;
+                if (v.y > fq && v.y < kq) kq = v.y;
             }
             const int re_i = sc.re[i], qe_i = sc.qe[i];
             const bool ign_i = (re_i - sc.rs[i] < 0) || (qe_i - sc.qs[i] < 0);
+            // fr == INT_MAX leaves the window (cr, kr) empty for every real key, so no separate test is needed:
+            // kr stays INT_MAX only if no close key exceeds fr, and with fr == INT_MAX no open key exceeds cr
+            const bool any_r = fr != 0x7fffffff, any_q = fq != 0x7fffffff;
             for (int wd = 0; wd < nw; ++wd) {
                 uint32_t bits = 0;
                 if (!ign_i) {
                     const int jend = min(32, n - wd * 32);
                     for (int b = 0; b < jend; ++b) {
-                        const int j = wd * 32 + b;
-                        const int opr = sc.op_r[j], opq = sc.op_q[j];
-                        const bool one_d = (fr != 0x7fffffff && opr > cr && opr < kr) || (fq != 0x7fffffff && opq > cq && opq < kq);
-                        const int rs_j = sc.rs[j], qs_j = sc.qs[j];
-                        const int w_j = sc.re[j] - rs_j;
-                        const bool ok = one_d && re_i < rs_j && qe_i < qs_j && w_j > 0 && (sc.qe[j] - qs_j) >= 0;
+                        const int4 v = sc.nodej[wd * 32 + b];
+                        const bool one_d = (any_r && v.x > cr && v.x < kr) || (any_q && v.y > cq && v.y < kq);
+                        const bool ok = one_d && re_i < v.z && qe_i < v.w;
                         bits |= (ok ? 1u : 0u) << b;
                     }
                 }
@@ -219,7 +223,7 @@ __device__ int smx_chain_search(const SmxChainScratch &sc, const int4 *R, int N,
 
 __global__ void __launch_bounds__(SMX_CHAIN_WARPS * 32) smx_chain_kernel(const SmxChainArgs a)
 {
-    extern __shared__ int chain_smem[];
+    extern __shared__ __align__(16) int chain_smem[];
     const int task_id = blockIdx.x / a.n_slices, slice = blockIdx.x % a.n_slices;
     const SmxChainTask tk = a.tasks[task_id];
     const int N = tk.n, nmax = a.nmax;
@@ -228,8 +232,11 @@ __global__ void __launch_bounds__(SMX_CHAIN_WARPS * 32) smx_chain_kernel(const S
     int *wbase = chain_smem + 4 * nmax + warp * smx_chain_scratch_ints(nmax);
     SmxChainScratch sc;
     sc.rs = wbase; sc.re = sc.rs + nmax; sc.qs = sc.re + nmax; sc.qe = sc.qs + nmax; sc.keep = sc.qe + nmax;
-    sc.op_r = sc.keep + nmax; sc.cl_r = sc.op_r + nmax; sc.op_q = sc.cl_r + nmax; sc.cl_q = sc.op_q + nmax;
-    sc.score = sc.cl_q + nmax; sc.parent = sc.score + nmax; sc.indeg = sc.parent + nmax;
+    // nodej needs 16-byte alignment: wbase is (4 + warp * (17 + nmax / 32)) * nmax ints into a 16-byte aligned array and
+    // nmax is a multiple of 32, keep + nmax is therefore 16-byte aligned too
+    sc.nodej = reinterpret_cast<int4 *>(sc.keep + nmax);
+    sc.close = reinterpret_cast<int2 *>(sc.keep + 5 * nmax);
+    sc.score = sc.keep + 7 * nmax; sc.parent = sc.score + nmax; sc.indeg = sc.parent + nmax;
     sc.list0 = sc.indeg + nmax; sc.list1 = sc.list0 + nmax; sc.trace = sc.list1 + nmax;
     sc.adj = reinterpret_cast<uint32_t *>(sc.trace + nmax);
     sc.nw = nmax / 32;
