@@ -949,6 +949,9 @@ namespace {
 
 const int kRegionCap = SMX_SEL_REGION_CAP;   // device slots per pair-strand (overflow -> host re-decision)
 const int64_t kCountsBudget = 400ll << 20;  // int32 diagonal counts kept on the device per chunk
+// chain search: classes with fewer pair-strands than this many CTAs per SM spread the origins of a pair-strand over
+// several CTAs (a launch of few long CTAs is bound by its slowest CTA: 3.9 ms for 195 pair-strands of ~100 regions)
+const int kChainCtaTarget = []{ const char *e = getenv("SMX_CHAIN_CTAS"); const int v = e ? atoi(e) : 16; return v < 1 ? 1 : v; }();
 
 uint8_t g_comp[256];
 bool g_comp_ready = false;
@@ -1218,7 +1221,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
                 // few pair-strands with many regions: spread the origins of one pair-strand over several CTAs so
                 // that the launch fills the GPU, then pick across the slices in a second launch
                 int slices = 1;
-                if (topology == 0 && cnt < 2 * h->sm_count) slices = std::max(1, std::min(nmax / SMX_CHAIN_WARPS, (2 * h->sm_count + cnt - 1) / cnt));
+                if (topology == 0 && cnt < kChainCtaTarget * h->sm_count) slices = std::max(1, std::min(nmax / SMX_CHAIN_WARPS, (kChainCtaTarget * h->sm_count + cnt - 1) / cnt));
                 ca.n_slices = slices; ca.phase = 0;
                 smx_chain_kernel<<<cnt * slices, SMX_CHAIN_WARPS * 32, smem, h->stream_hi>>>(ca);
                 SMX_CUDA(h, cudaGetLastError());
