@@ -730,6 +730,7 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
     h->h_dense_off[(size_t)h->n] = acc;
     h->total_runs = acc;
     if (int rc = ensure(h, h->d_dense, sizeof(uint32_t) * (size_t)std::max<int64_t>(acc, 1))) return rc;
+    if (int rc = mark(h, -1, h->stream_hi)) return rc;  // the compaction interval starts here, not at the end of the traceback (host work lies between)
     if (int rc = h2d(h, PIN_DENSE_OFF, h->d_dense_off.p, h->h_dense_off.data(), sizeof(int64_t) * ((size_t)h->n + 1), h->stream_hi)) return rc;
     const int threads = 256, wpb = threads / 32;
     smx_compact_runs<<<(h->n + wpb - 1) / wpb, threads, 0, h->stream_hi>>>((const SmxProblem *)h->d_probs.p, (const SmxResult *)h->d_results.p,

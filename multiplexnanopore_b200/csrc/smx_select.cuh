@@ -41,6 +41,30 @@ struct SmxSelArgs {
     int32_t topology;
 };
 
+// first bin b of hist[0..256) with prefix(hist, b + 1) > rank, and the rank inside that bin; warp 0 scans 8 bins per lane
+__device__ __forceinline__ void smx_hist_find(const int *hist, int rank, int *out_bin, int *out_rank)
+{
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    int h[8], local = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) { h[b] = hist[lane * 8 + b]; local += h[b]; }
+    int incl = local;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(SMX_FULL_MASK, incl, off); if (lane >= off) incl += t; }
+    const int before = incl - local;  // counts in the bins of the lanes below
+    const unsigned owns = __ballot_sync(SMX_FULL_MASK, incl > rank);  // lanes whose inclusive prefix passes the rank
+    const int owner = owns ? __ffs(owns) - 1 : 31;
+    if (lane == owner) {
+        int acc = before, b = 0;
+#pragma unroll
+        for (; b < 8; ++b) { if (acc + h[b] > rank) break; acc += h[b]; }
+        if (b == 8) { b = 7; acc -= h[7]; }  // rank beyond the total (cannot happen for rank < count)
+        *out_bin = lane * 8 + b;
+        *out_rank = rank - acc;
+    }
+}
+
 // k-th smallest (0-based rank) of v[lo..hi) with values in [0, 65535]
 __device__ int smx_select_rank(const int32_t *v, int lo, int hi, int rank, int *hist /*256*/, int *bcast)
 {
@@ -49,11 +73,7 @@ __device__ int smx_select_rank(const int32_t *v, int lo, int hi, int rank, int *
     __syncthreads();
     for (int x = lo + tid; x < hi; x += SMX_SEL_THREADS) atomicAdd(&hist[(v[x] >> 8) & 255], 1);
     __syncthreads();
-    if (tid == 0) {
-        int acc = 0, b = 0;
-        for (; b < 256; ++b) { if (acc + hist[b] > rank) break; acc += hist[b]; }
-        bcast[0] = b; bcast[1] = rank - acc;
-    }
+    smx_hist_find(hist, rank, &bcast[0], &bcast[1]);
     __syncthreads();
     const int hb = bcast[0], r2 = bcast[1];
     __syncthreads();
@@ -61,13 +81,9 @@ __device__ int smx_select_rank(const int32_t *v, int lo, int hi, int rank, int *
     __syncthreads();
     for (int x = lo + tid; x < hi; x += SMX_SEL_THREADS) { const int c = v[x]; if (((c >> 8) & 255) == hb) atomicAdd(&hist[c & 255], 1); }
     __syncthreads();
-    if (tid == 0) {
-        int acc = 0, b = 0;
-        for (; b < 256; ++b) { if (acc + hist[b] > r2) break; acc += hist[b]; }
-        bcast[2] = (hb << 8) | b;
-    }
+    smx_hist_find(hist, r2, &bcast[2], &bcast[3]);
     __syncthreads();
-    const int res = bcast[2];
+    const int res = (hb << 8) | bcast[2];
     __syncthreads();
     return res;
 }
