@@ -311,3 +311,66 @@ class QueryAssignment:
         path = Path(save_dir) / f"{combined_name_stem}.summary_scores.csv"
         df.to_csv(path, sep="\t", index=False, na_rep="NaN")
         return path
+
+
+class DenseResult:
+    """Result of one legacy dense alignment (the fields the legacy MyResult reads off parasail's Result:
+    Modules/1_alignment_consensus_core.py:297-330): score, cigar (RLE text), beg/end on query and reference."""
+    __slots__ = ("score", "cigar", "beg_query", "beg_ref", "end_query", "end_ref")
+
+    def __init__(self, score, cigar, beg_query, beg_ref, end_query, end_ref):
+        self.score, self.cigar = score, cigar
+        self.beg_query, self.beg_ref, self.end_query, self.end_ref = beg_query, beg_ref, end_query, end_ref
+
+
+def legacy_dense_align(ref_seq_list, my_fastq, param_dict, engine=None, batch_cells=int(2e10)):
+    """Row N4, the pre-0.2 alignment mode kept in the reference under Modules/ (MyAligner.align_all /
+    MyAlignerLinear.align_all, Modules/1_alignment_consensus_core.py:219-296): one local alignment
+    `parasail.sw_trace(read, reference + reference)` (circular; `reference` alone for linear topology) per read,
+    plasmid and strand, no seeding.  Returns {query_id: [DenseResult(ref0), DenseResult(ref0, rc), DenseResult(ref1), ...]}.
+    Runs on the int32 local-alignment kernels through `Engine.align_batch` (mode 3), `batch_cells` DP cells per call."""
+    from .engine import MODE_SW
+    _check_params(param_dict)
+    eng = engine or default_engine()
+    circular = param_dict["topology_of_dna"] == 0
+    refs = [_seq_of(r) for r in ref_seq_list]
+    targets = [r + r if circular else r for r in refs]
+    ids = list(my_fastq.keys())
+    comp = str.maketrans("ACGTMRWSYKVHDBN", "TGCAKYWSRMBDHVN")
+    out = {}
+    go, ge = param_dict["gap_open_penalty"], param_dict["gap_extend_penalty"]
+    ma, mi = param_dict["match_score"], param_dict["mismatch_score"]
+    pos = 0
+    while pos < len(ids):
+        # reads of this call: as many as fit the cell budget (at least one)
+        end, cells = pos, 0
+        while end < len(ids):
+            c = 2 * len(_seq_of(my_fastq[ids[end]][0])) * sum(len(t) for t in targets)
+            if end > pos and cells + c > batch_cells:
+                break
+            cells += c
+            end += 1
+        seqs = list(targets)
+        for qid in ids[pos:end]:
+            q = _seq_of(my_fastq[qid][0])
+            seqs += [q, q.translate(comp)[::-1]]
+        offs, lens = eng.upload_sequences(seqs)
+        nt = len(targets)
+        s1, s2 = [], []
+        for k in range(end - pos):
+            for t in range(nt):
+                for strand in range(2):
+                    s1.append(nt + 2 * k + strand)
+                    s2.append(t)
+        s1 = np.array(s1); s2 = np.array(s2)
+        res = eng.align_batch(offs[s1], lens[s1], offs[s2], lens[s2], np.full(len(s1), MODE_SW, np.uint8), go, ge, ma, mi)
+        p = 0
+        for qid in ids[pos:end]:
+            row = []
+            for _ in range(2 * nt):
+                row.append(DenseResult(int(res.score[p]), res.cigar_string(p), int(res.beg_query[p]), int(res.beg_ref[p]),
+                                       int(res.end_query[p]), int(res.end_ref[p])))
+                p += 1
+            out[qid] = row
+        pos = end
+    return out
