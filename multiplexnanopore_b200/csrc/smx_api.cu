@@ -1054,6 +1054,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     }
 
     // ---- A3 + A4 on the device, chunked by the counts budget ----
+    const bool force_host_select = [] { const char *e = getenv("SMX_SELECT"); return e && std::string(e) == "host"; }();  // cross-check switch
     std::vector<int> active;
     for (size_t i = 0; i < st.ps.size(); ++i) if (!st.ps[i].skip) active.push_back((int)i);
     size_t pos = 0;
@@ -1131,7 +1132,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
             const SmxSelOut &o = sel_out[i];
             const SmxRegion *rg = &reg_host[(size_t)o.region_base];
             int nreg = o.n_regions;
-            if (o.flags) {  // ambiguous threshold or overflow: decide on the host from this pair-strand's counts
+            if (o.flags || force_host_select) {  // ambiguous threshold or overflow (or SMX_SELECT=host): decide on the host from this pair-strand's counts
                 const SmxSelPair &s = sel_pairs[i];
                 counts_host.resize((size_t)s.max_k);
                 SMX_CUDA(h, cudaMemcpy(counts_host.data(), (const int32_t *)h->d_counts.p + s.counts_off, sizeof(int32_t) * (size_t)s.max_k, cudaMemcpyDeviceToHost));

@@ -135,3 +135,22 @@ def test_device_chain_equals_host_chain(engine, topology, monkeypatch):
     assert np.array_equal(dev.score, host.score)
     assert np.array_equal(dev.new_query_seq_offset, host.new_query_seq_offset)
     assert np.array_equal(dev.cigar_off, host.cigar_off) and np.array_equal(dev.cigar_rle, host.cigar_rle)
+
+
+@pytest.mark.parametrize("topology", [0, 1])
+def test_device_select_equals_host_redecision(engine, topology, monkeypatch):
+    """Row A4 has two implementations as well: the select kernel and the host re-decision that takes over when a
+    threshold lies within 1e-6 of an integer or a pair-strand overflows the device slots (forced for every
+    pair-strand by SMX_SELECT=host: numpy's exact summation order); every output must be identical."""
+    rng = np.random.default_rng(97 + topology)
+    plasmids = synth.plasmid_set(rng, 4, 1500, 4000, backbone=800)
+    reads, _ = synth.reads_for(rng, plasmids, 60, topology=topology)
+    params = dict(PARAMS, topology_of_dna=topology)
+    monkeypatch.delenv("SMX_SELECT", raising=False)
+    dev = sm.align_all(plasmids, reads, params, True, engine=engine)
+    monkeypatch.setenv("SMX_SELECT", "host")
+    host = sm.align_all(plasmids, reads, params, True, engine=engine)
+    assert host.stats["n_host_redecisions"] > 0 and dev.stats["n_host_redecisions"] == 0
+    assert np.array_equal(dev.score, host.score) and np.array_equal(dev.status, host.status)
+    assert np.array_equal(dev.new_query_seq_offset, host.new_query_seq_offset)
+    assert np.array_equal(dev.cigar_off, host.cigar_off) and np.array_equal(dev.cigar_rle, host.cigar_rle)
