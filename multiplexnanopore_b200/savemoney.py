@@ -176,6 +176,9 @@ def _raise_failed(res):
 def execute_alignment_core(ref_seq_list, my_fastq, param_dict, engine=None):
     """result_dict[query_id] = [MyResult] * (2 * N_ref), order [ref0, ref0_rc, ref1, ...] (:63-65, :85)."""
     ids = list(my_fastq.keys())
+    if not ids:
+        _check_params(param_dict)
+        return {}  # an empty FASTQ maps to an empty result_dict (the reference's pool.map over no reads)
     reads = [my_fastq[i][0] for i in ids]
     res = align_all(ref_seq_list, reads, param_dict, omit_too_long=True, engine=engine,
                     n_threads=0)

@@ -1,0 +1,64 @@
+"""Edge inputs through the reference-facing API (execute_alignment_core, calc_distance) against the oracle port:
+empty FASTQ, one read, reads too short for any conserved region, all-N reads, lower-case input, reads longer than
+1.75 references (omit_too_long), a read batch boundary (1001 reads -> two batches in flight)."""
+import numpy as np
+import pytest
+
+from multiplexnanopore_b200 import savemoney as sm
+from multiplexnanopore_b200 import synth
+from oracle import oracle as orc
+from oracle import savemoney_port as port
+
+pytestmark = pytest.mark.gpu
+PARAMS = dict(gap_open_penalty=3, gap_extend_penalty=1, match_score=1, mismatch_score=-2, topology_of_dna=0)
+
+
+def _want(plasmids, read, params, omit=True):
+    return [[orc.rle(r.my_cigar), int(r.score), None if r.new_query_seq_offset is None else int(r.new_query_seq_offset)]
+            for r in port.align_read([p.upper() for p in plasmids], read.upper(), params, omit)]
+
+
+def test_edge_reads(engine):
+    rng = np.random.default_rng(81)
+    plasmids = synth.plasmid_set(rng, 3, 900, 1600, backbone=400)
+    good, _ = synth.reads_for(rng, plasmids, 2, topology=0)
+    reads = {
+        "one_base": "A", "too_short": plasmids[0][100:118], "just_21": plasmids[1][200:221], "all_n": "N" * 300,
+        "lower": good[0].lower(), "long": (good[1] * 3)[: int(len(plasmids[0]) * 2.2)], "good": good[1],
+        "poly_a": "A" * 500,
+    }
+    fastq = {k: [v, [20] * len(v)] for k, v in reads.items()}
+    assert sm.execute_alignment_core(plasmids, {}, PARAMS, engine=engine) == {}
+    rd = sm.execute_alignment_core([p.lower() for p in plasmids], fastq, PARAMS, engine=engine)
+    assert list(rd) == list(reads)
+    for qid, read in reads.items():
+        got = [[r.cigar, r.score, r.new_query_seq_offset] for r in rd[qid]]
+        assert got == _want(plasmids, read, PARAMS), qid
+    assert all(r.my_cigar == "" and r.score == 0 and r.new_query_seq_offset is None for r in rd["one_base"])
+    one = sm.execute_alignment_core(plasmids, {"good": fastq["good"]}, PARAMS, engine=engine)
+    assert [[r.cigar, r.score, r.new_query_seq_offset] for r in one["good"]] == _want(plasmids, reads["good"], PARAMS)
+
+
+def test_batch_boundary_and_order(engine):
+    """1001 short reads: two batches (1000 + 1) in flight; results must come back in read order."""
+    rng = np.random.default_rng(82)
+    plasmids = synth.plasmid_set(rng, 2, 300, 420, backbone=120)
+    reads, _ = synth.reads_for(rng, plasmids, 1001, topology=0, frac_full=0.3, frac_partial=0.6)
+    res = sm.align_all(plasmids, reads, PARAMS, True, engine=engine)
+    n2 = 2 * len(plasmids)
+    assert len(res.score) == 1001 * n2 and int(res.stats["n_pair_strands"]) == 1001 * n2
+    for qi in list(range(0, 1001, 97)) + [999, 1000]:
+        want = _want(plasmids, reads[qi], PARAMS)
+        got = [[res.cigar_string(qi * n2 + j), int(res.score[qi * n2 + j]), res.offset(qi * n2 + j)] for j in range(n2)]
+        assert got == want, qi
+
+
+def test_calc_distance_edges(engine):
+    rng = np.random.default_rng(83)
+    a = synth.random_bases(rng, 700).tobytes().decode()
+    b = synth.random_bases(rng, 650).tobytes().decode()
+    params = dict(PARAMS)
+    assert sm.calc_distance(a, a, params, engine=engine) == 0
+    assert sm.calc_distance(a, synth.revcomp_bytes(np.frombuffer(a.encode(), np.uint8)).tobytes().decode(), params, engine=engine) == 0
+    assert sm.calc_distance(a, b, params, engine=engine) == port.distance(a, b, params)
+    assert sm.set_distance_matrix([a], params, engine=engine).tolist() == [[0]]
