@@ -121,16 +121,17 @@ def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None,
             param_dict["mismatch_score"], param_dict["topology_of_dna"], omit_too_long)
     if pairs is not None or len(queries) <= batch_queries:
         return eng.pipeline_run(refs, queries, sig, *args, pairs=pairs, n_threads=n_threads)
-    starts = list(range(0, len(queries), batch_queries))
     from .engine import _pack
     refs = _pack(refs)
     if overlap <= 1:
+        starts = list(range(0, len(queries), batch_queries))
         parts = [eng.pipeline_run(refs, _pack(queries[b:b + batch_queries]), sig, *args, n_threads=n_threads) for b in starts]
         return _merge(parts)
+    bounds = _batch_bounds(len(queries), batch_queries, overlap)
     import queue
     import threading
     from concurrent.futures import ThreadPoolExecutor
-    engines = _engines_for(eng, min(overlap, len(starts)))
+    engines = _engines_for(eng, min(overlap, len(bounds) - 1))
     if n_threads <= 0:  # host stages need about three cores per GPU; every handle in flight runs its own pool
         import os
         n_threads = max(1, min(4, (os.cpu_count() or 4) // len(engines)))
@@ -138,13 +139,14 @@ def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None,
     for e in engines:
         free.put(e)
     # the batches are packed (str -> bytes + offsets) by one producer thread while the first ones are already on the GPU
-    packed = [None] * len(starts)
-    ready = [threading.Event() for _ in starts]
+    n_batches = len(bounds) - 1
+    packed = [None] * n_batches
+    ready = [threading.Event() for _ in range(n_batches)]
 
     def producer():
-        for k, b in enumerate(starts):
+        for k in range(n_batches):
             try:
-                packed[k] = _pack(queries[b:b + batch_queries])
+                packed[k] = _pack(queries[bounds[k]:bounds[k + 1]])
             except Exception as exc:  # surfaces in the worker that waits for this batch
                 packed[k] = exc
             ready[k].set()
@@ -163,8 +165,30 @@ def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None,
             free.put(e)
 
     with ThreadPoolExecutor(max_workers=len(engines)) as ex:
-        parts = list(ex.map(work, range(len(starts))))
+        parts = list(ex.map(work, range(n_batches)))
     return _merge(parts)
+
+
+def _batch_bounds(n, batch, overlap):
+    """Batch boundaries for `n` queries.  With several batches in flight the first and the last batches are smaller
+    (a quarter, then half a batch): the first forward-DP launch starts sooner and the last handles drain together
+    instead of one full batch after the other."""
+    import os
+    head = [batch // 4] * min(overlap // 2, 3) + [batch // 2] * min(overlap // 2, 3)
+    tail = head[::-1]
+    if n < sum(head) + sum(tail) + batch or min(head, default=0) < 1 or os.environ.get("SMX_RAMP", "1") == "0":
+        return list(range(0, n, batch)) + [n]
+    bounds, pos = [0], 0
+    for sz in head:
+        pos += sz; bounds.append(pos)
+    end_tail = n - sum(tail)
+    while pos + batch <= end_tail:
+        pos += batch; bounds.append(pos)
+    if pos < end_tail:
+        pos = end_tail; bounds.append(pos)
+    for sz in tail:
+        pos += sz; bounds.append(pos)
+    return bounds
 
 
 def _raise_failed(res):
