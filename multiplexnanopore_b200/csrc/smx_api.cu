@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <condition_variable>
 #include <mutex>
 #include <new>
@@ -971,8 +972,26 @@ void init_comp()
 static SmxPipelineState *pipeline_state(smx_handle *h);
 
 // SMX_PHASE_LOG=1: one stderr line per GPU phase of a pipeline call ("PH handle label t0 t1", steady-clock seconds)
+static double cpu_now_s()
+{
+    timespec ts;
+    clock_gettime(CLOCK_PROCESS_CPUTIME_ID, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 struct PhaseLog {
     bool on = getenv("SMX_PHASE_LOG") != nullptr;
+    double cpu_last = cpu_now_s();
+    // process CPU seconds since the previous stage boundary (meaningful with one batch in flight)
+    void cpu(const void *h, const char *label)
+    {
+        if (!on) return;
+        const double c = cpu_now_s();
+        char buf[160];
+        snprintf(buf, sizeof buf, "CPU %p %s %.6f\n", h, label, c - cpu_last);
+        lines.emplace_back(buf);
+        cpu_last = c;
+    }
     std::vector<std::string> lines;
     void add(const void *h, const char *label, double t0, double t1)
     {
@@ -1034,6 +1053,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         if (int rc = smx_pool_upload(h, pool, total)) return rc;  // the pinned copy stays for the rare host re-decisions
     }
     st.t_pool = now_s() - t_begin;
+    plog.cpu(h, "pool");
 
     // ---- pair-strand table ----
     const int64_t np_ = pair_ref ? n_pairs : (int64_t)n_qrys * n_refs;
@@ -1084,6 +1104,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         { const double p0 = now_s(); if (int rc = smx_scan_run(h)) return rc; plog.add(h, "scan", p0, now_s()); }
         st.gpu_scan_ms += h->last_ms; st.scan_cells += h->scan_cells; st.launches += 1;
         st.t_scan += now_s() - t0;
+        plog.cpu(h, "scan");
         t0 = now_s();
         sel_pairs.resize(n); sel_out.resize(n);
         for (int i = 0; i < n; ++i) {
@@ -1159,6 +1180,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
             }
         }
         st.t_select += now_s() - t0;
+        plog.cpu(h, "select");
         pos = end;
     }
 
@@ -1351,6 +1373,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     }
     local.clear();
     st.t_chain = now_s() - t0;
+    plog.cpu(h, "chain_plan");
 
     // ---- A8 on the device ----
     t0 = now_s();
@@ -1375,6 +1398,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         { const double p0 = now_s(); if (int rc = smx_align_fetch(h, nullptr, nullptr, nullptr, nullptr, nullptr, cg_off.data(), cg, std::max<int64_t>(truns, 1))) return rc; plog.add(h, "fetch", p0, now_s()); }
     }
     st.t_dp = now_s() - t0;
+    plog.cpu(h, "dp");
     plog.add(h, "call", t_begin, now_s());
 
     // ---- A9-A11 on host threads (run-length domain; re-clipping already happened in the traceback kernel) ----
@@ -1423,6 +1447,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     });
     st.n_failed += n_bad.load();
     st.t_stitch = now_s() - t0;
+    plog.cpu(h, "stitch");
 
     st.out_off.assign(st.ps.size() + 1, 0);
     for (size_t i = 0; i < st.ps.size(); ++i) st.out_off[i + 1] = st.out_off[i] + (int64_t)st.ps[i].runs.size();

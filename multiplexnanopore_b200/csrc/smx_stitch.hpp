@@ -100,44 +100,52 @@ inline void finish_qb_db(SgResult &r, const Scoring &sc)
     r.cig.assign(rev.rbegin(), rev.rend());
 }
 
-// generate_msa reduced to my_cigar_list_aligned for two rows
+// generate_msa reduced to my_cigar_list_aligned for two rows.  Each row is read as `c + "Z" + c.back()` (the sentinel
+// of generate_msa and the letter Python's index -1 wraps to) without building that string; the outputs are written
+// into pre-sized buffers (this runs once per matched pair-strand over ~10 k columns and was half of the host CPU time).
 inline bool aligned_columns(const std::string &c1, const std::string &c2, size_t n_ref, size_t nq1, size_t nq2,
                             std::string &a1, std::string &a2)
 {
     if (c1.empty() || c2.empty()) return false;
-    const std::string cg[2] = {c1 + "Z" + c1.back(), c2 + "Z" + c2.back()};
+    const std::string *c[2] = {&c1, &c2};
+    const size_t len[2] = {c1.size(), c2.size()};
+    auto at = [&](int i, size_t x) -> char { return x < len[i] ? (*c[i])[x] : (x == len[i] ? 'Z' : c[i]->back()); };
     const size_t nq[2] = {nq1, nq2};
-    size_t ci[2] = {0, 0}, qi[2] = {0, 0}, ri = 0;
-    std::string *out[2] = {&a1, &a2};
-    a1.clear(); a2.clear();
+    size_t ci[2] = {0, 0}, qi[2] = {0, 0}, ri = 0, w = 0;
+    const size_t cap = c1.size() + c2.size() + 2;  // every output column consumes a letter of at least one row
+    a1.resize(cap); a2.resize(cap);
+    char *out[2] = {&a1[0], &a2[0]};
     auto filler = [&](int i) -> char {
-        const std::string &c = cg[i];
         const size_t x = ci[i];
-        const char before = x == 0 ? c.back() : c[x - 1];  // Python index -1 wraps to the appended last letter
-        return (c[x] == 'H' || before == 'H' || (c[x] == 'Z' && c[0] == 'H')) ? 'O' : 'N';
+        const char cur = at(i, x);
+        const char before = x == 0 ? c[i]->back() : at(i, x - 1);  // Python index -1 wraps to the appended last letter
+        return (cur == 'H' || before == 'H' || (cur == 'Z' && (*c[i])[0] == 'H')) ? 'O' : 'N';
     };
     for (;;) {
-        const char col[2] = {cg[0][ci[0]], cg[1][ci[1]]};
+        const char col[2] = {at(0, ci[0]), at(1, ci[1])};
         const bool has_i = col[0] == 'I' || col[1] == 'I', has_s = col[0] == 'S' || col[1] == 'S';
+        if (w >= cap) return false;
         if (!has_i && !has_s) {
             if (ri == n_ref) {  // the sentinel 'Z' of the reference
                 if (!(col[0] == 'Z' && col[1] == 'Z' && qi[0] == nq[0] && qi[1] == nq[1])) return false;
+                a1.resize(w); a2.resize(w);
                 return true;
             }
             for (int i = 0; i < 2; ++i) {
                 const char L = col[i];
                 if (L == '=' || L == 'X') ++qi[i];
                 else if (L != 'D' && L != 'H') return false;
-                out[i]->push_back(L);
+                out[i][w] = L;
                 ++ci[i];
             }
-            ++ri;
+            ++ri; ++w;
         } else {
             const char want = has_s ? 'S' : 'I';
             for (int i = 0; i < 2; ++i) {
-                if (col[i] == want) { out[i]->push_back(want); ++ci[i]; ++qi[i]; }
-                else out[i]->push_back(filler(i));
+                if (col[i] == want) { out[i][w] = want; ++ci[i]; ++qi[i]; }
+                else out[i][w] = filler(i);
             }
+            ++w;
         }
     }
 }
@@ -170,23 +178,40 @@ inline bool merge_special(const SgResult &r1, const SgResult &r2, size_t n_ref, 
         out.append(r2.cig, h2, std::string::npos);
         return true;
     }
-    std::string a1, a2;
+    thread_local std::string a1, a2;
+    thread_local std::vector<int32_t> left, right;
     if (!aligned_columns(r1.cig, r2.cig, n_ref, nq1, nq2, a1, a2)) return false;
-    std::vector<int64_t> left, right;
-    prefix_scores(a1, sc, left);
-    std::string a2r(a2.rbegin(), a2.rend());
-    prefix_scores(a2r, sc, right);  // right[x] = score of the last x columns of a2
     const size_t L = a1.size();
     if (a2.size() != L) return false;
+    // left[x] = score of the first x columns of row 1; right[x] = score of the LAST x columns of row 2 read from the
+    // end (cumsum_my_cigar_scores on the reversed string: a gap run is charged its open at the column nearest the end)
+    left.resize(L + 1); right.resize(L + 1);
+    {
+        int32_t acc = 0; char prev = 0;
+        left[0] = 0;
+        for (size_t i = 0; i < L; ++i) {
+            const char c = a1[i];
+            if (c == '=') acc += sc.ma; else if (c == 'X') acc += sc.mi; else if (c == 'D' || c == 'I') acc -= (prev == c) ? sc.ge : sc.go;
+            left[i + 1] = acc; prev = c;
+        }
+        acc = 0; prev = 0;
+        right[0] = 0;
+        for (size_t i = 0; i < L; ++i) {
+            const char c = a2[L - 1 - i];
+            if (c == '=') acc += sc.ma; else if (c == 'X') acc += sc.mi; else if (c == 'D' || c == 'I') acc -= (prev == c) ? sc.ge : sc.go;
+            right[i + 1] = acc; prev = c;
+        }
+    }
     size_t cut = 0;
     int64_t best = 0;
     for (size_t x = 0; x <= L; ++x) {
-        const int64_t v = left[x] + right[L - x];
+        const int64_t v = (int64_t)left[x] + right[L - x];
         if (x == 0 || v > best) { best = v; cut = x; }
     }
     const int64_t n_s1 = (int64_t)(L - cut) - count_of(a1, cut, L, "DNHO");
     const int64_t n_s2 = (int64_t)cut - count_of(a2, 0, cut, "DNHO");
     out.clear();
+    out.reserve(L + (size_t)(n_s1 + n_s2));
     for (size_t x = 0; x < cut; ++x) if (a1[x] != 'N' && a1[x] != 'O') out.push_back(a1[x]);
     out.append((size_t)(n_s1 + n_s2), 'S');
     for (size_t x = cut; x < L; ++x) if (a2[x] != 'N' && a2[x] != 'O') out.push_back(a2[x]);
