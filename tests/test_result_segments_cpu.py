@@ -29,3 +29,15 @@ def test_segmented_result_equals_flat_concatenation():
     assert seg.nbytes == flat.nbytes
     assert np.array_equal(seg.cigar_rle, flat.cigar_rle)   # lazily concatenated
     assert seg.stats["dp_cells"] == 100.0 and seg.stats["t_total"] == 4.0
+
+
+def test_batch_bounds_cover_all_queries_in_order():
+    """savemoney._batch_bounds: ramped batch sizes must partition [0, n) whatever n, batch size and overlap are."""
+    from multiplexnanopore_b200.savemoney import _batch_bounds
+    for n in (1, 2, 999, 1000, 1001, 3999, 4000, 4001, 5499, 5500, 5501, 20000, 123457):
+        for batch, overlap in ((1000, 6), (1000, 2), (1000, 8), (3, 6), (250, 4), (1, 6)):
+            b = _batch_bounds(n, batch, overlap)
+            assert b[0] == 0 and b[-1] == n and all(y > x for x, y in zip(b, b[1:])), (n, batch, overlap)
+            assert max(y - x for x, y in zip(b, b[1:])) <= max(batch, 1), (n, batch, overlap)
+    sizes = [y - x for x, y in zip(_batch_bounds(20000, 1000, 6), _batch_bounds(20000, 1000, 6)[1:])]
+    assert sizes[:6] == [250, 250, 250, 500, 500, 500] and sizes[-6:] == [500, 500, 500, 250, 250, 250]
