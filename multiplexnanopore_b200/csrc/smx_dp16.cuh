@@ -55,25 +55,6 @@ __device__ __forceinline__ uint32_t smx16_max_tr(uint32_t a, uint32_t b, uint32_
     return r;
 }
 
-// first flag of a cell: starts the cell's own nibble registers (selp instead of a predicated OR), so that the
-// eight cells of a column do not serialise on one accumulator
-template <uint32_t IMM>
-__device__ __forceinline__ uint32_t smx16_max_tr_first(uint32_t a, uint32_t b, uint32_t &n_lo, uint32_t &n_hi)
-{
-    uint32_t r;
-    asm("{.reg .pred pu, pv; .reg .s16 r0, r1, r2, r3;\n\t"
-        "mov.b32 {r2, r3}, %3;\n\t"  // read a before %0 is written: the output may share its register
-        "max.s16x2 %0, %3, %4;\n\t"
-        "mov.b32 {r0, r1}, %0;\n\t"
-        "setp.eq.s16 pv, r0, r2;\n\t"
-        "setp.eq.s16 pu, r1, r3;\n\t"
-        "selp.b32 %1, 0, %5, pv;\n\t"
-        "selp.b32 %2, 0, %5, pu;}\n\t"
-        : "=r"(r), "=r"(n_lo), "=r"(n_hi)
-        : "r"(a), "r"(b), "n"(IMM));
-    return r;
-}
-
 struct Smx16Col {  // per-column scalars threaded through the K cells of a lane
     uint32_t hd, fu, hugo, h, f, w_lo, w_hi, w_lo2, w_hi2, one;
 };

@@ -5,7 +5,7 @@
 //   soft_clip()        MyResult.set_soft_clipping(_core)              :562-622
 //   merge_special()    MyAlignerBase.my_special_DP                    :89-163
 //   aligned_columns()  msa.MyMSA.generate_msa for two rows            modules/msa.py:882-982
-//   prefix_scores()    cumsum_my_cigar_scores                         :164-185
+//   (inside merge_special) cumsum_my_cigar_scores                     :164-185
 //   rotate_to_ref0()   MyResult.set_ref_seq_offset_as_0 (+ helpers)   :465-511
 //   cigar_score()      MyResult.set_cigar_score                       :452-464
 #pragma once
@@ -147,22 +147,6 @@ inline bool aligned_columns(const std::string &c1, const std::string &c2, size_t
             }
             ++w;
         }
-    }
-}
-
-// cumsum_my_cigar_scores: acc[0] = 0, acc[x+1] = score after column x; gap runs are maximal same-letter runs
-inline void prefix_scores(const std::string &cig, const Scoring &sc, std::vector<int64_t> &acc)
-{
-    acc.assign(cig.size() + 1, 0);
-    char prev = 0;
-    for (size_t i = 0; i < cig.size(); ++i) {
-        const char L = cig[i];
-        int64_t d = 0;
-        if (L == '=') d = sc.ma;
-        else if (L == 'X') d = sc.mi;
-        else if (L == 'D' || L == 'I') d = (prev == L) ? -sc.ge : -sc.go;
-        acc[i + 1] = acc[i] + d;
-        prev = L;
     }
 }
 
