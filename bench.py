@@ -184,7 +184,7 @@ def run_engine(args, rank, world, local_rank):
     n_threads = args.threads or max(1, min(4, (cores // max(world, 1)) // 2))
     refs = [p.upper() for p in plasmids]
     reads = [r.upper() for r in reads]
-    in_bytes = sum(len(p) for p in refs) + sum(len(r) for r in reads)
+    ref_bytes, read_bytes = sum(len(p) for p in refs), sum(len(r) for r in reads)
 
     def step(overlap=None):
         return sm.align_all(refs, reads, PARAMS, True, engine=eng, n_threads=n_threads, batch_queries=args.batch,
@@ -211,6 +211,10 @@ def run_engine(args, rank, world, local_rank):
         dist.barrier()
     cells = agg["dp_cells"]
     timed_stats = agg
+    # host -> device per step (rank 0): the sequence pool of every batch (each read on both strands, stored twice so that
+    # rotated slices are contiguous; the plasmid maps twice per batch) + DP descriptors (48 B + two 4 B orders per problem)
+    n_batches = -(-len(reads) // args.batch)
+    h2d_bytes = 4 * read_bytes + 2 * ref_bytes * n_batches + 56 * agg["n_dp_problems"] / args.steps
     if args.overlap > 1:
         # Device-time pass: with several batches in flight the CUDA-event intervals of one handle also contain
         # the other handles' kernels, so the per-kernel times behind `value` and `roofline` come from one extra
@@ -280,9 +284,9 @@ def run_engine(args, rank, world, local_rank):
     line = {
         "metric": "alignment-stage DP throughput (post_analysis, C2)", "value": cells_all / dev_s / 1e9, "unit": "GCUPS",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16x2 (int32 for problems of <= 32 rows)", "data": "synthetic",
         "config": config_dict(args, host_threads_per_rank=n_threads, host_cores=cores),
-        "e2e": {"value": cells_all / wall / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": 2 * in_bytes + in_bytes, "d2h_bytes_per_step": int(out_bytes),
+        "e2e": {"value": cells_all / wall / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(out_bytes),
                 "reads_per_s": reads_all / wall,
                 "note": "smx_pipeline_run from host buffers: pool upload, descriptors, region lists, CIGAR runs and results cross PCIe inside the timed region"},
         "reads_per_s_device": reads_all / dev_s, "scan_gcups_device": scan_all / (agg["gpu_scan_ms"] * 1e-3) / 1e9 if agg["gpu_scan_ms"] else None,

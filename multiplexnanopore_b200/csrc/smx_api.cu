@@ -129,6 +129,8 @@ static int fail(smx_handle *h, int code, const char *fmt, ...)
 static int ensure(smx_handle *h, DevBuf &b, size_t bytes)
 {
     if (bytes <= b.cap) return 0;
+    static const bool log_on = getenv("SMX_PHASE_LOG") != nullptr;
+    if (log_on) fprintf(stderr, "REALLOC dev %zu -> %zu\n", b.cap, bytes);
     if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
     size_t want = bytes + bytes / 8 + 256;
     cudaError_t e = cudaMalloc(&b.p, want);
@@ -144,6 +146,8 @@ static int ensure(smx_handle *h, DevBuf &b, size_t bytes)
 static int ensure_pinned(smx_handle *h, PinBuf &b, size_t bytes)
 {
     if (bytes <= b.cap) return 0;
+    static const bool log_on = getenv("SMX_PHASE_LOG") != nullptr;
+    if (log_on) fprintf(stderr, "REALLOC pin %zu -> %zu\n", b.cap, bytes);
     if (b.p) { cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
     const size_t want = bytes + bytes / 4 + 4096;
     cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocDefault);
@@ -208,8 +212,9 @@ static int mark(smx_handle *h, int tag, cudaStream_t stream = nullptr)
 // cores).  A blocking-sync event is recorded behind the work and waited for.
 static cudaError_t smx_sync(smx_handle *h, cudaStream_t stream)
 {
+    static const bool spin = [] { const char *e = getenv("SMX_SPIN_SYNC"); return e && e[0] == '1'; }();
     cudaEvent_t ev = stream == h->stream ? h->ev_sync_lo : h->ev_sync_hi;
-    if (!ev) return cudaStreamSynchronize(stream);
+    if (!ev || spin) return cudaStreamSynchronize(stream);
     cudaError_t e = cudaEventRecord(ev, stream);
     if (e != cudaSuccess) return e;
     return cudaEventSynchronize(ev);

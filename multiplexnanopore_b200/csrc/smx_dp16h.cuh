@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
                     s_top[wib][lane] = tv;
                     __syncwarp();
                 }
-                if (s0 >= 32 + LAG && s0 + 33 <= n) {
+                if (s0 >= (has_hi ? 32 + LAG : 32) && s0 + 33 <= n) {  // a pair without a high band needs no lag (single-band problems)
                     uint32_t *tp_lo = trace + ((size_t)band_lo * steps + s0) * 32 + lane;
                     uint32_t *tp_hi = trace + ((size_t)band_hi * steps + (s0 - LAG)) * 32 + lane;
                     uint32_t *bl = bot_lo + (s0 - 31);
