@@ -279,7 +279,7 @@ def run_engine(args, rank, world, local_rank):
         except Exception:
             pass
     cpu = None
-    if world >= 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:  # rank 0 at N = 1 only
         cpu = cpu_sample(plasmids, reads, args.cpu_reads or max(4 * cores, 16), cores)
     line = {
         "metric": "alignment-stage DP throughput (post_analysis, C2)", "value": cells_all / dev_s / 1e9, "unit": "GCUPS",

@@ -1410,6 +1410,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     t0 = now_s();
     std::atomic<int> n_bad(0);
     const std::vector<SmxResult> &dres = h->h_results;
+    const bool merge_chars = [] { const char *e = getenv("SMX_MERGE"); return e && std::string(e) == "chars"; }();  // cross-check switch
     parallel_for((int)todo.size(), n_threads, [&](int ti, int) {
         PairStrand &x = st.ps[(size_t)todo[(size_t)ti]];
         if (x.failed) return;
@@ -1440,7 +1441,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
                 ClippedSg r1, r2;
                 if (pc.prob[0] >= 0) r1 = clipped(pc.prob[0]); else r1.n_h = pc.n_ref;   // "H" * len(ref), end_ref = -1
                 if (pc.prob[1] >= 0) r2 = clipped(pc.prob[1]); else r2.n_h = pc.n_ref;   // "H" * len(ref), beg_ref = len(ref)
-                if (!merge_special_runs(r1, r2, pc.n_ref, pc.nq1, pc.nq2, sc, cig)) { x.failed = true; n_bad++; return; }
+                if (!merge_special_runs(r1, r2, pc.n_ref, pc.nq1, pc.nq2, sc, cig, merge_chars)) { x.failed = true; n_bad++; return; }
                 break;
             }
             }

@@ -360,19 +360,132 @@ struct ClippedSg {
     int64_t n_kept = 0, n_s = 0, n_h = 0;
 };
 
-// my_special_DP on re-clipped results; r1 = sg_qe_de(q1, ref) = kept1 + S*n_s1 + H*n_h1,
-// r2 = sg_qb_db(q2, ref) = H*n_h2 + S*n_s2 + kept2.  Appends the merged column runs to `out`.
-inline bool merge_special_runs(const ClippedSg &r1, const ClippedSg &r2, int64_t n_ref, int64_t nq1, int64_t nq2, const Scoring &sc, Runs &out)
+// One stretch of columns of the two-row alignment of r1 and r2 against the reference (generate_msa for two rows):
+// both rows hold one letter each over `len` columns.  Op codes as in the runs; FILL = the N / O filler columns.
+struct MergeSeg { uint32_t o1, o2; int64_t len; };
+static const uint32_t MERGE_FILL = 15u;
+
+// score of the first t columns of a stretch of letter `op` (t <= len) when the neighbouring column on the charged side
+// holds `nb`: cumsum_my_cigar_scores (:164-185) charges a gap run its open once, at its first column in reading order
+inline int64_t stretch_score(uint32_t op, uint32_t nb, int64_t t, const Scoring &sc)
 {
-    const int64_t gap = r2.n_h + r1.n_h - n_ref;  // r2.beg_ref - r1.end_ref - 1
-    if (gap > 0) {
-        append_runs(out, r1.kept, r1.n_kept);
-        push_run(out, 4, r1.n_s);
-        push_run(out, 5, gap);
-        push_run(out, 4, r2.n_s);
-        append_runs(out, r2.kept, r2.n_kept);
-        return true;
+    if (t <= 0) return 0;
+    switch (op) {
+    case 7: return (int64_t)sc.ma * t;
+    case 8: return (int64_t)sc.mi * t;
+    case 1: case 2: return -((int64_t)(nb == op ? sc.ge : sc.go) + (int64_t)sc.ge * (t - 1));
+    default: return 0;
     }
+}
+
+// The overlap branch of my_special_DP (:124-152) on runs.  The two-row generate_msa (modules/msa.py:882-982) only ever
+// emits stretches of constant (row 1 letter, row 2 letter); over such a stretch the left prefix score of row 1 and the
+// right suffix score of row 2 are linear except for the open charged at the first (row 1) resp. last (row 2) column of
+// a gap run, so left + right is linear between cut 1 and cut len - 1 of a stretch and the FIRST maximum (np.argmax,
+// :136) lies on one of the cuts 0, 1, len - 1 of some stretch or at the very end.  O(runs) instead of O(columns); the
+// column-level version above (merge_special) is kept as the cross-check (tests/test_stitch_cpu.py).
+inline bool merge_overlap_runs(const ClippedSg &r1, const ClippedSg &r2, int64_t n_ref, int64_t nq1, int64_t nq2, const Scoring &sc, Runs &out)
+{
+    // row 1 = kept1, S * n_s1, H * n_h1;  row 2 = H * n_h2, S * n_s2, kept2
+    struct Cursor {
+        const uint32_t *kept; int64_t n_kept; int64_t extra[2]; uint32_t extra_op[2]; bool extras_first;
+        int64_t pos = 0, left = 0; uint32_t op = 0; bool done = false;
+        int64_t n_items() const { return n_kept + 2; }
+        void load()
+        {
+            for (;; ++pos) {
+                if (pos >= n_items()) { done = true; op = 0; left = 0; return; }
+                const int64_t e = extras_first ? pos : pos - n_kept;  // index into the extras, if in range
+                if (e >= 0 && e < 2) { op = extra_op[e]; left = extra[e]; }
+                else { const uint32_t r = kept[extras_first ? pos - 2 : pos]; op = r & 15u; left = (int64_t)(r >> 4); }
+                if (left > 0) return;
+            }
+        }
+        void take(int64_t n) { left -= n; if (left == 0) { ++pos; load(); } }
+    };
+    Cursor c1{r1.kept, r1.n_kept, {r1.n_s, r1.n_h}, {4u, 5u}, false};
+    Cursor c2{r2.kept, r2.n_kept, {r2.n_h, r2.n_s}, {5u, 4u}, true};
+    c1.load(); c2.load();
+    if (c1.done || c2.done) return false;
+    thread_local std::vector<MergeSeg> tl_segs;
+    thread_local std::vector<int64_t> tl_suf;
+    std::vector<MergeSeg> &segs = tl_segs;  // one TLS lookup per call, not per stretch
+    std::vector<int64_t> &suf = tl_suf;
+    segs.clear();
+    segs.reserve((size_t)(r1.n_kept + r2.n_kept + 8));
+    int64_t ref1 = 0, ref2 = 0, q1 = 0, q2 = 0;
+    while (!c1.done || !c2.done) {
+        const uint32_t a = c1.done ? 0u : c1.op, b = c2.done ? 0u : c2.op;
+        const bool has_s = a == 4u || b == 4u, has_i = a == 1u || b == 1u;
+        if (has_s || has_i) {
+            const uint32_t want = has_s ? 4u : 1u;
+            if (a == want && b == want) {
+                const int64_t n = c1.left < c2.left ? c1.left : c2.left;
+                segs.push_back({want, want, n}); q1 += n; q2 += n; c1.take(n); c2.take(n);
+            } else if (a == want) { const int64_t n = c1.left; segs.push_back({want, MERGE_FILL, n}); q1 += n; c1.take(n); }
+            else { const int64_t n = c2.left; segs.push_back({MERGE_FILL, want, n}); q2 += n; c2.take(n); }
+        } else {
+            if (c1.done || c2.done) return false;  // one row ran out of reference columns before the other
+            const int64_t n = c1.left < c2.left ? c1.left : c2.left;
+            segs.push_back({a, b, n});
+            if (a == 7u || a == 8u) q1 += n;
+            if (b == 7u || b == 8u) q2 += n;
+            ref1 += n; ref2 += n;
+            c1.take(n); c2.take(n);
+        }
+    }
+    if (ref1 != n_ref || ref2 != n_ref || q1 != nq1 || q2 != nq2) return false;
+    const size_t ns = segs.size();
+    // suf[k] = score of row 2 over the stretches k.. (read from the end)
+    suf.assign(ns + 1, 0);
+    for (size_t k = ns; k-- > 0;) {
+        const uint32_t nb = k + 1 < ns ? segs[k + 1].o2 : 0u;
+        suf[k] = suf[k + 1] + stretch_score(segs[k].o2, nb, segs[k].len, sc);
+    }
+    // first maximum of left[x] + right[x] over the cuts x = 0 .. L
+    int64_t best = suf[0], best_k = 0, best_t = 0, left = 0;
+    for (size_t k = 0; k < ns; ++k) {
+        const MergeSeg &g = segs[k];
+        const uint32_t pb = k > 0 ? segs[k - 1].o1 : 0u, nb = k + 1 < ns ? segs[k + 1].o2 : 0u;
+        const int64_t cand[3] = {0, 1, g.len - 1};
+        int64_t last_t = -1;
+        for (int c = 0; c < 3; ++c) {
+            const int64_t t = cand[c];
+            if (t <= last_t || t >= g.len) continue;
+            last_t = t;
+            const int64_t v = left + stretch_score(g.o1, pb, t, sc) + stretch_score(g.o2, nb, g.len - t, sc) + suf[k + 1];
+            if (v > best) { best = v; best_k = (int64_t)k; best_t = t; }
+        }
+        left += stretch_score(g.o1, pb, g.len, sc);
+    }
+    if (left > best) { best = left; best_k = (int64_t)ns; best_t = 0; }  // cut = L: all of row 1
+    // row 1 up to the cut, the clipped query letters of both rows as S, row 2 from the cut (fillers dropped)
+    auto consumes_query = [](uint32_t op) { return op == 7u || op == 8u || op == 1u || op == 4u; };
+    int64_t n_s = 0;
+    for (size_t k = 0; k < ns; ++k) {
+        const MergeSeg &g = segs[k];
+        const int64_t before = (int64_t)k < best_k ? g.len : ((int64_t)k == best_k ? best_t : 0);
+        if (consumes_query(g.o2)) n_s += before;
+        if (consumes_query(g.o1)) n_s += g.len - before;
+    }
+    for (size_t k = 0; k < ns; ++k) {
+        const MergeSeg &g = segs[k];
+        const int64_t before = (int64_t)k < best_k ? g.len : ((int64_t)k == best_k ? best_t : 0);
+        if (before == 0) break;
+        if (g.o1 != MERGE_FILL) push_run(out, g.o1, before);
+    }
+    push_run(out, 4u, n_s);
+    for (size_t k = (size_t)(best_k < (int64_t)ns ? best_k : (int64_t)ns); k < ns; ++k) {
+        const MergeSeg &g = segs[k];
+        const int64_t after = (int64_t)k == best_k ? g.len - best_t : g.len;
+        if (g.o2 != MERGE_FILL) push_run(out, g.o2, after);
+    }
+    return true;
+}
+
+// the same branch through the column strings (the round's first implementation, kept as the cross-check)
+inline bool merge_overlap_chars(const ClippedSg &r1, const ClippedSg &r2, int64_t n_ref, int64_t nq1, int64_t nq2, const Scoring &sc, Runs &out)
+{
     SgResult a, b;
     expand_runs(r1.kept, r1.n_kept, a.cig);
     a.cig.append((size_t)r1.n_s, 'S');
@@ -392,6 +505,23 @@ inline bool merge_special_runs(const ClippedSg &r1, const ClippedSg &r2, int64_t
         i = j;
     }
     return true;
+}
+
+// my_special_DP on re-clipped results; r1 = sg_qe_de(q1, ref) = kept1 + S*n_s1 + H*n_h1,
+// r2 = sg_qb_db(q2, ref) = H*n_h2 + S*n_s2 + kept2.  Appends the merged column runs to `out`.
+inline bool merge_special_runs(const ClippedSg &r1, const ClippedSg &r2, int64_t n_ref, int64_t nq1, int64_t nq2, const Scoring &sc, Runs &out,
+                               bool column_strings = false)
+{
+    const int64_t gap = r2.n_h + r1.n_h - n_ref;  // r2.beg_ref - r1.end_ref - 1
+    if (gap > 0) {
+        append_runs(out, r1.kept, r1.n_kept);
+        push_run(out, 4, r1.n_s);
+        push_run(out, 5, gap);
+        push_run(out, 4, r2.n_s);
+        append_runs(out, r2.kept, r2.n_kept);
+        return true;
+    }
+    return column_strings ? merge_overlap_chars(r1, r2, n_ref, nq1, nq2, sc, out) : merge_overlap_runs(r1, r2, n_ref, nq1, nq2, sc, out);
 }
 
 }  // namespace smx

@@ -154,3 +154,20 @@ def test_device_select_equals_host_redecision(engine, topology, monkeypatch):
     assert np.array_equal(dev.score, host.score) and np.array_equal(dev.status, host.status)
     assert np.array_equal(dev.new_query_seq_offset, host.new_query_seq_offset)
     assert np.array_equal(dev.cigar_off, host.cigar_off) and np.array_equal(dev.cigar_rle, host.cigar_rle)
+
+
+def test_run_length_merge_equals_column_string_merge(engine, monkeypatch):
+    """Row A10 has two implementations: the run-length overlap merge (default) and the column-string one
+    (SMX_MERGE=chars, the first implementation; tests/test_stitch_cpu.py compares them on random rows without a GPU);
+    on real pipeline output every pair-strand must be identical."""
+    rng = np.random.default_rng(131)
+    plasmids = synth.plasmid_set(rng, 6, 4000, 9000, backbone=2500)
+    reads, _ = synth.reads_for(rng, plasmids, 600, topology=0, homopolymer_rate=0.5)
+    monkeypatch.delenv("SMX_MERGE", raising=False)
+    runs = sm.align_all(plasmids, reads, PARAMS, True, engine=engine)
+    monkeypatch.setenv("SMX_MERGE", "chars")
+    chars = sm.align_all(plasmids, reads, PARAMS, True, engine=engine)
+    assert int(runs.stats.get("n_failed", 0)) == int(chars.stats.get("n_failed", 0))
+    assert np.array_equal(runs.status, chars.status) and np.array_equal(runs.score, chars.score)
+    assert np.array_equal(runs.new_query_seq_offset, chars.new_query_seq_offset)
+    assert np.array_equal(runs.cigar_off, chars.cigar_off) and np.array_equal(runs.cigar_rle, chars.cigar_rle)
