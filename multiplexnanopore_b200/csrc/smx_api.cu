@@ -1416,6 +1416,12 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         if (x.failed) return;
         Runs &cig = x.runs;
         cig.clear();
+        auto n_runs_of = [&](int pid) { return pid >= 0 ? cg_off[(size_t)pid + 1] - cg_off[(size_t)pid] : (int64_t)0; };
+        {
+            int64_t need = 4;
+            for (const Piece &pc : x.pieces) need += 4 + n_runs_of(pc.kind == PIECE_LITERAL ? -1 : pc.prob[0]) + (pc.kind == PIECE_SPECIAL ? n_runs_of(pc.prob[1]) : 0);
+            cig.reserve((size_t)need);
+        }
         auto clipped = [&](int pid) {
             ClippedSg c;
             c.kept = &cg[(size_t)cg_off[(size_t)pid]];
@@ -1426,15 +1432,15 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         for (const Piece &pc : x.pieces) {
             switch (pc.kind) {
             case PIECE_LITERAL: push_run(cig, op_code(pc.letter), pc.len); break;
-            case PIECE_NW: append_runs(cig, &cg[(size_t)cg_off[(size_t)pc.prob[0]]], cg_off[(size_t)pc.prob[0] + 1] - cg_off[(size_t)pc.prob[0]]); break;
+            case PIECE_NW: append_maximal_runs(cig, &cg[(size_t)cg_off[(size_t)pc.prob[0]]], n_runs_of(pc.prob[0])); break;
             case PIECE_SG_HEAD: {  // my_special_sg_qb_db: H.. S.. aligned
                 const ClippedSg c = clipped(pc.prob[0]);
-                push_run(cig, 5, c.n_h); push_run(cig, 4, c.n_s); append_runs(cig, c.kept, c.n_kept);
+                push_run(cig, 5, c.n_h); push_run(cig, 4, c.n_s); append_maximal_runs(cig, c.kept, c.n_kept);
                 break;
             }
             case PIECE_SG_TAIL: {  // my_special_sg_qe_de: aligned S.. H..
                 const ClippedSg c = clipped(pc.prob[0]);
-                append_runs(cig, c.kept, c.n_kept); push_run(cig, 4, c.n_s); push_run(cig, 5, c.n_h);
+                append_maximal_runs(cig, c.kept, c.n_kept); push_run(cig, 4, c.n_s); push_run(cig, 5, c.n_h);
                 break;
             }
             case PIECE_SPECIAL: {

@@ -279,6 +279,16 @@ inline void append_runs(Runs &v, const uint32_t *r, int64_t n)
     for (int64_t i = 0; i < n; ++i) push_run(v, r[i] & 15u, (int64_t)(r[i] >> 4));
 }
 
+// append_runs for an array that is itself a maximal-run decomposition without empty runs (what the traceback kernel
+// emits per problem, smx_traceback.cuh: SmxWalk::emit merges equal neighbours and drops empty runs; a clipped result
+// is a contiguous slice of such an array): only the first run can merge with what is already there.
+inline void append_maximal_runs(Runs &v, const uint32_t *r, int64_t n)
+{
+    if (n <= 0) return;
+    push_run(v, r[0] & 15u, (int64_t)(r[0] >> 4));
+    if (n > 1) v.insert(v.end(), r + 1, r + n);
+}
+
 inline int64_t total_columns(const Runs &v)
 {
     int64_t n = 0;
@@ -324,17 +334,28 @@ inline int64_t rotate_to_ref0_runs(Runs &v, int64_t ref_off, int64_t q_off)
     else new_off = 0;
     if (a_r > 0) {
         const int64_t n = total_columns(v);
-        int64_t head = a_r >= n ? 0 : n - a_r;  // columns that move to the back
-        Runs front, back;
-        for (uint32_t r : v) {
-            const int64_t len = r >> 4;
-            const uint32_t op = r & 15u;
-            if (head >= len) { push_run(back, op, len); head -= len; }
-            else if (head > 0) { push_run(back, op, head); push_run(front, op, len - head); head = 0; }
-            else push_run(front, op, len);
+        const int64_t head = a_r >= n ? 0 : n - a_r;  // columns that move to the back
+        // v is maximal, so after cutting at column `head` only the wrap-around junction (old last run, old first
+        // run) can merge; everything else moves as blocks
+        size_t idx = 0;
+        int64_t acc = 0;
+        while (idx < v.size() && acc + (int64_t)(v[idx] >> 4) <= head) { acc += v[idx] >> 4; ++idx; }
+        const int64_t part = head - acc;  // leading columns of v[idx] that still lie before the cut (they move to the back)
+        if (idx > 0 || part > 0) {
+            thread_local Runs tl_rot;
+            Runs &t = tl_rot;
+            t.clear();
+            t.reserve(v.size() + 2);
+            size_t start = idx;
+            if (part > 0) { t.push_back((uint32_t)(((int64_t)(v[idx] >> 4) - part) << 4) | (v[idx] & 15u)); start = idx + 1; }
+            t.insert(t.end(), v.begin() + (std::ptrdiff_t)start, v.end());
+            if (idx > 0) {
+                push_run(t, v[0] & 15u, (int64_t)(v[0] >> 4));
+                t.insert(t.end(), v.begin() + 1, v.begin() + (std::ptrdiff_t)idx);
+            }
+            if (part > 0) push_run(t, v[idx] & 15u, part);
+            v.assign(t.begin(), t.end());
         }
-        append_runs(front, back.data(), (int64_t)back.size());
-        v.swap(front);
     }
     return new_off;
 }
@@ -514,11 +535,11 @@ inline bool merge_special_runs(const ClippedSg &r1, const ClippedSg &r2, int64_t
 {
     const int64_t gap = r2.n_h + r1.n_h - n_ref;  // r2.beg_ref - r1.end_ref - 1
     if (gap > 0) {
-        append_runs(out, r1.kept, r1.n_kept);
+        append_maximal_runs(out, r1.kept, r1.n_kept);
         push_run(out, 4, r1.n_s);
         push_run(out, 5, gap);
         push_run(out, 4, r2.n_s);
-        append_runs(out, r2.kept, r2.n_kept);
+        append_maximal_runs(out, r2.kept, r2.n_kept);
         return true;
     }
     return column_strings ? merge_overlap_chars(r1, r2, n_ref, nq1, nq2, sc, out) : merge_overlap_runs(r1, r2, n_ref, nq1, nq2, sc, out);

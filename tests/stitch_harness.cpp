@@ -17,3 +17,20 @@ extern "C" long long smx_test_merge(const uint32_t *k1, long long nk1, long long
     if (!runs.empty()) memcpy(out, runs.data(), sizeof(uint32_t) * runs.size());
     return (long long)runs.size();
 }
+
+// rotate_to_ref0 on runs (in place, returns the run count) and on the column string; both return new_query_seq_offset
+extern "C" long long smx_test_rotate(uint32_t *runs, long long n, long long cap, long long ref_off, long long q_off, int column_strings, long long *new_off)
+{
+    smx::Runs v(runs, runs + n);
+    if (column_strings) {
+        std::string cig;
+        smx::expand_runs(v.data(), (int64_t)v.size(), cig);
+        *new_off = smx::rotate_to_ref0(cig, ref_off, q_off);
+        smx::encode_runs(cig, v);
+    } else {
+        *new_off = smx::rotate_to_ref0_runs(v, ref_off, q_off);
+    }
+    if ((long long)v.size() > cap) return -2;
+    if (!v.empty()) memcpy(runs, v.data(), sizeof(uint32_t) * v.size());
+    return (long long)v.size();
+}

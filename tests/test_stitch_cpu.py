@@ -130,3 +130,35 @@ def test_long_overlap(harness):
         a = merge(harness, kept1, 7, n_ref - e1 - 1, kept2, 0, b2, n_ref, nq1, nq2, sc, False)
         b = merge(harness, kept1, 7, n_ref - e1 - 1, kept2, 0, b2, n_ref, nq1, nq2, sc, True)
         assert a is not None and a == b
+
+
+def test_rotation_on_runs_matches_column_strings(harness):
+    """Row A11 (set_ref_seq_offset_as_0, ref_query_alignment.py:465-511): block rotation of the runs against the
+    column-string restatement in the same header and the oracle port."""
+    ll = ctypes.c_longlong
+    harness.smx_test_rotate.restype = ll
+    harness.smx_test_rotate.argtypes = [ctypes.POINTER(ctypes.c_uint32), ll, ll, ll, ll, ctypes.c_int, ctypes.POINTER(ll)]
+    rng = np.random.default_rng(11)
+    n_rot = 0
+    for it in range(1500):
+        n_ref = int(rng.integers(1, 200))
+        cig = rand_aligned(rng, n_ref, float(rng.choice([0.03, 0.2])), bool(rng.integers(0, 2)))
+        if rng.random() < 0.5:  # clipped tail / head as the stitcher produces them
+            cig = "H" * int(rng.integers(0, 9)) + "S" * int(rng.integers(0, 9)) + cig + "S" * int(rng.integers(0, 9)) + "H" * int(rng.integers(0, 9))
+        n_r = sum(cig.count(x) for x in "=XDH")
+        n_q = sum(cig.count(x) for x in "=XIS")
+        ref_off, q_off = int(rng.integers(0, n_r + 1)) * int(rng.integers(0, 2)), int(rng.integers(0, n_q + 1)) * int(rng.integers(0, 2))
+        got = []
+        for mode in (0, 1):
+            runs = np.zeros(len(cig) + 4, np.uint32)
+            enc = encode(cig)
+            runs[:len(enc)] = enc
+            off = ll(0)
+            n = harness.smx_test_rotate(runs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(enc), len(runs), ref_off, q_off, mode, ctypes.byref(off))
+            assert n >= 0
+            got.append((decode(runs[:n]), int(off.value), [int(r) for r in runs[:n]]))
+        assert got[0] == got[1], (cig, ref_off, q_off)
+        want_cig, want_off = port.rotate_to_ref0(cig, ref_off, q_off)
+        assert got[0][0] == want_cig and got[0][1] == want_off, (cig, ref_off, q_off)
+        n_rot += want_cig != cig
+    assert n_rot > 300
