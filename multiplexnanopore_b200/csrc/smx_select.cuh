@@ -153,48 +153,71 @@ __global__ void __launch_bounds__(SMX_SEL_THREADS) smx_select_kernel(const SmxSe
     const int nr = pr.nr, nq = pr.nq;
     const bool linear = a.topology == 1;
     SmxRegion *out = s_regs;
+    // Lane w keeps the ballot word of bases [g + 32 w, g + 32 w + 32) of a 1024-base group; every lane then looks at
+    // its own word: the run open at the word's first bit (its start comes from the nearest lower word that is not
+    // all ones), and the one run of more than 20 matches that can lie strictly inside 32 bits (found by AND-shifts).
+    // A run is reported by the lane in whose word it ends; bits at and beyond nq are 0, so every run ends.
+    auto report = [&](int k, int rs, int re) {
+        if (re - rs + 1 > SMX_RUN_MIN) {
+            const int idx = atomicAdd(&n_reg, 1);
+            if (idx < pr.region_cap) out[idx] = SmxRegion{k, rs, re};
+        }
+    };
     for (int si = warp; si < nsel; si += SMX_SEL_THREADS / 32) {
         const int k = sel[si];
-        int start = -1;  // lane 0: start of the open run
-        for (int base = 0; base < nq; base += 32) {
-            const int i = base + lane;
-            bool eq = false;
-            if (i < nq) {
-                int p = linear ? (k - (nq - 1) + i) : ((k + i) % nr);
-                if (!linear || (p >= 0 && p < nr)) eq = ref[p] == qry[i];
-            }
-            unsigned m = __ballot_sync(SMX_FULL_MASK, eq);
-            if (lane == 0) {
-                int pos = 0;
-                while (pos < 32) {
-                    if (start >= 0) {
-                        const unsigned z = ~m >> pos;  // first mismatch at or after pos
-                        if (z == 0) break;
-                        const int off = __ffs(z) - 1;
-                        const int end = base + pos + off - 1;
-                        if (end - start + 1 > SMX_RUN_MIN) {
-                            const int idx = atomicAdd(&n_reg, 1);
-                            if (idx < pr.region_cap) out[idx] = SmxRegion{k, start, end};
-                        }
-                        start = -1;
-                        pos += off;
+        int carry = -1;  // start of the run open at the beginning of the group (warp-uniform)
+        for (int g = 0; g < nq; g += 1024) {
+            const int nwords = min(32, (nq - g + 31) >> 5);
+            uint32_t mine = 0;
+            for (int w = 0; w < nwords; ++w) {
+                const int i = g + w * 32 + lane;
+                bool eq = false;
+                if (i < nq) {
+                    if (linear) {
+                        const int p = k - (nq - 1) + i;
+                        if (p >= 0 && p < nr) eq = ref[p] == qry[i];
                     } else {
-                        const unsigned o = m >> pos;
-                        if (o == 0) break;
-                        const int off = __ffs(o) - 1;
-                        start = base + pos + off;
-                        pos += off;
+                        int p = k + i;
+                        if (p >= nr) { p -= nr; if (p >= nr) p %= nr; }
+                        eq = ref[p] == qry[i];
                     }
                 }
+                const unsigned m = __ballot_sync(SMX_FULL_MASK, eq);
+                if (lane == w) mine = m;
             }
-        }
-        if (lane == 0 && start >= 0) {
-            const int end = nq - 1;
-            if (end - start + 1 > SMX_RUN_MIN) {
-                const int idx = atomicAdd(&n_reg, 1);
-                if (idx < pr.region_cap) out[idx] = SmxRegion{k, start, end};
+            const int base = g + lane * 32;
+            const uint32_t nm = ~mine;
+            const int c = nm ? __ffs(nm) - 1 : 32;  // ones from bit 0 up
+            const int h = nm ? __clz(nm) : 32;      // ones from bit 31 down
+            const unsigned allones = __ballot_sync(SMX_FULL_MASK, nm == 0u);
+            // start of the run that is open when this lane's word ends (-1: none; all-ones words resolved below)
+            const int open_out = h == 0 ? -1 : base + 32 - h;
+            const unsigned lower = ~allones & ((1u << lane) - 1u);  // lower lanes whose word has a zero bit
+            const int src = lower ? 31 - __clz(lower) : -1;
+            int entering = __shfl_sync(SMX_FULL_MASK, open_out, src < 0 ? 0 : src);
+            if (src < 0) entering = carry;
+            // all-ones words between src and this lane: a run that was not open before them starts at the first of them
+            if (entering < 0 && lane - 1 > src) entering = g + (src + 1) * 32;
+            uint32_t rest = mine;
+            if (entering >= 0) {
+                if (c < 32) report(k, entering, base + c - 1);
+                rest = c == 32 ? 0u : (mine & ~((1u << c) - 1u));
             }
+            {
+                const uint32_t a2 = rest & (rest >> 1), a4 = a2 & (a2 >> 2), a8 = a4 & (a4 >> 4), a16 = a8 & (a8 >> 8);
+                const uint32_t a21 = a16 & (a4 >> 16) & (rest >> 20);  // bit p: bits p .. p+20 of `rest` are set
+                if (a21) {
+                    const int p = __ffs(a21) - 1;
+                    const uint32_t inv = ~(rest >> p);
+                    const int e = inv ? p + __ffs(inv) - 2 : 31;  // last bit of that run (inv == 0: all 32 bits set)
+                    if (e < 31) report(k, base + p, base + e);  // a run touching bit 31 is still open: a later word ends it
+                }
+            }
+            // run open at the end of the group
+            int out31 = nm == 0u ? (entering >= 0 ? entering : base) : open_out;
+            carry = __shfl_sync(SMX_FULL_MASK, out31, 31);
         }
+        if (lane == 0 && carry >= 0) report(k, carry, nq - 1);  // nq a multiple of 1024 and the last base matches
     }
     __syncthreads();
     const int n_keep = min(n_reg, pr.region_cap);
