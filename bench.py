@@ -211,10 +211,11 @@ def run_engine(args, rank, world, local_rank):
         dist.barrier()
     cells = agg["dp_cells"]
     timed_stats = agg
-    # host -> device per step (rank 0): the sequence pool of every batch (each read on both strands, stored twice so that
-    # rotated slices are contiguous; the plasmid maps twice per batch) + DP descriptors (48 B + two 4 B orders per problem)
+    # host -> device per step (rank 0): every read once and the plasmid maps once per batch (the pool -- both strands,
+    # each stored twice so that rotated slices are contiguous -- is built on the device), the 24-byte expansion items,
+    # the DP descriptors (48 B + two 4 B orders per problem)
     n_batches = -(-len(reads) // args.batch)
-    h2d_bytes = 4 * read_bytes + 2 * ref_bytes * n_batches + 56 * agg["n_dp_problems"] / args.steps
+    h2d_bytes = read_bytes + ref_bytes * n_batches + 24 * (2 * len(reads) + len(refs) * n_batches) + 56 * agg["n_dp_problems"] / args.steps
     if args.overlap > 1:
         # Device-time pass: with several batches in flight the CUDA-event intervals of one handle also contain
         # the other handles' kernels, so the per-kernel times behind `value` and `roofline` come from one extra

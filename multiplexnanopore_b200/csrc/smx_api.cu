@@ -87,6 +87,7 @@ struct smx_handle {
     int64_t runs_scratch = 0;
     int64_t total_runs = -1;
     DevBuf d_probs, d_order_cls, d_order_all, d_results, d_trace, d_boundary, d_runs, d_dense, d_dense_off, d_tickets, d_slots;
+    DevBuf d_compact, d_expand_items, d_comp;  // pipeline pool: sequences as given, expansion list, complement table
     std::vector<SmxResult> h_results;
     std::vector<int64_t> h_dense_off;
 
@@ -100,7 +101,7 @@ struct smx_handle {
     DevBuf d_sel_pairs, d_sel_out, d_regions;
     DevBuf d_chain_tasks, d_chain_regions, d_chain_traces, d_chain_out, d_chain_scratch;
     std::vector<uint8_t> host_pool;
-    PinBuf pin_regions, pin_cigar, pin_pool;
+    PinBuf pin_regions, pin_cigar, pin_pool, pin_special;
     PinBuf pin_stage[16];  // page-locked staging of the small descriptor / result copies (PinSlot)
     struct SmxPipelineState *pipe = nullptr;
 };
@@ -161,7 +162,7 @@ static int ensure_pinned(smx_handle *h, PinBuf &b, size_t bytes)
 // descriptor / result copies of a batch's front end were measured to wait 30 ms and more behind the other handles'
 // work (the select phase took 41 ms of which the kernel 9 ms).
 enum PinSlot { PIN_PROBS, PIN_ORDER_CLS, PIN_ORDER_ALL, PIN_RESULTS, PIN_DENSE_OFF, PIN_SCAN_PAIRS, PIN_SCAN_TILES, PIN_SEL_PAIRS,
-               PIN_SEL_OUT, PIN_NREG, PIN_CHAIN_TASKS, PIN_CHAIN_REGS, PIN_CHAIN_OUT, PIN_CHAIN_TR };
+               PIN_SEL_OUT, PIN_NREG, PIN_CHAIN_TASKS, PIN_CHAIN_REGS, PIN_CHAIN_OUT, PIN_CHAIN_TR, PIN_EXPAND };
 
 // host -> device through staging slot `slot`; the slot must not be reused before `stream` has been synchronised
 static int h2d(smx_handle *h, int slot, void *dst_dev, const void *src, size_t bytes, cudaStream_t stream)
@@ -285,9 +286,9 @@ extern "C" void smx_destroy(smx_handle *h)
     DevBuf *bufs[] = {&h->pool, &h->pool2, &h->pool_special, &h->d_probs, &h->d_order_cls, &h->d_order_all, &h->d_results, &h->d_trace, &h->d_boundary,
                       &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_slots, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts,
                       &h->d_sel_pairs, &h->d_sel_out, &h->d_regions, &h->d_chain_tasks, &h->d_chain_regions, &h->d_chain_traces,
-                      &h->d_chain_out, &h->d_chain_scratch};
+                      &h->d_chain_out, &h->d_chain_scratch, &h->d_compact, &h->d_expand_items, &h->d_comp};
     smx_pipeline_free(h);
-    for (PinBuf *b : {&h->pin_regions, &h->pin_cigar, &h->pin_pool}) if (b->p) cudaFreeHost(b->p);
+    for (PinBuf *b : {&h->pin_regions, &h->pin_cigar, &h->pin_pool, &h->pin_special}) if (b->p) cudaFreeHost(b->p);
     for (PinBuf &b : h->pin_stage) if (b.p) cudaFreeHost(b.p);
     for (DevBuf *b : bufs) release(*b);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -308,6 +309,8 @@ extern "C" int smx_set_trace_budget(smx_handle *h, int64_t bytes)
     return 0;
 }
 
+static int pool_finish(smx_handle *h, int64_t n);
+
 extern "C" int smx_pool_upload(smx_handle *h, const uint8_t *seqs, int64_t n)
 {
     if (!h) return -1;
@@ -315,6 +318,31 @@ extern "C" int smx_pool_upload(smx_handle *h, const uint8_t *seqs, int64_t n)
     SMX_CUDA(h, cudaSetDevice(h->device));
     if (int rc = ensure(h, h->pool, (size_t)n + 64)) return rc;
     SMX_CUDA(h, cudaMemcpyAsync(h->pool.p, seqs, (size_t)n, cudaMemcpyHostToDevice, h->stream_hi));
+    return pool_finish(h, n);
+}
+
+// The pipeline's pool is built on the device: the sequences cross PCIe once, as given; every pool entry is a sequence
+// (or its reverse complement, Biopython's IUPAC table) written twice back to back.
+struct SmxExpandItem { int64_t src, dst; int32_t len, rc; };
+
+__global__ void __launch_bounds__(256) smx_expand_pool_kernel(const uint8_t *compact, const SmxExpandItem *items, const uint8_t *comp, uint8_t *pool)
+{
+    __shared__ uint8_t s_comp[256];
+    s_comp[threadIdx.x] = comp[threadIdx.x];
+    __syncthreads();
+    const SmxExpandItem it = items[blockIdx.x];
+    const uint8_t *src = compact + it.src;
+    uint8_t *dst = pool + it.dst;
+    for (int i = threadIdx.x; i < it.len; i += 256) {
+        const uint8_t b = it.rc ? s_comp[src[it.len - 1 - i]] : src[i];
+        dst[i] = b;
+        dst[it.len + i] = b;
+    }
+}
+
+// bit planes, non-ACGT flags and the host-side block prefix for the pool bytes already in h->pool (on stream_hi)
+static int pool_finish(smx_handle *h, int64_t n)
+{
     {
         const int64_t n_words = (n + 31) / 32;  // bit planes: one uint2 per 32 bases
         if (int rc = ensure(h, h->pool2, sizeof(uint2) * (size_t)(n_words + 4))) return rc;
@@ -324,28 +352,24 @@ extern "C" int smx_pool_upload(smx_handle *h, const uint8_t *seqs, int64_t n)
         smx_pack_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, h->stream_hi>>>((const uint8_t *)h->pool.p, n, (uint2 *)h->pool2.p,
                                                                                  (uint8_t *)h->pool_special.p, n_words);
         SMX_CUDA(h, cudaGetLastError());
+        // the per-word "holds a byte other than A/C/G/T" flags come back for the host-side kernel choice (1 byte per 32 bases)
+        if (int rc = ensure_pinned(h, h->pin_special, (size_t)n_words)) return rc;
+        SMX_CUDA(h, cudaMemcpyAsync(h->pin_special.p, h->pool_special.p, (size_t)n_words, cudaMemcpyDeviceToHost, h->stream_hi));
     }
     SMX_CUDA(h, smx_sync(h, h->stream_hi));
     h->pool_len = n;
-    // per 64-byte block: does it hold a byte other than A/C/G/T?  prefix over blocks (s16 kernel eligibility)
+    // per 64-byte block: does it hold a byte other than A/C/G/T?  prefix over blocks (s16 kernel eligibility); the flags
+    // were computed by smx_pack_kernel (the first version scanned the 30 MB pool of a batch again on 16 host threads)
     {
-        const int64_t nb = (n + 63) / 64;
-        h->pool_nonacgt.assign((size_t)nb + 1, 0);
-        std::vector<uint8_t> flag((size_t)nb, 0);
-        const int nt = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; ++t)
-            th.emplace_back([&, t]() {
-                for (int64_t b = t; b < nb; b += nt) {
-                    const int64_t lo = b * 64, hi = std::min(n, lo + 64);
-                    uint8_t f = 0;
-                    for (int64_t i = lo; i < hi; ++i) { const uint8_t c = seqs[i]; f |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T'); }
-                    flag[(size_t)b] = f;
-                }
-            });
-        for (auto &x : th) x.join();
+        const int64_t nb = (n + 63) / 64, n_words = (n + 31) / 32;
+        const uint8_t *sp = (const uint8_t *)h->pin_special.p;
+        h->pool_nonacgt.resize((size_t)nb + 1);
+        h->pool_nonacgt[0] = 0;
         int32_t acc = 0;
-        for (int64_t b = 0; b < nb; ++b) { acc += flag[(size_t)b]; h->pool_nonacgt[(size_t)b + 1] = acc; }
+        for (int64_t b = 0; b < nb; ++b) {
+            acc += (sp[2 * b] | (2 * b + 1 < n_words ? sp[2 * b + 1] : 0)) ? 1 : 0;
+            h->pool_nonacgt[(size_t)b + 1] = acc;
+        }
     }
     return 0;
 }
@@ -1040,22 +1064,37 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         qpool[(size_t)q * 2 + 1] = total; total += 2ll * qry_len[q];
     }
     {
-        if (int rc = ensure_pinned(h, h->pin_pool, (size_t)total)) return rc;
-        uint8_t *pool = (uint8_t *)h->pin_pool.p;
+        // the sequences go up once, as given (page-locked staging); smx_expand_pool_kernel writes the pool
+        int64_t compact_total = 0;
+        std::vector<int64_t> rsrc((size_t)n_refs), qsrc((size_t)n_qrys);
+        for (int r = 0; r < n_refs; ++r) { rsrc[(size_t)r] = compact_total; compact_total += ref_len[r]; }
+        for (int q = 0; q < n_qrys; ++q) { qsrc[(size_t)q] = compact_total; compact_total += qry_len[q]; }
+        if (int rc = ensure_pinned(h, h->pin_pool, (size_t)compact_total)) return rc;
+        uint8_t *stage = (uint8_t *)h->pin_pool.p;
+        std::vector<SmxExpandItem> items((size_t)n_refs + 2 * (size_t)n_qrys);
         for (int r = 0; r < n_refs; ++r) {
-            const uint8_t *s = ref_seqs + ref_off[r];
-            memcpy(&pool[(size_t)rpool[(size_t)r]], s, (size_t)ref_len[r]);
-            memcpy(&pool[(size_t)rpool[(size_t)r] + (size_t)ref_len[r]], s, (size_t)ref_len[r]);
+            memcpy(stage + rsrc[(size_t)r], ref_seqs + ref_off[r], (size_t)ref_len[r]);
+            items[(size_t)r] = SmxExpandItem{rsrc[(size_t)r], rpool[(size_t)r], ref_len[r], 0};
         }
         parallel_for(n_qrys, n_threads, [&](int q, int) {
-            const uint8_t *s = qry_seqs + qry_off[q];
-            const int L = qry_len[q];
-            uint8_t *f = &pool[(size_t)qpool[(size_t)q * 2]], *c = &pool[(size_t)qpool[(size_t)q * 2 + 1]];
-            memcpy(f, s, (size_t)L); memcpy(f + L, s, (size_t)L);
-            for (int i = 0; i < L; ++i) c[i] = g_comp[s[L - 1 - i]];
-            memcpy(c + L, c, (size_t)L);
+            memcpy(stage + qsrc[(size_t)q], qry_seqs + qry_off[q], (size_t)qry_len[q]);
+            items[(size_t)n_refs + 2 * (size_t)q] = SmxExpandItem{qsrc[(size_t)q], qpool[(size_t)q * 2], qry_len[q], 0};
+            items[(size_t)n_refs + 2 * (size_t)q + 1] = SmxExpandItem{qsrc[(size_t)q], qpool[(size_t)q * 2 + 1], qry_len[q], 1};
         });
-        if (int rc = smx_pool_upload(h, pool, total)) return rc;  // the pinned copy stays for the rare host re-decisions
+        if (int rc = ensure(h, h->pool, (size_t)total + 64)) return rc;
+        if (int rc = ensure(h, h->d_compact, (size_t)compact_total + 64)) return rc;
+        if (int rc = ensure(h, h->d_expand_items, sizeof(SmxExpandItem) * items.size())) return rc;
+        if (!h->d_comp.p) {
+            if (int rc = ensure(h, h->d_comp, 256)) return rc;
+            SMX_CUDA(h, cudaMemcpyAsync(h->d_comp.p, g_comp, 256, cudaMemcpyHostToDevice, h->stream_hi));
+        }
+        SMX_CUDA(h, cudaMemcpyAsync(h->d_compact.p, stage, (size_t)compact_total, cudaMemcpyHostToDevice, h->stream_hi));
+        if (int rc = h2d(h, PIN_EXPAND, h->d_expand_items.p, items.data(), sizeof(SmxExpandItem) * items.size(), h->stream_hi)) return rc;
+        smx_expand_pool_kernel<<<(unsigned)items.size(), 256, 0, h->stream_hi>>>((const uint8_t *)h->d_compact.p, (const SmxExpandItem *)h->d_expand_items.p,
+                                                                                (const uint8_t *)h->d_comp.p, (uint8_t *)h->pool.p);
+        SMX_CUDA(h, cudaGetLastError());
+        st.launches += 1;
+        if (int rc = pool_finish(h, total)) return rc;
     }
     st.t_pool = now_s() - t_begin;
     plog.cpu(h, "pool");
@@ -1089,6 +1128,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     std::vector<SmxSelOut> sel_out;
     std::vector<SmxRegion> redo;
     std::vector<int32_t> counts_host;
+    std::vector<uint8_t> redo_rc;
     while (pos < active.size()) {
         size_t end = pos;
         int64_t budget = 0;
@@ -1162,7 +1202,13 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
                 const SmxSelPair &s = sel_pairs[i];
                 counts_host.resize((size_t)s.max_k);
                 SMX_CUDA(h, cudaMemcpy(counts_host.data(), (const int32_t *)h->d_counts.p + s.counts_off, sizeof(int32_t) * (size_t)s.max_k, cudaMemcpyDeviceToHost));
-                host_regions((const uint8_t *)h->pin_pool.p + x.ref_pool, (const uint8_t *)h->pin_pool.p + x.qry_pool, x.nr, x.nq, topology, counts_host.data(),
+                const uint8_t *qp = qry_seqs + qry_off[x.qry];
+                if (x.strand) {  // the reverse-complement strand exists only on the device
+                    redo_rc.resize((size_t)x.nq);
+                    for (int t = 0; t < x.nq; ++t) redo_rc[(size_t)t] = g_comp[qp[x.nq - 1 - t]];
+                    qp = redo_rc.data();
+                }
+                host_regions(ref_seqs + ref_off[x.ref], qp, x.nr, x.nq, topology, counts_host.data(),
                              s.max_k, s.slice_lo, s.slice_hi, s.sigma, redo);
                 rg = redo.data(); nreg = (int)redo.size();
                 ++st.n_host_redo;
