@@ -45,6 +45,14 @@ DPX_PER_CELL_PACKED = 2.0  # VIMNMX.U16x2 per cell (4 per cell pair)
 TRACE_BYTES_PER_CELL = 0.5
 
 
+def usable_cores() -> int:
+    """cores this process may run on (taskset / cgroup cpusets), not the machine's core count"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -132,7 +140,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     plasmids, reads, _ = workload(0, args.reads)
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     n_sample = args.cpu_reads or max(4 * cores, 16)   # four reads per worker process: ~10 s of CPU work per step
     for _ in range(args.warmup):
         cpu_sample(plasmids, reads, min(2, n_sample), min(2, cores))
@@ -179,7 +187,7 @@ def run_engine(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     eng = Engine(local_rank)
     plasmids, reads, _ = workload(rank, args.reads)
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     # host stages need about three cores per GPU (measured); more threads per handle only add scheduling noise
     n_threads = args.threads or max(1, min(4, (cores // max(world, 1)) // 2))
     refs = [p.upper() for p in plasmids]

@@ -134,7 +134,8 @@ def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None,
     engines = _engines_for(eng, min(overlap, len(bounds) - 1))
     if n_threads <= 0:  # host stages need about three cores per GPU; every handle in flight runs its own pool
         import os
-        n_threads = max(1, min(4, (os.cpu_count() or 4) // len(engines)))
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
+        n_threads = max(1, min(4, cores // len(engines)))
     free = queue.SimpleQueue()
     for e in engines:
         free.put(e)
