@@ -982,7 +982,7 @@ const int kRegionCap = SMX_SEL_REGION_CAP;   // device slots per pair-strand (ov
 const int64_t kCountsBudget = 400ll << 20;  // int32 diagonal counts kept on the device per chunk
 // chain search: classes with fewer pair-strands than this many CTAs per SM spread the origins of a pair-strand over
 // several CTAs (a launch of few long CTAs is bound by its slowest CTA: 3.9 ms for 195 pair-strands of ~100 regions)
-const int kChainCtaTarget = []{ const char *e = getenv("SMX_CHAIN_CTAS"); const int v = e ? atoi(e) : 16; return v < 1 ? 1 : v; }();
+const int kChainCtaTarget = []{ const char *e = getenv("SMX_CHAIN_CTAS"); const int v = e ? atoi(e) : 32; return v < 1 ? 1 : v; }();
 
 uint8_t g_comp[256];
 bool g_comp_ready = false;
