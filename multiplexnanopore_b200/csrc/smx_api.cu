@@ -87,6 +87,7 @@ struct smx_handle {
     int64_t runs_scratch = 0;
     int64_t total_runs = -1;
     DevBuf d_probs, d_order_cls, d_order_all, d_results, d_trace, d_boundary, d_runs, d_dense, d_dense_off, d_tickets, d_slots;
+    int split_last = 1;  // SMX_S16H_SPLIT=0: lone last bands at K = 8 (cross-check)
     DevBuf d_compact, d_expand_items, d_comp;  // pipeline pool: sequences as given, expansion list, complement table
     std::vector<SmxResult> h_results;
     std::vector<int64_t> h_dense_off;
@@ -467,6 +468,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         if (const char *mr = getenv("SMX_S16_MINROWS")) { const int v = atoi(mr); if (v >= 32 && v <= 4096) h->s16_min_rows = v; }
         if (const char *tm = getenv("SMX_TEAM_MIN_MCELLS")) h->team_min_cells = (int64_t)atol(tm) << 20;
         { const char *pe = getenv("SMX_PERSISTENT"); h->persistent_fwd = pe && pe[0] == '1'; }
+        { const char *se = getenv("SMX_S16H_SPLIT"); h->split_last = !(se && se[0] == '0'); }
         const char *envh = getenv("SMX_S16H");
         h->use_s16h = !(envh && envh[0] == '0') && s16h_scoring_ok(h->sc);
         const char *mw = getenv("SMX_S16_MAXW");
@@ -636,6 +638,7 @@ static int launch_forward(smx_handle *h, const Chunk &c, int cls, int chunk_idx)
     a.sc = h->sc;
     a.one = 1u;
     a.max_tickets = INT32_MAX; a.n_slots = 0; a.slot_flags = nullptr;
+    a.split_last = 0;
     smx_dp_forward<K, LOCAL, TEAM><<<blocks, threads, 0, h->stream>>>(a);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
@@ -676,6 +679,7 @@ static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_id
     a.max_tickets = persistent ? INT32_MAX : 1;
     a.n_slots = kLineSlots;
     a.slot_flags = persistent ? nullptr : (int32_t *)h->d_slots.p;
+    a.split_last = h->split_last;
     kern<<<blocks, threads, 0, h->stream>>>(a);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
@@ -740,6 +744,7 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
         t.results = (SmxResult *)h->d_results.p;
         t.runs = (uint32_t *)h->d_runs.p;
         t.sc = h->sc;
+        t.split_last = h->use_s16h ? h->split_last : 0;
         const long long tb_threads = 32ll * c.n_big + (c.count - c.n_big);
         smx_traceback<<<(unsigned)((tb_threads + 127) / 128), 128, 0, h->stream>>>(t);
         SMX_CUDA(h, cudaGetLastError());

@@ -88,6 +88,7 @@ struct SmxFwdArgs {
     int32_t max_tickets;
     int32_t n_slots;
     int32_t *slot_flags;
+    int32_t split_last;  // smx_dp16h.cuh, W = 1: run a last band without a partner as two half-bands of 128 rows (K = 4)
 };
 
 #define SMX_TEAM_WARPS 8  // warps of a CTA that share one large problem (bands interleaved)

@@ -22,6 +22,7 @@ struct SmxTbArgs {
     SmxResult *results;
     uint32_t *runs;  // scratch, reversed order per problem
     SmxScoring sc;
+    int32_t split_last;  // class-10 problems with an odd band count keep their last band as two K = 4 half-bands (smx_dp16h.cuh)
 };
 
 __device__ __forceinline__ uint32_t smx_trace_nibble(const uint8_t *tr, int n, int kshift, int i, int j)
@@ -131,20 +132,29 @@ __global__ void __launch_bounds__(128) smx_traceback(const SmxTbArgs a)
     // more line and one word back).  Only a band crossing (every 32*K rows) recomputes the address.
     // Direction bits left L2 long ago: every move lowers the step index by 0..2, so the lines the walk is about
     // to touch are known without knowing the path and are prefetched SMX_TB_AHEAD lines ahead.
-    const int kshift = pr.kshift;
-    const int K = 1 << kshift;
-    const int wbytes = K >= 2 ? K >> 1 : 1;
-    const int rows_per_band = 32 << kshift;
-    const long long line = 32ll * wbytes;
-    const long long band_bytes = (long long)(n + 31) * line;
+    // A split last band (smx_dp16h.cuh): rows >= row_base use the K = 4 layout inside that band's region; the walk starts
+    // there (it starts in the last row or the last column) and switches to the problem's own layout when it leaves it.
+    const int nb8 = (m + 255) >> 8;
+    const bool split = a.split_last != 0 && pr.cls == 10 && (nb8 & 1);
+    const int R0 = split ? (nb8 - 1) * 256 : 0;
+    const uint8_t *const tr_split = tr + (long long)(nb8 - 1) * (long long)(n + 31) * 128;
+    int kshift = pr.kshift, row_base = 0;
+    const uint8_t *base = tr;
+    if (split && i >= R0) { kshift = 2; row_base = R0; base = tr_split; }
+    int K = 1 << kshift;
+    int wbytes = K >= 2 ? K >> 1 : 1;
+    int rows_per_band = 32 << kshift;
+    long long line = 32ll * wbytes;
+    long long band_bytes = (long long)(n + 31) * line;
     int lane_t = 0, k = 0;
     const uint8_t *wp = tr;
     if (i >= 0 && j >= 0) {
-        const int band = i / rows_per_band;
-        const int rin = i - band * rows_per_band;
+        const int ii = i - row_base;
+        const int band = ii / rows_per_band;
+        const int rin = ii - band * rows_per_band;
         lane_t = rin >> kshift;
         k = rin & (K - 1);
-        wp = tr + (long long)band * band_bytes + (long long)(j + lane_t) * line + (long long)lane_t * wbytes;
+        wp = base + (long long)band * band_bytes + (long long)(j + lane_t) * line + (long long)lane_t * wbytes;
     }
     while (local ? (i >= 0 && j >= 0) : (i >= 0 || j >= 0)) {
         if (i < 0) { w.emit(SMX_OP_D, j + 1); j = -1; break; }
@@ -186,8 +196,13 @@ __global__ void __launch_bounds__(128) smx_traceback(const SmxTbArgs a)
             if (k > 0) --k;
             else if (lane_t > 0) { --lane_t; k = K - 1; wp -= line + wbytes; }
             else if (i >= 0) {  // previous band: last lane, last row
+                if (i < row_base) {  // leaving the split last band: back to the problem's own layout
+                    kshift = pr.kshift; row_base = 0; base = tr;
+                    K = 1 << kshift; wbytes = K >= 2 ? K >> 1 : 1; rows_per_band = 32 << kshift;
+                    line = 32ll * wbytes; band_bytes = (long long)(n + 31) * line;
+                }
                 lane_t = 31; k = K - 1;
-                wp = tr + (long long)(i / rows_per_band) * band_bytes + (long long)(j + 31) * line + 31ll * wbytes;
+                wp = base + (long long)((i - row_base) / rows_per_band) * band_bytes + (long long)(j + 31) * line + 31ll * wbytes;
             }
         }
     }
