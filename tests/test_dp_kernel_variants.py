@@ -39,7 +39,7 @@ def _mixed_problems(seed, n=40, max_len=1400):
 
 
 @pytest.mark.parametrize("env", [dict(SMX_S16H="0"), dict(SMX_S16="0"), dict(SMX_PERSISTENT="1"), dict(SMX_S16_MINROWS="256"),
-                                 dict(SMX_S16_MAXW="1"), dict(SMX_S16_MAXW="8"), dict(SMX_TEAM_MIN_MCELLS="1")])
+                                 dict(SMX_S16_MAXW="1"), dict(SMX_S16_MAXW="8"), dict(SMX_TEAM_MIN_MCELLS="1"), dict(SMX_S16H_SPLIT="0")])
 def test_kernel_families_and_launch_modes(engine, env):
     probs, modes = _mixed_problems(61)
     with _Env(**env):
@@ -69,3 +69,23 @@ def test_value_range_ends(engine):
     modes = [0, 0, 1, 2, 0]
     run_and_compare(engine, probs, modes, (3, 1, 1, -2))
     run_and_compare(engine, probs[:2], modes[:2], (5, 2, 2, -3))
+
+
+@pytest.mark.parametrize("split", ["1", "0"])
+def test_split_last_band_row_counts(engine, split):
+    """A last band without a partner runs as two half-bands of 128 rows at 4 rows per lane (smx_dp16h.cuh) and keeps its
+    direction bits in the K = 4 layout, which the traceback enters and leaves: row counts around every boundary of
+    that scheme (one half-band, two half-bands, one and two full pairs in front), short and long references, all three
+    global / semi-global modes, with the split and without it (SMX_S16H_SPLIT=0)."""
+    rng = np.random.default_rng(63)
+    probs, modes = [], []
+    for m in (33, 127, 128, 129, 130, 255, 256, 257, 511, 512, 513, 639, 640, 641, 767, 768, 769, 1025, 1153, 1281):
+        for n in (40, 97, 700):
+            ref = util.rand_seq(rng, max(n, m) + 40)
+            q = util.mutate(rng, ref, 0.05, 0.04, 0.04)
+            q = (q * (m // max(1, len(q)) + 1))[:m]
+            for mode in (0, 1, 2):
+                probs.append((q, ref[:n]))
+                modes.append(mode)
+    with _Env(SMX_S16H_SPLIT=split):
+        run_and_compare(engine, probs, np.array(modes), (3, 1, 1, -2))
