@@ -15,6 +15,9 @@
 // and the integer ALU pipe -- two cycles per warp instruction, the binding resource of smx_dp16.cuh -- is left with
 // four VIMNMX.U16x2 and one PRMT per cell pair.
 //
+// A last band without a partner band (odd band count) runs as two half-bands of 128 rows at 4 rows per lane, see the
+// kernel; its direction bits then use the K = 4 layout inside that band's region of the arena.
+//
 // Eligibility (host, smx_api.cu: s16h_eligible): as smx_dp16.cuh, plus mismatch + 2*ge >= 0 (values never fall along
 // a diagonal), match + go + ge <= 127, and the biased range bound below 65000.
 #pragma once
@@ -266,158 +269,158 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
             unsigned short *const t16 = reinterpret_cast<unsigned short *>(trace + (size_t)band_lo * steps * 32);
             auto split_ptr_lo = [&](int s) { return t16 + ((long long)s * 32 + lane); };
             auto split_ptr_hi = [&](int s) { return t16 + ((long long)(steps + s - LAG) * 32 + lane); };
-                uint32_t plo[K], phi[K];
-                uint32_t Hc[K], El[K];
-    #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const int il = i0_lo + k, ih = i0_hi + k;
-                    plo[k] = smx16h_profile(il < m ? smx_code(s1[il]) : 4, ma2, mi2, wild2);
-                    phi[k] = smx16h_profile(ih < m ? smx_code(s1[ih]) : 4, ma2, mi2, wild2);
-                    Hc[k] = free_beg ? smx16h_pack(ge * il + u_free, ge * ih + u_free) : smx16h_pack(u_edge, u_edge);  // column -1
-                    El[k] = 0u;                                                                                        // E^ = -inf
-                }
-                // Hc(i0 - 1, -1): diagonal input of the first row at column 0
-                uint32_t hd = smx16h_pack(i0_lo == 0 ? u_corner : (free_beg ? ge * (i0_lo - 1) + u_free : u_edge),
-                                          free_beg ? ge * (i0_hi - 1) + u_free : u_edge);
-                uint32_t out_h = 0, out_f = 0, sel_prev = 0;
-                int rch1 = 0, rch2 = 0;  // reference codes of the two previous chunks (the high half reads 64 columns back)
-                const bool st_lo = lane == 31 && !lo_is_last, st_hi = lane == 31 && has_hi && !hi_is_last;
-                const bool track_lo = mode == 1 && lo_is_last, track_hi = mode == 1 && hi_is_last;
+            uint32_t plo[K], phi[K];
+            uint32_t Hc[K], El[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int il = i0_lo + k, ih = i0_hi + k;
+                plo[k] = smx16h_profile(il < m ? smx_code(s1[il]) : 4, ma2, mi2, wild2);
+                phi[k] = smx16h_profile(ih < m ? smx_code(s1[ih]) : 4, ma2, mi2, wild2);
+                Hc[k] = free_beg ? smx16h_pack(ge * il + u_free, ge * ih + u_free) : smx16h_pack(u_edge, u_edge);  // column -1
+                El[k] = 0u;                                                                                        // E^ = -inf
+            }
+            // Hc(i0 - 1, -1): diagonal input of the first row at column 0
+            uint32_t hd = smx16h_pack(i0_lo == 0 ? u_corner : (free_beg ? ge * (i0_lo - 1) + u_free : u_edge),
+                                      free_beg ? ge * (i0_hi - 1) + u_free : u_edge);
+            uint32_t out_h = 0, out_f = 0, sel_prev = 0;
+            int rch1 = 0, rch2 = 0;  // reference codes of the two previous chunks (the high half reads 64 columns back)
+            const bool st_lo = lane == 31 && !lo_is_last, st_hi = lane == 31 && has_hi && !hi_is_last;
+            const bool track_lo = mode == 1 && lo_is_last, track_hi = mode == 1 && hi_is_last;
 
-                for (int s0 = 0, chunk = 0; s0 < psteps; s0 += 32, ++chunk) {
-                    if (TEAM && pair > 0) {
-                        const int need = (pair - 1) * nchunks + min(chunk + 4, nchunks);
-                        if (lane == 0) { while (s_prog[(pair - 1) % W] < need) __nanosleep(64); }
-                        __syncwarp();
-                        __threadfence_block();
-                    }
+            for (int s0 = 0, chunk = 0; s0 < psteps; s0 += 32, ++chunk) {
+                if (TEAM && pair > 0) {
+                    const int need = (pair - 1) * nchunks + min(chunk + 4, nchunks);
+                    if (lane == 0) { while (s_prog[(pair - 1) % W] < need) __nanosleep(64); }
                     __syncwarp();
-                    // chunk prefetch: lane l holds column s0 + l (low band inputs) and column s0 + l - LAG (high band top line)
-                    const int jc = s0 + lane;
-                    const int jb = jc - LAG;
-                    // row above the low band / above the high band: (Hc, F^ = -inf); band 0 reads the matrix edge
-                    uint32_t topA = smx16h_pack(free_beg ? ge * jc + u_free : u_edge, 0);
-                    uint32_t topB = smx16h_pack(u_edge, 0);
-                    int rch0 = 0;
-                    if (jc < n) {
-                        if (band_lo != 0) topA = __ldcg(&top_lo[jc]);
-                        rch0 = smx_code(s2[jc]) & 3;
-                    }
-                    if (jb >= 0 && jb < n) topB = __ldcg(&top_hi[jb]);
-                    {
-                        const uint32_t c_lo = (uint32_t)rch0, c_hi = (uint32_t)rch2;
-                        uint4 tv;
-                        tv.x = (topA & 0xffffu) | (topB << 16);
-                        tv.y = (topA >> 16) | (topB & 0xffff0000u);
-                        tv.z = c_lo | ((c_lo | 8u) << 4) | ((c_hi | 4u) << 8) | ((c_hi | 12u) << 12);
-                        tv.w = 0u;
-                        s_top[wib][lane] = tv;
-                        __syncwarp();
-                    }
-                    if (s0 >= (has_hi ? 32 + LAG : 32) && s0 + 33 <= n) {  // a pair without a high band needs no lag (single-band problems)
-                        uint32_t *tp_lo = SPLIT ? reinterpret_cast<uint32_t *>(split_ptr_lo(s0)) : trace + ((size_t)band_lo * steps + s0) * 32 + lane;
-                        uint32_t *tp_hi = SPLIT ? reinterpret_cast<uint32_t *>(split_ptr_hi(s0)) : trace + ((size_t)band_hi * steps + (s0 - LAG)) * 32 + lane;
-                        uint32_t *bl = bot_lo + (s0 - 31);
-                        uint32_t *bh = bot_hi + (s0 - 31 - LAG);
-                        const uint32_t st_flags = (st_lo ? 1u : 0u) | (st_hi ? 2u : 0u);
-                        if (track_lo | track_hi) {
-                            const int jbase = s0 - lane - (track_lo ? 0 : LAG);
-                            const uint32_t tmask = lane == last_lane ? (track_lo ? 0x0000ffffu : 0xffff0000u) : 0u;
-                            const int tconst = hconst - ge * (m - 1);
-                            if (has_hi) smx16h_fast_chunk<K, true, true, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, ge, tconst, row_best, row_best_j, one);
-                            else smx16h_fast_chunk<K, false, true, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, ge, tconst, row_best, row_best_j, one);
-                        } else {
-                            if (has_hi) smx16h_fast_chunk<K, true, false, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one);
-                            else smx16h_fast_chunk<K, false, false, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one);
-                        }
-                    } else {
-                        const int send = min(32, psteps - s0);
-    #pragma unroll 1
-                        for (int ss = 0; ss < send; ++ss) {
-                            const int s = s0 + ss;
-                            uint32_t hu = __shfl_up_sync(SMX_FULL_MASK, out_h, 1);
-                            uint32_t fu = __shfl_up_sync(SMX_FULL_MASK, out_f, 1);
-                            uint32_t sel = __shfl_up_sync(SMX_FULL_MASK, sel_prev, 1);
-                            const uint4 tv = s_top[wib][ss];
-                            if (lane == 0) { hu = tv.x; fu = tv.y; sel = tv.z; }
-                            sel_prev = sel;
-                            const int j_lo = s - lane, j_hi = s - lane - LAG;
-                            const bool v_lo = j_lo >= 0 && j_lo < n;
-                            const bool v_hi = has_hi && j_hi >= 0 && j_hi < n;
-                            // Both halves are computed on every step (no divergence); a half whose column is still left of
-                            // the matrix produces values nobody reads, and its state is (re)set to the boundary column at
-                            // the step where it enters the matrix.  A half right of the matrix is finished.
-                            if (j_lo == 0 || j_hi == 0) {
-                                const uint32_t keep = j_lo == 0 ? 0xffff0000u : 0x0000ffffu;  // the other half keeps its state
-                                const int i0 = j_lo == 0 ? i0_lo : i0_hi;
-                                const int sh = j_lo == 0 ? 0 : 16;
-    #pragma unroll
-                                for (int k = 0; k < K; ++k) {
-                                    const uint32_t hv = (uint32_t)(free_beg ? ge * (i0 + k) + u_free : u_edge) & 0xffffu;
-                                    Hc[k] = (Hc[k] & keep) | (hv << sh);
-                                    El[k] = El[k] & keep;
-                                }
-                                const uint32_t hdv0 = (uint32_t)(i0 == 0 ? u_corner : (free_beg ? ge * (i0 - 1) + u_free : u_edge)) & 0xffffu;
-                                hd = (hd & keep) | (hdv0 << sh);
-                            }
-                            Smx16hCol c;
-                            c.hd = hd; c.fu = fu; c.hcu = hu; c.w_lo[0] = 0; c.w_lo[1] = 0; c.w_hi[0] = 0; c.w_hi[1] = 0; c.one = one;
-                            Smx16hCell<K, 0>::run(Hc, El, plo, phi, c, sel, negc2);
-                            hd = hu;  // Hc(i0-1, j) is the diagonal input of the next column
-                            out_h = c.hcu;
-                            out_f = c.fu;
-                            if (v_lo) {
-                                if (SPLIT) *split_ptr_lo(s) = (unsigned short)c.w_lo[0];
-                                else trace[((size_t)band_lo * steps + s) * 32 + lane] = c.w_lo[0] | c.w_lo[1];
-                                if (lane == 31 && !lo_is_last) __stcg(&bot_lo[j_lo], (out_h & 0xffffu) | (out_f << 16));
-                            }
-                            if (v_hi) {
-                                if (SPLIT) *split_ptr_hi(s) = (unsigned short)c.w_hi[0];
-                                else trace[((size_t)band_hi * steps + (s - LAG)) * 32 + lane] = c.w_hi[0] | c.w_hi[1];
-                                if (lane == 31 && !hi_is_last) __stcg(&bot_hi[j_hi], (out_h >> 16) | (out_f & 0xffff0000u));
-                            }
-                            // end-cell candidates (rare paths, scalar): back to H = half + hconst - ge * (i + j)
-                            if (v_lo && j_lo == n - 1) {
-    #pragma unroll
-                                for (int k = 0; k < K; ++k) {
-                                    const int i = i0_lo + k, hv = smx16h_lo(Hc[k]) + hconst - ge * (i + n - 1);
-                                    if (i < m - 1 && hv > col_best) { col_best = hv; col_best_i = i; }
-                                    if (i == m - 1) corner = hv;
-                                }
-                            }
-                            if (v_hi && j_hi == n - 1) {
-    #pragma unroll
-                                for (int k = 0; k < K; ++k) {
-                                    const int i = i0_hi + k, hv = smx16h_hi(Hc[k]) + hconst - ge * (i + n - 1);
-                                    if (i < m - 1 && hv > col_best) { col_best = hv; col_best_i = i; }
-                                    if (i == m - 1) corner = hv;
-                                }
-                            }
-                            if (mode == 1 && lane == last_lane) {
-                                if (lo_is_last && v_lo) {
-                                    uint32_t hw = Hc[0];
-    #pragma unroll
-                                    for (int k = 1; k < K; ++k) if (k == last_k) hw = Hc[k];
-                                    const int hv = smx16h_lo(hw) + hconst - ge * (m - 1 + j_lo);
-                                    if (hv > row_best) { row_best = hv; row_best_j = j_lo; }
-                                }
-                                if (hi_is_last && v_hi) {
-                                    uint32_t hw = Hc[0];
-    #pragma unroll
-                                    for (int k = 1; k < K; ++k) if (k == last_k) hw = Hc[k];
-                                    const int hv = smx16h_hi(hw) + hconst - ge * (m - 1 + j_hi);
-                                    if (hv > row_best) { row_best = hv; row_best_j = j_hi; }
-                                }
-                            }
-                        }
-                    }
-                    rch2 = rch1;
-                    rch1 = rch0;
-                    if (TEAM) {
-                        if (lane == 31) { __threadfence_block(); s_prog[wib] = pair * nchunks + chunk + 1; }
-                    }
+                    __threadfence_block();
                 }
                 __syncwarp();
+                // chunk prefetch: lane l holds column s0 + l (low band inputs) and column s0 + l - LAG (high band top line)
+                const int jc = s0 + lane;
+                const int jb = jc - LAG;
+                // row above the low band / above the high band: (Hc, F^ = -inf); band 0 reads the matrix edge
+                uint32_t topA = smx16h_pack(free_beg ? ge * jc + u_free : u_edge, 0);
+                uint32_t topB = smx16h_pack(u_edge, 0);
+                int rch0 = 0;
+                if (jc < n) {
+                    if (band_lo != 0) topA = __ldcg(&top_lo[jc]);
+                    rch0 = smx_code(s2[jc]) & 3;
+                }
+                if (jb >= 0 && jb < n) topB = __ldcg(&top_hi[jb]);
+                {
+                    const uint32_t c_lo = (uint32_t)rch0, c_hi = (uint32_t)rch2;
+                    uint4 tv;
+                    tv.x = (topA & 0xffffu) | (topB << 16);
+                    tv.y = (topA >> 16) | (topB & 0xffff0000u);
+                    tv.z = c_lo | ((c_lo | 8u) << 4) | ((c_hi | 4u) << 8) | ((c_hi | 12u) << 12);
+                    tv.w = 0u;
+                    s_top[wib][lane] = tv;
+                    __syncwarp();
+                }
+                if (s0 >= (has_hi ? 32 + LAG : 32) && s0 + 33 <= n) {  // a pair without a high band needs no lag (single-band problems)
+                    uint32_t *tp_lo = SPLIT ? reinterpret_cast<uint32_t *>(split_ptr_lo(s0)) : trace + ((size_t)band_lo * steps + s0) * 32 + lane;
+                    uint32_t *tp_hi = SPLIT ? reinterpret_cast<uint32_t *>(split_ptr_hi(s0)) : trace + ((size_t)band_hi * steps + (s0 - LAG)) * 32 + lane;
+                    uint32_t *bl = bot_lo + (s0 - 31);
+                    uint32_t *bh = bot_hi + (s0 - 31 - LAG);
+                    const uint32_t st_flags = (st_lo ? 1u : 0u) | (st_hi ? 2u : 0u);
+                    if (track_lo | track_hi) {
+                        const int jbase = s0 - lane - (track_lo ? 0 : LAG);
+                        const uint32_t tmask = lane == last_lane ? (track_lo ? 0x0000ffffu : 0xffff0000u) : 0u;
+                        const int tconst = hconst - ge * (m - 1);
+                        if (has_hi) smx16h_fast_chunk<K, true, true, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, ge, tconst, row_best, row_best_j, one);
+                        else smx16h_fast_chunk<K, false, true, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, ge, tconst, row_best, row_best_j, one);
+                    } else {
+                        if (has_hi) smx16h_fast_chunk<K, true, false, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one);
+                        else smx16h_fast_chunk<K, false, false, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one);
+                    }
+                } else {
+                    const int send = min(32, psteps - s0);
+#pragma unroll 1
+                    for (int ss = 0; ss < send; ++ss) {
+                        const int s = s0 + ss;
+                        uint32_t hu = __shfl_up_sync(SMX_FULL_MASK, out_h, 1);
+                        uint32_t fu = __shfl_up_sync(SMX_FULL_MASK, out_f, 1);
+                        uint32_t sel = __shfl_up_sync(SMX_FULL_MASK, sel_prev, 1);
+                        const uint4 tv = s_top[wib][ss];
+                        if (lane == 0) { hu = tv.x; fu = tv.y; sel = tv.z; }
+                        sel_prev = sel;
+                        const int j_lo = s - lane, j_hi = s - lane - LAG;
+                        const bool v_lo = j_lo >= 0 && j_lo < n;
+                        const bool v_hi = has_hi && j_hi >= 0 && j_hi < n;
+                        // Both halves are computed on every step (no divergence); a half whose column is still left of
+                        // the matrix produces values nobody reads, and its state is (re)set to the boundary column at
+                        // the step where it enters the matrix.  A half right of the matrix is finished.
+                        if (j_lo == 0 || j_hi == 0) {
+                            const uint32_t keep = j_lo == 0 ? 0xffff0000u : 0x0000ffffu;  // the other half keeps its state
+                            const int i0 = j_lo == 0 ? i0_lo : i0_hi;
+                            const int sh = j_lo == 0 ? 0 : 16;
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                const uint32_t hv = (uint32_t)(free_beg ? ge * (i0 + k) + u_free : u_edge) & 0xffffu;
+                                Hc[k] = (Hc[k] & keep) | (hv << sh);
+                                El[k] = El[k] & keep;
+                            }
+                            const uint32_t hdv0 = (uint32_t)(i0 == 0 ? u_corner : (free_beg ? ge * (i0 - 1) + u_free : u_edge)) & 0xffffu;
+                            hd = (hd & keep) | (hdv0 << sh);
+                        }
+                        Smx16hCol c;
+                        c.hd = hd; c.fu = fu; c.hcu = hu; c.w_lo[0] = 0; c.w_lo[1] = 0; c.w_hi[0] = 0; c.w_hi[1] = 0; c.one = one;
+                        Smx16hCell<K, 0>::run(Hc, El, plo, phi, c, sel, negc2);
+                        hd = hu;  // Hc(i0-1, j) is the diagonal input of the next column
+                        out_h = c.hcu;
+                        out_f = c.fu;
+                        if (v_lo) {
+                            if (SPLIT) *split_ptr_lo(s) = (unsigned short)c.w_lo[0];
+                            else trace[((size_t)band_lo * steps + s) * 32 + lane] = c.w_lo[0] | c.w_lo[1];
+                            if (lane == 31 && !lo_is_last) __stcg(&bot_lo[j_lo], (out_h & 0xffffu) | (out_f << 16));
+                        }
+                        if (v_hi) {
+                            if (SPLIT) *split_ptr_hi(s) = (unsigned short)c.w_hi[0];
+                            else trace[((size_t)band_hi * steps + (s - LAG)) * 32 + lane] = c.w_hi[0] | c.w_hi[1];
+                            if (lane == 31 && !hi_is_last) __stcg(&bot_hi[j_hi], (out_h >> 16) | (out_f & 0xffff0000u));
+                        }
+                        // end-cell candidates (rare paths, scalar): back to H = half + hconst - ge * (i + j)
+                        if (v_lo && j_lo == n - 1) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                const int i = i0_lo + k, hv = smx16h_lo(Hc[k]) + hconst - ge * (i + n - 1);
+                                if (i < m - 1 && hv > col_best) { col_best = hv; col_best_i = i; }
+                                if (i == m - 1) corner = hv;
+                            }
+                        }
+                        if (v_hi && j_hi == n - 1) {
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                const int i = i0_hi + k, hv = smx16h_hi(Hc[k]) + hconst - ge * (i + n - 1);
+                                if (i < m - 1 && hv > col_best) { col_best = hv; col_best_i = i; }
+                                if (i == m - 1) corner = hv;
+                            }
+                        }
+                        if (mode == 1 && lane == last_lane) {
+                            if (lo_is_last && v_lo) {
+                                uint32_t hw = Hc[0];
+#pragma unroll
+                                for (int k = 1; k < K; ++k) if (k == last_k) hw = Hc[k];
+                                const int hv = smx16h_lo(hw) + hconst - ge * (m - 1 + j_lo);
+                                if (hv > row_best) { row_best = hv; row_best_j = j_lo; }
+                            }
+                            if (hi_is_last && v_hi) {
+                                uint32_t hw = Hc[0];
+#pragma unroll
+                                for (int k = 1; k < K; ++k) if (k == last_k) hw = Hc[k];
+                                const int hv = smx16h_hi(hw) + hconst - ge * (m - 1 + j_hi);
+                                if (hv > row_best) { row_best = hv; row_best_j = j_hi; }
+                            }
+                        }
+                    }
+                }
+                rch2 = rch1;
+                rch1 = rch0;
+                if (TEAM) {
+                    if (lane == 31) { __threadfence_block(); s_prog[wib] = pair * nchunks + chunk + 1; }
+                }
+            }
+            __syncwarp();
         };
         for (int pair = wib % W; pair < npairs; pair += W) {
             if (SPLIT_OK && split && pair == npairs - 1) run_pair(std::integral_constant<int, 4>{}, std::true_type{}, pair);
