@@ -272,7 +272,7 @@ def run_engine(args, rank, world, local_rank):
         "peak_source": "measured live by smx_measure_int_peak: independent IADD3+LOP3 chains on all SMs (ALU and FMA pipes together, 128 lanes/clk/SM)",
         "algorithmic_ops_per_cell": ops_per_cell, "cells_per_launch": k8_cells / n_launch_k8, "launches": n_launch_k8,
         "kernel_ms_per_launch": k8_ms / n_launch_k8, "kernel_tcups": k8_tcups,
-        "note": "cells are the reference's m x n per problem; the kernel also computes the padding of the last band pair (14 % on this workload)",
+        "note": "cells are the reference's m x n per problem; the kernel also computes the band padding (17 % of the cells on this workload before lone last bands were moved to 4 rows per lane); the launch time is measured with the batches serialised, where it is bound by the largest problems of the batch (one warp each), so this is a lower bound of the sustained rate (DESIGN.md 3.1)",
         "dpx_view": {"achieved_tops": k8_tcups * DPX_PER_CELL_PACKED, "peak_tops": dpx_peak_tops,
                      "frac": k8_tcups * DPX_PER_CELL_PACKED / dpx_peak_tops if dpx_peak_tops else None,
                      "note": "VIMNMX.U16x2 lane-instructions against the measured DPX rate of the ALU pipe (64 lanes/clk/SM)"},
