@@ -320,26 +320,90 @@ inline int64_t aligned_offset_runs(const Runs &v, int64_t off, uint32_t mask)
     return a;
 }
 
+// Suffix sums over a run array: columns, I/S columns and D/H columns of runs[i..).  The fixed-point iterations of
+// get_aligned_ref_seq_offset / get_aligned_query_seq_offset ask for "how many I/S (D/H) columns among the last `a`
+// columns" about a dozen times per pair-strand; scanning the tail each time was most of the stitch stage (12 ns per run
+// and pair-strand), with the sums one pass and a binary search per question.
+struct TailSums {
+    std::vector<int64_t> cols, is, dh;  // size n + 1, entry n = 0
+    const Runs *v = nullptr;
+    void build(const Runs &runs)
+    {
+        v = &runs;
+        const size_t n = runs.size();
+        cols.resize(n + 1); is.resize(n + 1); dh.resize(n + 1);
+        int64_t c = 0, a = 0, b = 0;
+        cols[n] = 0; is[n] = 0; dh[n] = 0;
+        for (size_t i = n; i-- > 0;) {
+            const int64_t len = runs[i] >> 4;
+            const uint32_t op = runs[i] & 15u;
+            c += len;
+            if (op == 1u || op == 4u) a += len;
+            else if (op == 2u || op == 5u) b += len;
+            cols[i] = c; is[i] = a; dh[i] = b;
+        }
+    }
+    // columns among the last `a` columns that are I/S (which = 0) or D/H (which = 1); a beyond the length clamps
+    int64_t count(int64_t a, int which) const
+    {
+        if (a <= 0) return 0;
+        const std::vector<int64_t> &w = which ? dh : is;
+        const size_t n = v->size();
+        if (a >= cols[0]) return w[0];
+        // smallest i with cols[i] <= a (cols is non-increasing in i): runs i.. lie inside the tail entirely
+        size_t lo = 0, hi = n;
+        while (lo < hi) {
+            const size_t mid = (lo + hi) >> 1;
+            if (cols[mid] <= a) hi = mid; else lo = mid + 1;
+        }
+        int64_t cnt = w[lo];
+        if (lo > 0) {  // the run before contributes its last a - cols[lo] columns
+            const uint32_t op = (*v)[lo - 1] & 15u;
+            const bool hit = which ? (op == 2u || op == 5u) : (op == 1u || op == 4u);
+            if (hit) cnt += a - cols[lo];
+        }
+        return cnt;
+    }
+    int64_t aligned_offset(int64_t off, int which) const
+    {
+        if (off == 0) return 0;
+        int64_t a = off, prev = 0, cnt = count(a, which);
+        while (off != a - cnt) {
+            a += cnt - prev;
+            prev = cnt;
+            cnt = count(a, which);
+        }
+        return a;
+    }
+};
+
 // set_ref_seq_offset_as_0 on runs: rotates in place, returns new_query_seq_offset
 inline int64_t rotate_to_ref0_runs(Runs &v, int64_t ref_off, int64_t q_off)
 {
-    const uint32_t IS = (1u << 1) | (1u << 4), DH = (1u << 2) | (1u << 5);
-    const int64_t a_r = aligned_offset_runs(v, ref_off, IS);
-    const int64_t a_q = aligned_offset_runs(v, q_off, DH);
+    if (ref_off == 0 && q_off == 0) return 0;
+    thread_local TailSums ts;
+    ts.build(v);
+    const int64_t a_r = ts.aligned_offset(ref_off, 0);
+    const int64_t a_q = ts.aligned_offset(q_off, 1);
     const int64_t diff = a_q - a_r;
     int64_t new_off;
-    if (a_q > a_r) new_off = diff - (tail_count(v, a_q, DH) - tail_count(v, a_r, DH));
-    else if (a_q != 0) new_off = diff + (tail_count(v, a_r, DH) - tail_count(v, a_q, DH));
-    else if (a_r != 0) new_off = diff + tail_count(v, a_r, DH);
+    if (a_q > a_r) new_off = diff - (ts.count(a_q, 1) - ts.count(a_r, 1));
+    else if (a_q != 0) new_off = diff + (ts.count(a_r, 1) - ts.count(a_q, 1));
+    else if (a_r != 0) new_off = diff + ts.count(a_r, 1);
     else new_off = 0;
     if (a_r > 0) {
-        const int64_t n = total_columns(v);
+        const int64_t n = ts.cols[0];
         const int64_t head = a_r >= n ? 0 : n - a_r;  // columns that move to the back
         // v is maximal, so after cutting at column `head` only the wrap-around junction (old last run, old first
         // run) can merge; everything else moves as blocks
-        size_t idx = 0;
-        int64_t acc = 0;
-        while (idx < v.size() && acc + (int64_t)(v[idx] >> 4) <= head) { acc += v[idx] >> 4; ++idx; }
+        // idx = leading runs that lie before the cut entirely: the largest i with n - cols[i] <= head
+        size_t lo = 0, hi = v.size();
+        while (lo < hi) {  // smallest i with cols[i] < n - head
+            const size_t mid = (lo + hi) >> 1;
+            if (ts.cols[mid] < n - head) hi = mid; else lo = mid + 1;
+        }
+        const size_t idx = lo > 0 ? lo - 1 : 0;
+        const int64_t acc = n - ts.cols[idx];
         const int64_t part = head - acc;  // leading columns of v[idx] that still lie before the cut (they move to the back)
         if (idx > 0 || part > 0) {
             thread_local Runs tl_rot;
