@@ -104,6 +104,11 @@ def _engines_for(engine, n):
     pool = _engine_pools.setdefault(key, [engine])
     while len(pool) < n:
         pool.append(Engine(engine.device))
+    if n > 6:
+        # every handle grows its direction-bit arena up to its budget (16 GiB by default): more than six handles would
+        # not fit 180 GB next to the other workspaces, so the handles share 100 GiB (smaller chunks per batch)
+        for e in pool[:n]:
+            e.set_trace_budget(max(1 << 30, (100 << 30) // n))
     return pool[:n]
 
 
