@@ -59,7 +59,15 @@ def lib():
         _lib.pp_kmer_offset_scan.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
         _lib.pp_matrix_create.restype = None
         _lib.pp_matrix_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        _lib.pp_set_tie_rules.restype = None
+        _lib.pp_set_tie_rules.argtypes = [ctypes.c_int] * 4
     return _lib
+
+
+def set_tie_rules(gap_prefers_extend: int = 1, h_order_diag_f_e: int = 1, sg_end_order: int = 0, sw_end_order: int = 0):
+    """Flip the tie rules of parasail_port.c that could not be checked against a real parasail (defaults = what the
+    product implements).  Only oracle/tie_sensitivity.py and its test call this with non-default values."""
+    lib().pp_set_tie_rules(int(gap_prefers_extend), int(h_order_diag_f_e), int(sg_end_order), int(sw_end_order))
 
 
 def rle(ops: str) -> str:

@@ -28,13 +28,31 @@
 #include <string.h>
 
 /* ---- tie rules -------------------------------------- */
+/* Run-time switches, defaults = the rules the product implements.  oracle/tie_sensitivity.py
+ * flips them one at a time and counts how many reference-level results (CIGAR, score, offset)
+ * move: that table is what is at stake while no real parasail is reachable. */
 /* gap open vs extend: parasail tests `opn > ext ? DIAG_x : extend`  => tie goes to EXTEND */
-#define TIE_GAP_PREFERS_EXTEND 1
+static int TIE_GAP_PREFERS_EXTEND = 1;
 /* H source: DIAG if H == H_dag, else DEL (F, vertical, CIGAR 'I') if H == F, else INS (E, CIGAR 'D') */
-#define TIE_H_ORDER_DIAG_F_E 1
-/* sg_qe_de end cell: strict '>' scan, last column (rows ascending) first, then last row
- * (columns ascending) => on ties the last column beats the last row, smaller index wins */
-#define TIE_SG_END_COLUMN_FIRST 1
+static int TIE_H_ORDER_DIAG_F_E = 1;
+/* sg_qe_de end cell, always strict '>' and ascending indices inside a pass:
+ *   0 (default): last column rows 0..m-2, then last row columns 0..n-1 (the corner is the LAST
+ *                candidate: a tied earlier last-row cell beats it) -- the loop structure of
+ *                parasail's serial sg code (`for i < s1Len` main loop, then a separate last-row block)
+ *   1          : last column rows 0..m-1 (corner included), then last row 0..n-2 (SURVEY A.6 as written:
+ *                the corner beats a tied last-row cell)
+ *   2          : last row first, then last column (the order of the striped SIMD kernels) */
+static int TIE_SG_END_ORDER = 0;
+/* sw end cell: 0 (default) first maximum in row-major order; 1 smallest end_ref, then smallest end_query */
+static int TIE_SW_END_ORDER = 0;
+
+void pp_set_tie_rules(int gap_prefers_extend, int h_order_diag_f_e, int sg_end_order, int sw_end_order)
+{
+    TIE_GAP_PREFERS_EXTEND = gap_prefers_extend;
+    TIE_H_ORDER_DIAG_F_E = h_order_diag_f_e;
+    TIE_SG_END_ORDER = sg_end_order;
+    TIE_SW_END_ORDER = sw_end_order;
+}
 
 /* trace byte layout (parasail.h): low 3 bits = H source, then E and F sources */
 enum { T_ZERO = 0, T_INS = 1, T_DEL = 2, T_DIAG = 4, T_DIAG_E = 8, T_INS_E = 16, T_DIAG_F = 32, T_DEL_F = 64 };
@@ -96,7 +114,8 @@ int pp_align(int mode, const char *s1, int len1, const char *s2, int len2,
     int32_t *H = (int32_t *)malloc(sizeof(int32_t) * ((size_t)len2 + 1));
     int32_t *F = (int32_t *)malloc(sizeof(int32_t) * ((size_t)len2 + 1));
     uint8_t *HT = (uint8_t *)malloc((size_t)len1 * (size_t)len2);
-    if (!a || !b || !H || !F || !HT) { free(a); free(b); free(H); free(F); free(HT); return -1; }
+    int32_t *lastcol = (int32_t *)malloc(sizeof(int32_t) * (size_t)len1);
+    if (!a || !b || !H || !F || !HT || !lastcol) { free(a); free(b); free(H); free(F); free(HT); free(lastcol); return -1; }
     for (int i = 0; i < len1; ++i) a[i] = (uint8_t)map_base((unsigned char)s1[i]);
     for (int j = 0; j < len2; ++j) b[j] = (uint8_t)map_base((unsigned char)s2[j]);
 
@@ -124,13 +143,13 @@ int pp_align(int mode, const char *s1, int len1, const char *s2, int len2,
             int32_t F_opn = NH - open, F_ext = F[j] - gap;
             int32_t E_opn = WH - open, E_ext = E - gap;
             uint8_t t;
-#if TIE_GAP_PREFERS_EXTEND
-            if (F_opn > F_ext) { F[j] = F_opn; t = T_DIAG_F; } else { F[j] = F_ext; t = T_DEL_F; }
-            if (E_opn > E_ext) { E = E_opn; t |= T_DIAG_E; } else { E = E_ext; t |= T_INS_E; }
-#else
-            if (F_opn >= F_ext) { F[j] = F_opn; t = T_DIAG_F; } else { F[j] = F_ext; t = T_DEL_F; }
-            if (E_opn >= E_ext) { E = E_opn; t |= T_DIAG_E; } else { E = E_ext; t |= T_INS_E; }
-#endif
+            if (TIE_GAP_PREFERS_EXTEND) {
+                if (F_opn > F_ext) { F[j] = F_opn; t = T_DIAG_F; } else { F[j] = F_ext; t = T_DEL_F; }
+                if (E_opn > E_ext) { E = E_opn; t |= T_DIAG_E; } else { E = E_ext; t |= T_INS_E; }
+            } else {
+                if (F_opn >= F_ext) { F[j] = F_opn; t = T_DIAG_F; } else { F[j] = F_ext; t = T_DEL_F; }
+                if (E_opn >= E_ext) { E = E_opn; t |= T_DIAG_E; } else { E = E_ext; t |= T_INS_E; }
+            }
             int32_t H_dag = NWH + mrow[b[j - 1]];
             int32_t Fv = F[j];
             WH = H_dag;
@@ -141,35 +160,43 @@ int pp_align(int mode, const char *s1, int len1, const char *s2, int len2,
                 /* parasail sw: a cell whose value is 0 stops the walk */
                 t |= T_ZERO;
             } else {
-#if TIE_H_ORDER_DIAG_F_E
-                if (WH == H_dag) t |= T_DIAG; else if (WH == Fv) t |= T_DEL; else t |= T_INS;
-#else
-                if (WH == H_dag) t |= T_DIAG; else if (WH == E) t |= T_INS; else t |= T_DEL;
-#endif
+                if (WH == H_dag) t |= T_DIAG;
+                else if (TIE_H_ORDER_DIAG_F_E) t |= (WH == Fv) ? T_DEL : T_INS;
+                else t |= (WH == E) ? T_INS : T_DEL;
             }
             H[j] = WH;
             trow[j - 1] = t;
-            if (local && WH > best) { best = WH; end_q = i - 1; end_r = j - 1; }
+            if (local && (WH > best || (TIE_SW_END_ORDER == 1 && WH == best && best > 0 && j - 1 < end_r))) {
+                best = WH; end_q = i - 1; end_r = j - 1;
+            }
         }
-        if (free_end && i < len1) {
-            /* last column candidate, rows ascending, strict '>' */
-            if (WH > best) { best = WH; end_q = i - 1; end_r = len2 - 1; }
-        }
+        if (free_end) lastcol[i - 1] = WH;
     }
     if (free_end) {
-#if TIE_SG_END_COLUMN_FIRST
-        for (int j = 1; j <= len2; ++j)
-            if (H[j] > best) { best = H[j]; end_q = len1 - 1; end_r = j - 1; }
-#else
-#error "alternative end-cell order not implemented"
-#endif
+        /* candidates: last column H(i, len2) for i = 1..len1 (kept in lastcol), last row H(len1, j) = H[j] */
+        if (TIE_SG_END_ORDER == 0) {
+            for (int i = 1; i < len1; ++i)
+                if (lastcol[i - 1] > best) { best = lastcol[i - 1]; end_q = i - 1; end_r = len2 - 1; }
+            for (int j = 1; j <= len2; ++j)
+                if (H[j] > best) { best = H[j]; end_q = len1 - 1; end_r = j - 1; }
+        } else if (TIE_SG_END_ORDER == 1) {
+            for (int i = 1; i <= len1; ++i)
+                if (lastcol[i - 1] > best) { best = lastcol[i - 1]; end_q = i - 1; end_r = len2 - 1; }
+            for (int j = 1; j < len2; ++j)
+                if (H[j] > best) { best = H[j]; end_q = len1 - 1; end_r = j - 1; }
+        } else {
+            for (int j = 1; j <= len2; ++j)
+                if (H[j] > best) { best = H[j]; end_q = len1 - 1; end_r = j - 1; }
+            for (int i = 1; i < len1; ++i)
+                if (lastcol[i - 1] > best) { best = lastcol[i - 1]; end_q = i - 1; end_r = len2 - 1; }
+        }
     } else if (!local) {
         best = H[len2]; end_q = len1 - 1; end_r = len2 - 1;
     }
 
     /* ---- traceback (parasail cigar_template.c); ops are produced reversed ---- */
     char *rev = (char *)malloc((size_t)len1 + (size_t)len2 + 2);
-    if (!rev) { free(a); free(b); free(H); free(F); free(HT); return -1; }
+    if (!rev) { free(a); free(b); free(H); free(F); free(HT); free(lastcol); return -1; }
     int64_t n = 0;
     int i = end_q, j = end_r;
     if (free_end) {
@@ -203,7 +230,7 @@ int pp_align(int mode, const char *s1, int len1, const char *s2, int len2,
     res->n_ops = n;
     for (int64_t k = 0; k < n; ++k) ops_out[k] = rev[n - 1 - k];
 
-    free(rev); free(a); free(b); free(H); free(F); free(HT);
+    free(rev); free(a); free(b); free(H); free(F); free(HT); free(lastcol);
     return 0;
 }
 
