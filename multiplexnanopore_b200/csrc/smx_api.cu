@@ -713,6 +713,7 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
     if (gate) gate->enter();
     SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     SMX_CUDA(h, cudaMemsetAsync(h->d_tickets.p, 0, sizeof(int32_t) * kNumFwdClasses * h->chunks.size(), h->stream));
+    SMX_CUDA(h, cudaMemsetAsync(h->d_slots.p, 0, sizeof(int32_t) * kLineSlots, h->stream));  // an aborted launch must not leave lines claimed
     h->ev_used = 0;
     for (int c = 0; c < kNumSlots; ++c) { h->kernel_ms[c] = 0.0; h->kernel_launches[c] = 0; }
     if (int rc = mark(h, -1)) return rc;
@@ -989,16 +990,22 @@ const int64_t kCountsBudget = 400ll << 20;  // int32 diagonal counts kept on the
 // several CTAs (a launch of few long CTAs is bound by its slowest CTA: 3.9 ms for 195 pair-strands of ~100 regions)
 const int kChainCtaTarget = []{ const char *e = getenv("SMX_CHAIN_CTAS"); const int v = e ? atoi(e) : 32; return v < 1 ? 1 : v; }();
 
-uint8_t g_comp[256];
-bool g_comp_ready = false;
-void init_comp()
+// complement table, built once (thread-safe magic static: several handles call smx_pipeline_run concurrently) and
+// never rewritten after publication
+struct CompTable {
+    uint8_t t[256];
+    CompTable()
+    {
+        for (int i = 0; i < 256; ++i) t[i] = (uint8_t)i;
+        // Bio.Seq.reverse_complement (my_classes.py:306-310): IUPAC-aware
+        const char *a = "ACGTMRWSYKVHDBN", *b = "TGCAKYWSRMBDHVN";
+        for (int i = 0; a[i]; ++i) t[(uint8_t)a[i]] = (uint8_t)b[i];
+    }
+};
+const uint8_t *comp_table()
 {
-    if (g_comp_ready) return;
-    for (int i = 0; i < 256; ++i) g_comp[i] = (uint8_t)i;
-    // Bio.Seq.reverse_complement (my_classes.py:306-310): IUPAC-aware
-    const char *a = "ACGTMRWSYKVHDBN", *b = "TGCAKYWSRMBDHVN";
-    for (int i = 0; a[i]; ++i) g_comp[(uint8_t)a[i]] = (uint8_t)b[i];
-    g_comp_ready = true;
+    static const CompTable tab;
+    return tab.t;
 }
 
 }  // namespace
@@ -1051,8 +1058,8 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         return fail(h, -1, "smx_pipeline_run: NULL or empty input");
     if (topology != 0 && topology != 1) return fail(h, -1, "unknown topology_of_dna: %d (ref_query_alignment.py:215)", topology);
     if ((pair_ref == nullptr) != (pair_qry == nullptr)) return fail(h, -1, "pair_ref and pair_qry must both be given or both be NULL");
-    if (n_threads <= 0) n_threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    init_comp();
+    if (n_threads <= 0) n_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));  // several handles may run per GPU: never every core per handle
+    const uint8_t *const g_comp = comp_table();
     PhaseLog plog;
     const double t_begin = now_s();
     SMX_CUDA(h, cudaSetDevice(h->device));
@@ -1064,7 +1071,9 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     for (int r = 0; r < n_refs; ++r) { if (ref_len[r] <= 0) return fail(h, -1, "reference %d is empty", r); rpool[(size_t)r] = total; total += 2ll * ref_len[r]; }
     for (int q = 0; q < n_qrys; ++q) {
         if (qry_len[q] <= 0) return fail(h, -1, "query %d is empty", q);
-        if (qry_len[q] > 65535) return fail(h, -1, "query %d: %d bases; this engine supports reads up to 65535 bases", q, qry_len[q]);
+        // reads of more than 65535 bases: the select kernel hands their pair-strands to the host re-decision (its
+        // histogram median holds 16-bit counts); with omit_too_long they are usually dropped before the scan (:207)
+        if (qry_len[q] > (1 << 24)) return fail(h, -1, "query %d: %d bases; this engine supports reads up to 16 Mi bases", q, qry_len[q]);
         qpool[(size_t)q * 2] = total; total += 2ll * qry_len[q];
         qpool[(size_t)q * 2 + 1] = total; total += 2ll * qry_len[q];
     }
@@ -1126,6 +1135,8 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     const bool force_host_select = [] { const char *e = getenv("SMX_SELECT"); return e && std::string(e) == "host"; }();  // cross-check switch
     std::vector<int> active;
     for (size_t i = 0; i < st.ps.size(); ++i) if (!st.ps[i].skip) active.push_back((int)i);
+    for (int i : active)  // the scan stages the whole query in shared memory as bit planes (20 bytes per 32 bases)
+        if (st.ps[(size_t)i].nq > 300000) return fail(h, -1, "query %d: %d bases are aligned against a reference of %d; the scan supports reads up to 300000 bases", st.ps[(size_t)i].qry, st.ps[(size_t)i].nq, st.ps[(size_t)i].nr);
     size_t pos = 0;
     std::vector<int64_t> s_roff, s_qoff, c_off;
     std::vector<int32_t> s_rlen, s_qlen;

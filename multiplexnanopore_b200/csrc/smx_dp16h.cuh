@@ -69,10 +69,21 @@ struct Smx16hCol {  // per-column scalars threaded through the K cells of a lane
     uint32_t one;
 };
 
-template <int K, int k>
+// EDGE: a chunk in which some lane's half is not inside the matrix (column < 0 or >= n).  Such a half HOLDS its state:
+// `hold` has 0xffff in every half that is inside, and the new state is merged as (new & hold) | (old & ~hold) -- one
+// LOP3 per state register.  A half therefore sits at its boundary-column values until it enters and at its
+// column n - 1 values after it has left (the end-cell candidates are read there once per band pair).
+__device__ __forceinline__ uint32_t smx16h_merge(uint32_t nv, uint32_t ov, uint32_t hold)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(r) : "r"(hold), "r"(nv), "r"(ov));  // hold ? nv : ov, bitwise
+    return r;
+}
+
+template <int K, int k, bool EDGE = false>
 struct Smx16hCell {
     static __device__ __forceinline__ void run(uint32_t (&Hc)[K], uint32_t (&El)[K], const uint32_t (&plo)[K], const uint32_t (&phi)[K],
-                                               Smx16hCol &c, uint32_t sel, uint32_t negc2)
+                                               Smx16hCol &c, uint32_t sel, uint32_t negc2, uint32_t hold = 0xffffffffu)
     {
         constexpr int A = K == 8 ? (k & 1) : (k >> 3);
         constexpr int SH = 4 * (k & 7);
@@ -85,17 +96,17 @@ struct Smx16hCell {
         const uint32_t h = smx16h_max_tr<(1u << SH), (SMX16H_ALU_FLAGS < 4)>(hdiag, t, n_lo, n_hi, c.one);
         const uint32_t hc = h + negc2;  // - (go - ge) in both halves; the low half never borrows (bias)
         c.hd = Hc[k];
-        Hc[k] = hc;
-        El[k] = e;
+        Hc[k] = EDGE ? smx16h_merge(hc, Hc[k], hold) : hc;
+        El[k] = EDGE ? smx16h_merge(e, El[k], hold) : e;
         c.fu = f;
         c.hcu = hc;
-        Smx16hCell<K, k + 1>::run(Hc, El, plo, phi, c, sel, negc2);
+        Smx16hCell<K, k + 1, EDGE>::run(Hc, El, plo, phi, c, sel, negc2, hold);
     }
 };
-template <int K>
-struct Smx16hCell<K, K> {
+template <int K, bool EDGE>
+struct Smx16hCell<K, K, EDGE> {
     static __device__ __forceinline__ void run(uint32_t (&)[K], uint32_t (&)[K], const uint32_t (&)[K], const uint32_t (&)[K], Smx16hCol &, uint32_t,
-                                               uint32_t) {}
+                                               uint32_t, uint32_t = 0) {}
 };
 
 // per-row substitution profile in the diagonal frame: byte c = s(query base, reference code c) + go + ge (0..127);
@@ -166,6 +177,60 @@ __device__ __forceinline__ void smx16h_fast_chunk(uint32_t (&Hc)[K], uint32_t (&
     }
 }
 
+
+// One 32-step chunk at an edge of the matrix (see Smx16hCell<EDGE>): the interior chunk plus the hold masks, per-lane
+// predicates on the direction-word and boundary-line stores, and validity on the last-row tracking.  `jl0` = column
+// of this lane's low half at the first step of the chunk (the high half is LAG columns behind).
+template <int K, bool HAS_HI, bool SPLIT>
+__device__ __forceinline__ void smx16h_edge_chunk(uint32_t (&Hc)[K], uint32_t (&El)[K], const uint32_t (&plo)[K], const uint32_t (&phi)[K],
+                                                  uint32_t &hd, uint32_t &out_h, uint32_t &out_f, uint32_t &sel_prev, const uint4 *tops,
+                                                  uint32_t lane0_mask, uint32_t negc2, uint32_t *tp_lo, uint32_t *tp_hi, uint32_t *bl, uint32_t *bh,
+                                                  uint32_t st_flags, uint32_t tmask, int last_k, int jl0, int n, int ge, int tconst, int &row_best,
+                                                  int &row_best_j, uint32_t one)
+{
+#pragma unroll 1
+    for (int ss = 0; ss < 32; ++ss) {
+        uint32_t hu = __shfl_up_sync(SMX_FULL_MASK, out_h, 1);
+        uint32_t fu = __shfl_up_sync(SMX_FULL_MASK, out_f, 1);
+        uint32_t sel = __shfl_up_sync(SMX_FULL_MASK, sel_prev, 1);
+        const uint4 tv = tops[ss];
+        hu = (tv.x & lane0_mask) | (hu & ~lane0_mask);
+        fu = (tv.y & lane0_mask) | (fu & ~lane0_mask);
+        sel = (tv.z & lane0_mask) | (sel & ~lane0_mask);
+        sel_prev = sel;
+        const int j_lo = jl0 + ss, j_hi = j_lo - SMX16_LAG;
+        const bool v_lo = (unsigned)j_lo < (unsigned)n;
+        const bool v_hi = HAS_HI && (unsigned)j_hi < (unsigned)n;
+        const uint32_t hold = (v_lo ? 0x0000ffffu : 0u) | (v_hi ? 0xffff0000u : 0u);
+        Smx16hCol c;
+        c.hd = hd; c.fu = fu; c.hcu = hu; c.w_lo[0] = 0; c.w_lo[1] = 0; c.w_hi[0] = 0; c.w_hi[1] = 0; c.one = one;
+        Smx16hCell<K, 0, true>::run(Hc, El, plo, phi, c, sel, negc2, hold);
+        hd = smx16h_merge(hu, hd, hold);
+        out_h = c.hcu;
+        out_f = c.fu;
+        if (SPLIT) {
+            if (v_lo) reinterpret_cast<unsigned short *>(tp_lo)[ss * 32] = (unsigned short)c.w_lo[0];
+            if (v_hi) reinterpret_cast<unsigned short *>(tp_hi)[ss * 32] = (unsigned short)c.w_hi[0];
+        } else {
+            if (v_lo) tp_lo[ss * 32] = c.w_lo[0] | c.w_lo[1];
+            if (v_hi) tp_hi[ss * 32] = c.w_hi[0] | c.w_hi[1];
+        }
+        if ((st_flags & 1u) && v_lo) __stcg(&bl[ss], __byte_perm(out_h, out_f, 0x5410));
+        if (HAS_HI) { if ((st_flags & 2u) && v_hi) __stcg(&bh[ss], __byte_perm(out_h, out_f, 0x7632)); }
+        if (tmask) {  // the lane that owns the last query row (semi-global end in the last row)
+            const bool lo_tr = (tmask & 1u) != 0;
+            if (lo_tr ? v_lo : v_hi) {
+                uint32_t hw = Hc[0];
+#pragma unroll
+                for (int k = 1; k < K; ++k) if (k == last_k) hw = Hc[k];
+                const int jj = lo_tr ? j_lo : j_hi;
+                const int hv = (lo_tr ? smx16h_lo(hw) : smx16h_hi(hw)) - ge * jj + tconst;
+                if (hv > row_best) { row_best = hv; row_best_j = jj; }
+            }
+        }
+    }
+}
+
 // boundary lines: one uint32 per column = F^ << 16 | Hc (biased unsigned halves)
 template <int W>
 __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM / (W == 1 ? 4 : W)) smx_dp_forward16h(const SmxFwdArgs a)
@@ -184,6 +249,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
             asm("mov.u32 %0, %%smid;" : "=r"(smid));
             int sl = (int)((smid * 61u + (unsigned)worker * 17u) % (unsigned)a.n_slots);
             while (atomicCAS(&a.slot_flags[sl], 0, 1) != 0) sl = sl + 1 == a.n_slots ? 0 : sl + 1;
+            __threadfence();  // acquire: the previous owner's line stores are ordered before ours
             s_slot[TEAM ? 0 : wib] = sl;
         }
         if (TEAM) __syncthreads(); else __syncwarp();
@@ -334,90 +400,37 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
                         else smx16h_fast_chunk<K, false, false, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one);
                     }
                 } else {
-                    const int send = min(32, psteps - s0);
-#pragma unroll 1
-                    for (int ss = 0; ss < send; ++ss) {
-                        const int s = s0 + ss;
-                        uint32_t hu = __shfl_up_sync(SMX_FULL_MASK, out_h, 1);
-                        uint32_t fu = __shfl_up_sync(SMX_FULL_MASK, out_f, 1);
-                        uint32_t sel = __shfl_up_sync(SMX_FULL_MASK, sel_prev, 1);
-                        const uint4 tv = s_top[wib][ss];
-                        if (lane == 0) { hu = tv.x; fu = tv.y; sel = tv.z; }
-                        sel_prev = sel;
-                        const int j_lo = s - lane, j_hi = s - lane - LAG;
-                        const bool v_lo = j_lo >= 0 && j_lo < n;
-                        const bool v_hi = has_hi && j_hi >= 0 && j_hi < n;
-                        // Both halves are computed on every step (no divergence); a half whose column is still left of
-                        // the matrix produces values nobody reads, and its state is (re)set to the boundary column at
-                        // the step where it enters the matrix.  A half right of the matrix is finished.
-                        if (j_lo == 0 || j_hi == 0) {
-                            const uint32_t keep = j_lo == 0 ? 0xffff0000u : 0x0000ffffu;  // the other half keeps its state
-                            const int i0 = j_lo == 0 ? i0_lo : i0_hi;
-                            const int sh = j_lo == 0 ? 0 : 16;
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                const uint32_t hv = (uint32_t)(free_beg ? ge * (i0 + k) + u_free : u_edge) & 0xffffu;
-                                Hc[k] = (Hc[k] & keep) | (hv << sh);
-                                El[k] = El[k] & keep;
-                            }
-                            const uint32_t hdv0 = (uint32_t)(i0 == 0 ? u_corner : (free_beg ? ge * (i0 - 1) + u_free : u_edge)) & 0xffffu;
-                            hd = (hd & keep) | (hdv0 << sh);
-                        }
-                        Smx16hCol c;
-                        c.hd = hd; c.fu = fu; c.hcu = hu; c.w_lo[0] = 0; c.w_lo[1] = 0; c.w_hi[0] = 0; c.w_hi[1] = 0; c.one = one;
-                        Smx16hCell<K, 0>::run(Hc, El, plo, phi, c, sel, negc2);
-                        hd = hu;  // Hc(i0-1, j) is the diagonal input of the next column
-                        out_h = c.hcu;
-                        out_f = c.fu;
-                        if (v_lo) {
-                            if (SPLIT) *split_ptr_lo(s) = (unsigned short)c.w_lo[0];
-                            else trace[((size_t)band_lo * steps + s) * 32 + lane] = c.w_lo[0] | c.w_lo[1];
-                            if (lane == 31 && !lo_is_last) __stcg(&bot_lo[j_lo], (out_h & 0xffffu) | (out_f << 16));
-                        }
-                        if (v_hi) {
-                            if (SPLIT) *split_ptr_hi(s) = (unsigned short)c.w_hi[0];
-                            else trace[((size_t)band_hi * steps + (s - LAG)) * 32 + lane] = c.w_hi[0] | c.w_hi[1];
-                            if (lane == 31 && !hi_is_last) __stcg(&bot_hi[j_hi], (out_h >> 16) | (out_f & 0xffff0000u));
-                        }
-                        // end-cell candidates (rare paths, scalar): back to H = half + hconst - ge * (i + j)
-                        if (v_lo && j_lo == n - 1) {
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                const int i = i0_lo + k, hv = smx16h_lo(Hc[k]) + hconst - ge * (i + n - 1);
-                                if (i < m - 1 && hv > col_best) { col_best = hv; col_best_i = i; }
-                                if (i == m - 1) corner = hv;
-                            }
-                        }
-                        if (v_hi && j_hi == n - 1) {
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                const int i = i0_hi + k, hv = smx16h_hi(Hc[k]) + hconst - ge * (i + n - 1);
-                                if (i < m - 1 && hv > col_best) { col_best = hv; col_best_i = i; }
-                                if (i == m - 1) corner = hv;
-                            }
-                        }
-                        if (mode == 1 && lane == last_lane) {
-                            if (lo_is_last && v_lo) {
-                                uint32_t hw = Hc[0];
-#pragma unroll
-                                for (int k = 1; k < K; ++k) if (k == last_k) hw = Hc[k];
-                                const int hv = smx16h_lo(hw) + hconst - ge * (m - 1 + j_lo);
-                                if (hv > row_best) { row_best = hv; row_best_j = j_lo; }
-                            }
-                            if (hi_is_last && v_hi) {
-                                uint32_t hw = Hc[0];
-#pragma unroll
-                                for (int k = 1; k < K; ++k) if (k == last_k) hw = Hc[k];
-                                const int hv = smx16h_hi(hw) + hconst - ge * (m - 1 + j_hi);
-                                if (hv > row_best) { row_best = hv; row_best_j = j_hi; }
-                            }
-                        }
-                    }
+                    // edge chunk: halves outside the matrix hold their state (smx16h_edge_chunk)
+                    uint32_t *tp_lo = SPLIT ? reinterpret_cast<uint32_t *>(split_ptr_lo(s0)) : trace + ((long long)band_lo * steps + s0) * 32 + lane;
+                    uint32_t *tp_hi = SPLIT ? reinterpret_cast<uint32_t *>(split_ptr_hi(s0)) : trace + ((long long)band_hi * steps + (s0 - LAG)) * 32 + lane;
+                    uint32_t *bl = bot_lo + (s0 - 31);
+                    uint32_t *bh = bot_hi + (s0 - 31 - LAG);
+                    const uint32_t st_flags = (st_lo ? 1u : 0u) | (st_hi ? 2u : 0u);
+                    const uint32_t tmask = (track_lo | track_hi) && lane == last_lane ? (track_lo ? 0x0000ffffu : 0xffff0000u) : 0u;
+                    const int tconst = hconst - ge * (m - 1);
+                    if (has_hi) smx16h_edge_chunk<K, true, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, s0 - lane, n, ge, tconst, row_best, row_best_j, one);
+                    else smx16h_edge_chunk<K, false, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, s0 - lane, n, ge, tconst, row_best, row_best_j, one);
                 }
                 rch2 = rch1;
                 rch1 = rch0;
                 if (TEAM) {
                     if (lane == 31) { __threadfence_block(); s_prog[wib] = pair * nchunks + chunk + 1; }
+                }
+            }
+            // end-cell candidates (last column): every half has held its column n - 1 values since it left the matrix.
+            // Back to H = half + hconst - ge * (i + j); rows ascending with strict '>' (the lanes are combined below).
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int i = i0_lo + k, hv = smx16h_lo(Hc[k]) + hconst - ge * (i + n - 1);
+                if (i < m - 1 && hv > col_best) { col_best = hv; col_best_i = i; }
+                if (i == m - 1) corner = hv;
+            }
+            if (has_hi) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int i = i0_hi + k, hv = smx16h_hi(Hc[k]) + hconst - ge * (i + n - 1);
+                    if (i < m - 1 && hv > col_best) { col_best = hv; col_best_i = i; }
+                    if (i == m - 1) corner = hv;
                 }
             }
             __syncwarp();
@@ -466,6 +479,6 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
     }
     if (a.slot_flags) {
         if (TEAM) __syncthreads(); else __syncwarp();
-        if (TEAM ? threadIdx.x == 0 : lane == 0) atomicExch(&a.slot_flags[worker], 0);
+        if (TEAM ? threadIdx.x == 0 : lane == 0) { __threadfence(); atomicExch(&a.slot_flags[worker], 0); }  // release after this worker's line stores
     }
 }

@@ -120,12 +120,15 @@ __global__ void __launch_bounds__(SMX_SEL_THREADS) smx_select_kernel(const SmxSe
         long long t1 = 0, t2 = 0;
         for (int w = 0; w < SMX_SEL_THREADS / 32; ++w) { t1 += red[w]; t2 += red[SMX_SEL_THREADS / 32 + w]; }
         const double med = ((double)m_lo + (double)m_hi) * 0.5;
-        const double var = (double)(t2 * (long long)n - t1 * t1) / ((double)n * (double)n);
+        // n * sum(c^2) - (sum c)^2 exceeds int64 for long references with long reads (200 kb x 65 kb): 128-bit
+        const unsigned __int128 vnum = (unsigned __int128)(unsigned long long)t2 * (unsigned long long)n - (unsigned __int128)(unsigned long long)t1 * (unsigned long long)t1;
+        const double var = (double)vnum / ((double)n * (double)n);
         thr_s = med + pr.sigma * sqrt(var > 0.0 ? var : 0.0);
     }
     __syncthreads();
     const double thr = thr_s;
     if (fabs(thr - rint(thr)) < 1e-6) flags |= 1;
+    if (pr.nq > 65535) flags |= 1;  // counts above 16 bits: the two-level histogram median does not apply, the host decides
 
     // selected diagonals, ascending k (ordered compaction, 256 candidates per round)
     for (int base = 0; base < pr.max_k; base += SMX_SEL_THREADS) {

@@ -64,9 +64,20 @@ class Engine:
         self._h = h
         self.device = device
         self._pool_len = 0
+        self._siblings = []
+
+    def siblings(self, n: int) -> list:
+        """`n` more engines on the same device, created on first use and closed with this engine (the batches in
+        flight of savemoney.align_all run one handle each)."""
+        while len(self._siblings) < n:
+            self._siblings.append(Engine(self.device))
+        return self._siblings[:n]
 
     # -- plumbing ---------------------------------------------------------------------------
     def close(self):
+        for e in getattr(self, "_siblings", []):
+            e.close()
+        self._siblings = []
         if getattr(self, "_h", None):
             self._lib.smx_destroy(self._h)
             self._h = None

@@ -78,14 +78,14 @@ def sigma_for(n_ref: int) -> float:
     return float(stats.norm.ppf(1 - 1 / n_ref * PERCENTILE_FACTOR, loc=0, scale=1))  # :200-201
 
 
-_default_engine = None
+_default_engines = {}
 
 
-def default_engine() -> Engine:
-    global _default_engine
-    if _default_engine is None:
-        _default_engine = Engine(0)
-    return _default_engine
+def default_engine(device: int = 0) -> Engine:
+    """the process-wide engine of `device` (created on first use)"""
+    if device not in _default_engines:
+        _default_engines[device] = Engine(device)
+    return _default_engines[device]
 
 
 def _merge(parts):
@@ -93,17 +93,13 @@ def _merge(parts):
     return parts[0] if len(parts) == 1 else SegmentedPipelineResult(parts)
 
 
-_engine_pools = {}
-
-
 def _engines_for(engine, n):
-    """`n` engines on the device of `engine`: the caller's engine plus lazily created siblings.  Several handles
-    in flight let the host stages (planning, stitching) of one batch overlap the GPU stages of the others, and
-    let kernels of different batches fill each other's tails (measured best on B200: 4 x 1000 reads)."""
-    key = id(engine)
-    pool = _engine_pools.setdefault(key, [engine])
-    while len(pool) < n:
-        pool.append(Engine(engine.device))
+    """`n` engines on the device of `engine`: the caller's engine plus lazily created siblings, owned by that engine
+    (`engine.close()` closes them).  Several handles in flight let the host stages (planning, stitching) of one batch
+    overlap the GPU stages of the others, and let kernels of different batches fill each other's tails (measured best
+    on B200: 6 x 1000 reads)."""
+    pool = engine.siblings(n - 1)
+    pool = [engine] + pool
     if n > 6:
         # every handle grows its direction-bit arena up to its budget (16 GiB by default): more than six handles would
         # not fit 180 GB next to the other workspaces, so the handles share 100 GiB (smaller chunks per batch)
