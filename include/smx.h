@@ -51,6 +51,10 @@ extern "C" {
 typedef struct smx_handle smx_handle;
 
 int smx_version(void);
+/* CUDA devices visible to this process (0 when there is none: the engine has no CPU path).  The host layer shards
+ * reads over them, one handle set per device, where the reference fans out over multiprocessing.Pool(n_cpu)
+ * (post_analysis_core.py:58-61, pre_survey_core.py:240-244). */
+int smx_device_count(void);
 
 /* Creates an engine bound to `device_ordinal`.  `stream` is a cudaStream_t passed as void*
  * (e.g. torch.cuda.current_stream().cuda_stream) or NULL to let the engine create its own. */
@@ -63,6 +67,7 @@ const char *smx_last_error(const smx_handle *h);
  * the free device memory at creation); SMX_TRACE_BUDGET_GB in the environment overrides);
  * larger batches are cut into chunks that are processed back to back. */
 int smx_set_trace_budget(smx_handle *h, int64_t bytes);
+int64_t smx_get_trace_budget(const smx_handle *h);
 
 /* ---- sequence pool -------------------------------------------------------------------------
  * Copies `n` bytes of upper-case ASCII sequence data to the device; the offsets handed to the

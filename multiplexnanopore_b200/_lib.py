@@ -18,10 +18,12 @@ LIB_PATH = Path(os.environ["SMX_LIB_PATH"]).resolve() if os.environ.get("SMX_LIB
 # every symbol include/smx.h declares: (restype, argtypes)
 _SIGNATURES = {
     "smx_version": (c_int, []),
+    "smx_device_count": (c_int, []),
     "smx_create": (c_int, [POINTER(c_void_p), c_int, c_void_p]),
     "smx_destroy": (None, [c_void_p]),
     "smx_last_error": (c_char_p, [c_void_p]),
     "smx_set_trace_budget": (c_int, [c_void_p, c_int64]),
+    "smx_get_trace_budget": (c_int64, [c_void_p]),
     "smx_pool_upload": (c_int, [c_void_p, c_void_p, c_int64]),
     "smx_align_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                   c_int32, c_int32, c_int32, c_int32]),

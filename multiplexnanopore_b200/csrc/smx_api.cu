@@ -222,7 +222,14 @@ static cudaError_t smx_sync(smx_handle *h, cudaStream_t stream)
     return cudaEventSynchronize(ev);
 }
 
-extern "C" int smx_version(void) { return 100; }
+extern "C" int smx_version(void) { return 200; }
+
+extern "C" int smx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 extern "C" const char *smx_last_error(const smx_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -301,6 +308,8 @@ extern "C" void smx_destroy(smx_handle *h)
     if (h->owns_stream) { cudaStreamDestroy(h->stream); cudaStreamDestroy(h->stream_hi); }
     delete h;
 }
+
+extern "C" int64_t smx_get_trace_budget(const smx_handle *h) { return h ? h->trace_budget : 0; }
 
 extern "C" int smx_set_trace_budget(smx_handle *h, int64_t bytes)
 {
@@ -651,7 +660,7 @@ static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_id
     const int count = c.cls_count[cls];
     if (count == 0) return 0;
     const bool TEAM = W > 1;
-    const int threads = TEAM ? W * 32 : 128;
+    const int threads = TEAM ? W * 32 : (h->use_s16h ? 32 * SMX16H_WPC : 128);
     int occ = 0;
     void (*kern)(const SmxFwdArgs) = h->use_s16h ? smx_dp_forward16h<W> : smx_dp_forward16<W>;
     SMX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));

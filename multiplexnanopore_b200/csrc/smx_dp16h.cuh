@@ -57,6 +57,9 @@ __device__ __forceinline__ uint32_t smx16h_max_tr(uint32_t a, uint32_t b, uint32
     }
     return r;
 }
+#ifndef SMX16H_WPC
+#define SMX16H_WPC 4  // warps (= problems) per CTA of the one-warp-per-problem kernel
+#endif
 #ifndef SMX16H_ALU_FLAGS
 #define SMX16H_ALU_FLAGS 1  // how many of the four flag kinds of a cell go through the ALU pipe
 #endif
@@ -233,14 +236,14 @@ __device__ __forceinline__ void smx16h_edge_chunk(uint32_t (&Hc)[K], uint32_t (&
 
 // boundary lines: one uint32 per column = F^ << 16 | Hc (biased unsigned halves)
 template <int W>
-__global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM / (W == 1 ? 4 : W)) smx_dp_forward16h(const SmxFwdArgs a)
+__global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_WARPS_PER_SM / (W == 1 ? SMX16H_WPC : W)) smx_dp_forward16h(const SmxFwdArgs a)
 {
     constexpr bool TEAM = W > 1;
     constexpr bool SPLIT_OK = W == 1;  // the K = 4 code for a lone last band exists in the one-warp-per-problem kernel only
     constexpr int LAG = SMX16_LAG;
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    __shared__ int s_slot[W == 1 ? 4 : 1];
+    __shared__ int s_slot[W == 1 ? SMX16H_WPC : 1];
     // claim a pair of boundary lines (see SmxFwdArgs::slot_flags); released when the worker leaves
     int worker = TEAM ? blockIdx.x : ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (a.slot_flags) {
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(W == 1 ? 128 : W * 32, SMX16_MIN_WARPS_PER_SM 
     __shared__ int s_ticket;
     __shared__ volatile int s_prog[W];
     __shared__ int s_red[W][6];
-    __shared__ uint4 s_top[W == 1 ? 4 : W][32];
+    __shared__ uint4 s_top[W == 1 ? SMX16H_WPC : W][32];
 
     for (int served = 0; served < a.max_tickets; ++served) {
         int ticket = 0;

@@ -21,6 +21,11 @@ class EngineError(RuntimeError):
     pass
 
 
+def device_count() -> int:
+    """CUDA devices visible to this process (smx_device_count)"""
+    return int(_lib.load().smx_device_count())
+
+
 @dataclass
 class AlignBatchResult:
     """parasail Result fields for n problems in structure-of-arrays form."""
@@ -100,6 +105,10 @@ class Engine:
 
     def set_trace_budget(self, nbytes: int):
         self._check(self._lib.smx_set_trace_budget(self._h, int(nbytes)), "smx_set_trace_budget")
+
+    @property
+    def trace_budget(self) -> int:
+        return int(self._lib.smx_get_trace_budget(self._h))
 
     @property
     def last_run_ms(self) -> float:
@@ -280,6 +289,61 @@ class SegmentedPipelineResult(_PipelineResultOps):
     def nbytes(self) -> int:
         return int(self.score.nbytes + self.new_query_seq_offset.nbytes + self.status.nbytes + self.cigar_off.nbytes
                    + sum(p.cigar_rle.nbytes for p in self.parts))
+
+
+class ShardedPipelineResult(_PipelineResultOps):
+    """One alignment stage computed on several GPUs: `units` (reads in post_analysis, plasmid pairs in pre_survey) were
+    dealt to the shards, every shard holds `per_unit` consecutive pair-strands per unit; this view restores the
+    caller's order (my_fastq.keys(), post_analysis_core.py:63-65) without moving the CIGAR runs.
+
+        parts[k]         result of shard k (PipelineResult or SegmentedPipelineResult)
+        unit_index[k]    the units of shard k, ascending (shard.deal)
+    """
+
+    def __init__(self, parts, unit_index, per_unit: int):
+        self.parts = list(parts)
+        self.per_unit = int(per_unit)
+        n_units = sum(len(ix) for ix in unit_index)
+        self._shard = np.empty(n_units, dtype=np.int32)
+        self._local = np.empty(n_units, dtype=np.int64)
+        for k, ix in enumerate(unit_index):
+            ix = np.asarray(ix, dtype=np.int64)
+            self._shard[ix] = k
+            self._local[ix] = np.arange(len(ix))
+        n = n_units * self.per_unit
+        self.score = np.empty(n, np.int32)
+        self.new_query_seq_offset = np.empty(n, np.int32)
+        self.status = np.empty(n, np.uint8)
+        lens = np.empty(n, np.int64)
+        for k, (p, ix) in enumerate(zip(self.parts, unit_index)):
+            if len(ix) == 0:
+                continue
+            dst = (np.asarray(ix, dtype=np.int64)[:, None] * self.per_unit + np.arange(self.per_unit)[None, :]).ravel()
+            self.score[dst] = p.score
+            self.new_query_seq_offset[dst] = p.new_query_seq_offset
+            self.status[dst] = p.status
+            lens[dst] = np.diff(p.cigar_off)
+        self.cigar_off = np.zeros(n + 1, np.int64)
+        np.cumsum(lens, out=self.cigar_off[1:])
+        self.stats = {}
+        for p in self.parts:
+            for key, v in p.stats.items():
+                self.stats[key] = self.stats.get(key, 0) + v
+        self._flat = None
+
+    def runs(self, i: int) -> np.ndarray:
+        u, j = divmod(int(i), self.per_unit)
+        return self.parts[int(self._shard[u])].runs(int(self._local[u]) * self.per_unit + j)
+
+    @property
+    def cigar_rle(self) -> np.ndarray:
+        if self._flat is None:
+            self._flat = np.concatenate([self.runs(i) for i in range(len(self.score))]) if len(self.score) else np.empty(0, np.uint32)
+        return self._flat
+
+    @property
+    def nbytes(self) -> int:
+        return int(sum(p.nbytes for p in self.parts))
 
 
 _STAT_KEYS = ("t_total", "t_pool", "t_scan", "t_select", "t_chain", "t_dp", "t_stitch", "gpu_scan_ms", "gpu_select_ms",

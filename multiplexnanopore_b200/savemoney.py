@@ -108,11 +108,64 @@ def _engines_for(engine, n):
     return pool[:n]
 
 
+def visible_devices() -> list:
+    from .engine import device_count
+    return list(range(device_count()))
+
+
+def _align_sharded(refs, queries, param_dict, omit_too_long, pairs, devices, n_threads, batch_queries, overlap):
+    """Row (e): the units of the stage (reads; plasmid pairs when `pairs` is given) are length-binned by predicted work
+    and dealt to the GPUs (shard.deal), every GPU runs its share on its own set of engine handles from its own host
+    thread (ctypes releases the GIL), and the results come back in the caller's order.  No collective: the only
+    inter-GPU step is this host-side gather.  Replaces multiprocessing.Pool(n_cpu).imap
+    (post_analysis_core.py:58-61, pre_survey_core.py:240-244)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    from . import shard
+    from .engine import ShardedPipelineResult
+    refs = [_seq_of(r) for r in refs]
+    queries = [_seq_of(q) for q in queries]
+    if pairs is None:
+        total_ref = sum(len(r) for r in refs)
+        weights = [len(q) * total_ref for q in queries]
+        per_unit = 2 * len(refs)
+    else:
+        pairs = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
+        weights = [len(refs[i]) * len(queries[j]) for i, j in pairs]
+        per_unit = 2
+    index = shard.deal(weights, len(devices))
+    if n_threads <= 0:
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
+        # one call per GPU in pair mode, `overlap` handles per GPU in read mode
+        n_threads = max(1, min(8, cores // len(devices))) if pairs is not None else max(1, min(4, cores // (len(devices) * max(1, overlap))))
+
+    def work(k):
+        if len(index[k]) == 0:
+            return None
+        eng = default_engine(devices[k])
+        if pairs is None:
+            return align_all(refs, [queries[i] for i in index[k]], param_dict, omit_too_long, engine=eng,
+                             n_threads=n_threads, batch_queries=batch_queries, overlap=overlap)
+        return align_all(refs, queries, param_dict, omit_too_long, pairs=pairs[index[k]], engine=eng, n_threads=n_threads)
+
+    with ThreadPoolExecutor(max_workers=len(devices)) as ex:
+        parts = list(ex.map(work, range(len(devices))))
+    keep = [k for k, p in enumerate(parts) if p is not None]
+    return ShardedPipelineResult([parts[k] for k in keep], [index[k] for k in keep], per_unit)
+
+
 def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None, n_threads=0, batch_queries=1000,
-              overlap=6):
+              overlap=6, devices=None):
     """The alignment stage for every (query, reference) pair and both strands (or the explicit `pairs`).
     Queries are processed in batches of `batch_queries` so that device workspaces stay bounded; `overlap`
-    batches are in flight at once (one engine handle and one Python thread each; ctypes drops the GIL)."""
+    batches are in flight at once (one engine handle and one Python thread each; ctypes drops the GIL).
+    `engine` pins the call to one handle's GPU; otherwise `devices` (default: every visible GPU) share the work."""
+    if engine is None:
+        devs = visible_devices() if devices is None else list(devices)
+        if len(devs) > 1 and (len(queries) if pairs is None else len(pairs)) >= 2 * len(devs):
+            _check_params(param_dict)
+            return _align_sharded(refs, queries, param_dict, omit_too_long, pairs, devs, n_threads, batch_queries, overlap)
+        engine = default_engine(devs[0] if devs else 0)
     _check_params(param_dict)
     eng = engine or default_engine()
     refs = [_seq_of(r) for r in refs]
@@ -199,15 +252,15 @@ def _raise_failed(res):
         raise AssertionError(f"alignment failed an internal assertion of the reference algorithm on pair-strand(s) {bad[:8].tolist()}")
 
 
-def execute_alignment_core(ref_seq_list, my_fastq, param_dict, engine=None):
-    """result_dict[query_id] = [MyResult] * (2 * N_ref), order [ref0, ref0_rc, ref1, ...] (:63-65, :85)."""
+def execute_alignment_core(ref_seq_list, my_fastq, param_dict, engine=None, devices=None):
+    """result_dict[query_id] = [MyResult] * (2 * N_ref), order [ref0, ref0_rc, ref1, ...] (:63-65, :85).
+    Reads are sharded over `devices` (default: every visible GPU; `engine` pins the call to one handle)."""
     ids = list(my_fastq.keys())
     if not ids:
         _check_params(param_dict)
         return {}  # an empty FASTQ maps to an empty result_dict (the reference's pool.map over no reads)
     reads = [my_fastq[i][0] for i in ids]
-    res = align_all(ref_seq_list, reads, param_dict, omit_too_long=True, engine=engine,
-                    n_threads=0)
+    res = align_all(ref_seq_list, reads, param_dict, omit_too_long=True, engine=engine, n_threads=0, devices=devices)
     _raise_failed(res)
     n2 = 2 * len(ref_seq_list)
     out = {}
@@ -237,15 +290,16 @@ def calc_distance(ref_seq_1, ref_seq_2, param_dict, engine=None) -> int:
     return calc_distance_from(res, 0, len(_seq_of(ref_seq_1)), len(_seq_of(ref_seq_2)))
 
 
-def set_distance_matrix(ref_seq_list, param_dict, engine=None) -> np.ndarray:
-    """all i < j pairs: reference = plasmid i, query = plasmid j and its reverse complement."""
+def set_distance_matrix(ref_seq_list, param_dict, engine=None, devices=None) -> np.ndarray:
+    """all i < j pairs: reference = plasmid i, query = plasmid j and its reverse complement; the pairs are sharded
+    over `devices` (default: every visible GPU)."""
     seqs = [_seq_of(r) for r in ref_seq_list]
     n = len(seqs)
     pairs = np.array(list(combinations(range(n), 2)), dtype=np.int32).reshape(-1, 2)
     dm = np.zeros((n, n), dtype=int)
     if len(pairs) == 0:
         return dm
-    res = align_all(seqs, seqs, param_dict, omit_too_long=False, pairs=pairs, engine=engine)
+    res = align_all(seqs, seqs, param_dict, omit_too_long=False, pairs=pairs, engine=engine, devices=devices)
     _raise_failed(res)
     for p, (i, j) in enumerate(pairs):
         dm[i, j] = dm[j, i] = calc_distance_from(res, p, len(seqs[i]), len(seqs[j]))
@@ -352,12 +406,13 @@ class DenseResult:
         self.beg_query, self.beg_ref, self.end_query, self.end_ref = beg_query, beg_ref, end_query, end_ref
 
 
-def legacy_dense_align(ref_seq_list, my_fastq, param_dict, engine=None, batch_cells=int(2e10)):
+def legacy_dense_align(ref_seq_list, my_fastq, param_dict, engine=None, batch_cells=int(2e10), stats=None):
     """Row N4, the pre-0.2 alignment mode kept in the reference under Modules/ (MyAligner.align_all /
     MyAlignerLinear.align_all, Modules/1_alignment_consensus_core.py:219-296): one local alignment
     `parasail.sw_trace(read, reference + reference)` (circular; `reference` alone for linear topology) per read,
     plasmid and strand, no seeding.  Returns {query_id: [DenseResult(ref0), DenseResult(ref0, rc), DenseResult(ref1), ...]}.
-    Runs on the int32 local-alignment kernels through `Engine.align_batch` (mode 3), `batch_cells` DP cells per call."""
+    Runs through `Engine.align_batch` (mode 3), `batch_cells` DP cells per call.  `stats` (a dict) receives the
+    cells, launches and CUDA-event kernel times of the call (bench.py --config legacy_dense)."""
     from .engine import MODE_SW
     _check_params(param_dict)
     eng = engine or default_engine()
@@ -369,6 +424,9 @@ def legacy_dense_align(ref_seq_list, my_fastq, param_dict, engine=None, batch_ce
     out = {}
     go, ge = param_dict["gap_open_penalty"], param_dict["gap_extend_penalty"]
     ma, mi = param_dict["match_score"], param_dict["mismatch_score"]
+    if stats is not None:
+        stats.update(cells=0, launches=0, problems=0, out_bytes=0, kernel_ms_total=0.0, class_ms=[0.0] * 16, class_cells=[0] * 14,
+                     class_launches=[0] * 16)
     pos = 0
     while pos < len(ids):
         # reads of this call: as many as fit the cell budget (at least one)
@@ -393,6 +451,15 @@ def legacy_dense_align(ref_seq_list, my_fastq, param_dict, engine=None, batch_ce
                     s2.append(t)
         s1 = np.array(s1); s2 = np.array(s2)
         res = eng.align_batch(offs[s1], lens[s1], offs[s2], lens[s2], np.full(len(s1), MODE_SW, np.uint8), go, ge, ma, mi)
+        if stats is not None:
+            kms, kcells = eng.align_kernel_ms()
+            stats["cells"] += eng.align_cells; stats["launches"] += eng.last_run_launches; stats["problems"] += len(s1)
+            stats["out_bytes"] += int(res.cigar_rle.nbytes + 5 * res.score.nbytes + res.cigar_off.nbytes)
+            stats["kernel_ms_total"] += float(kms.sum())
+            for c in range(16):
+                stats["class_ms"][c] += float(kms[c]); stats["class_launches"][c] += int(kms[c] > 0)
+            for c in range(14):
+                stats["class_cells"][c] += int(kcells[c])
         p = 0
         for qid in ids[pos:end]:
             row = []
