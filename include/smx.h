@@ -158,6 +158,21 @@ int smx_pipeline_fetch(smx_handle *h, int32_t *score, int32_t *new_query_seq_off
  * out[64] = chain kernel ms */
 int smx_pipeline_stats(smx_handle *h, double *out, int32_t n);
 
+/* ---- row N2: what consumes the score matrix and the CIGARs without per-result objects -------
+ * smx_assign: msa.QueryAssignment (savemoney/modules/msa.py:31-64) on the device, one thread per read.
+ *   score / status: [n_reads, 2 * n_refs] as smx_pipeline_fetch delivers them (status != 0 = empty MyResult());
+ *   normalized[n_reads, 2 * n_refs] = score / len(ref) in float64, NaN where empty; summary[n_reads, n_refs] = best
+ *   strand per plasmid, empty / negative -> 0; assignment[n_reads, 3] = (classified_ref_seq_idx, is_reverse_compliment,
+ *   assigned): (-1, -1, -1) without any result, (-1, -1, 0) on tied maxima, else (k / 2, k % 2, best > threshold). */
+int smx_assign(smx_handle *h, const int32_t *score, const uint8_t *status, const int32_t *ref_len, int32_t n_reads, int32_t n_refs,
+               double score_threshold, int32_t *assignment, double *normalized, double *summary);
+/* smx_ir_format: the `# result<idx>(dict)` text blocks of <stem>.intermediate_results.txt
+ * (post_analysis/post_analysis_core.py:89-128 over MyResult.to_dict, modules/ref_query_alignment.py:512-518; block
+ * syntax modules/my_classes.py:43-74) for pair-strands [0, n) numbered from `first_index`, written from the arrays
+ * smx_pipeline_fetch delivers (host threads; needs no device).  out == NULL returns the byte count. */
+int64_t smx_ir_format(const int32_t *score, const int32_t *new_query_seq_offset, const uint8_t *status, const int64_t *cigar_off,
+                      const uint32_t *cigar_rle, int64_t n, int64_t first_index, int32_t n_threads, char *out, int64_t capacity);
+
 /* ---- measurement helper: dependency-free int32 / DPX issue-rate microbenchmark ---------------
  * Runs `iters` rounds of independent VIADDMNMX / VIMNMX3 / IADD chains on every SM and returns
  * achieved giga-ops/s (one op = one 32-bit lane instruction) in out_gops[3] = {viaddmax, vimax3, iadd}. */

@@ -20,6 +20,7 @@
 #include "smx_dp16h.cuh"
 #include "smx_scan.cuh"
 #include "smx_traceback.cuh"
+#include "smx_outputs.cuh"
 
 namespace {
 
@@ -57,9 +58,14 @@ struct smx_handle {
     int64_t team_min_cells = 0;  // SMX_TEAM_MIN_MCELLS (in Mi cells): below it one warp per problem (measured: no gain on C2)
     bool persistent_fwd = false;  // SMX_PERSISTENT=1: launch smx_dp16h.cuh as a persistent grid (A/B switch)
     bool use_s16h = true;  // diagonal-frame u16x2 kernel (smx_dp16h.cuh) when the scoring allows it; SMX_S16H=0 keeps smx_dp16.cuh
-    int s16_max_wsel = 0;  // warps per problem of the packed kernels: 1 (measured best with several DP phases in flight, whose
-                           // launches fill each other's tails); SMX_S16_MAXW=2|4|8 turns the teams on (latency of few huge problems)
+    int s16_max_wsel = 3;  // upper bound of the team width selector (SMX_S16_MAXW=1|2|4|8; 1 = one warp per problem throughout)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fwd = nullptr, ev_sync_lo = nullptr, ev_sync_hi = nullptr;
+    // the largest problems of a chunk run as teams of 2 / 4 / 8 warps NEXT TO the one-warp-per-problem launch (own low-priority
+    // streams, forked and joined by events) so that their critical path does not become the tail of the forward phase
+    cudaStream_t stream_team[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    bool teams_concurrent = false;
+    int64_t team_cells[3] = {16ll << 20, 48ll << 20, 128ll << 20};  // cells from which a problem gets 2 / 4 / 8 warps (SMX_TEAM2/4/8_MCELLS)
     float last_ms = 0.f;
     int last_launches = 0;
     // per-kernel timing of the last smx_align_run: [0..13] forward classes (problem_class), [14] traceback, [15] compaction
@@ -265,6 +271,11 @@ extern "C" int smx_create(smx_handle **out, int device_ordinal, void *stream)
         if ((e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_least)) != cudaSuccess) { delete h; return fail(nullptr, -2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         if ((e = cudaStreamCreateWithPriority(&h->stream_hi, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return fail(nullptr, -2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         h->owns_stream = true;
+        for (int t = 0; t < 3; ++t) {
+            if (cudaStreamCreateWithPriority(&h->stream_team[t], cudaStreamNonBlocking, prio_least) != cudaSuccess) h->stream_team[t] = nullptr;
+            cudaEventCreateWithFlags(&h->ev_join[t], cudaEventDisableTiming);
+        }
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     }
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
@@ -306,6 +317,8 @@ extern "C" void smx_destroy(smx_handle *h)
     if (h->ev_sync_lo) cudaEventDestroy(h->ev_sync_lo);
     if (h->ev_sync_hi) cudaEventDestroy(h->ev_sync_hi);
     if (h->owns_stream) { cudaStreamDestroy(h->stream); cudaStreamDestroy(h->stream_hi); }
+    for (int t = 0; t < 3; ++t) { if (h->stream_team[t]) cudaStreamDestroy(h->stream_team[t]); if (h->ev_join[t]) cudaEventDestroy(h->ev_join[t]); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     delete h;
 }
 
@@ -481,8 +494,13 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         const char *envh = getenv("SMX_S16H");
         h->use_s16h = !(envh && envh[0] == '0') && s16h_scoring_ok(h->sc);
         const char *mw = getenv("SMX_S16_MAXW");
-        h->s16_max_wsel = 0;
+        h->s16_max_wsel = 3;
         if (mw) { const int v = atoi(mw); h->s16_max_wsel = v >= 8 ? 3 : v >= 4 ? 2 : v >= 2 ? 1 : 0; }
+        static const char *const tenv[3] = {"SMX_TEAM2_MCELLS", "SMX_TEAM4_MCELLS", "SMX_TEAM8_MCELLS"};
+        static const int64_t tdef[3] = {16, 48, 128};
+        for (int t = 0; t < 3; ++t) { const char *e = getenv(tenv[t]); h->team_cells[t] = (e && atol(e) > 0 ? (int64_t)atol(e) : tdef[t]) << 20; }
+        const char *tc = getenv("SMX_TEAMS_CONCURRENT");
+        h->teams_concurrent = h->use_s16h && !h->persistent_fwd && h->stream_team[0] && h->stream_team[1] && h->stream_team[2] && !(tc && tc[0] == '0');
     }
     h->nmax = 1;
     int64_t runs_off = 0;
@@ -505,16 +523,20 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         q.kshift = pick_kshift(m);
         q.cls = problem_class(m, mode[p]);
         if (h->use_s16 && s16_eligible(h, s2_off[p], m, nn, mode[p])) {
+            // Teams shorten the critical path of the largest problems -- the tail of the forward phase: one warp needs
+            // ~30 ms for a 35 M-cell problem, ~0.4 s for the 400 M cells of a 20 kb x 20 kb head of C4 -- but idle a warp
+            // whenever the band pairs do not divide evenly and pay a pipeline fill per band pair: only problems of many
+            // cells AND at least two band pairs per warp get one (2 / 4 / 8 warps from 16 / 48 / 128 Mi cells).
             const int pairs = ((m + 255) / 256 + 1) / 2;
-            int wsel = pairs >= 8 ? 3 : pairs >= 4 ? 2 : pairs >= 2 ? 1 : 0;
+            const int64_t pc = (int64_t)m * nn;
+            int wsel = pc >= h->team_cells[2] && pairs >= 16 ? 3 : pc >= h->team_cells[1] && pairs >= 8 ? 2 : pc >= h->team_cells[0] && pairs >= 4 ? 1 : 0;
             if (wsel > h->s16_max_wsel) wsel = h->s16_max_wsel;
-            // teams shorten the critical path of the largest problems (launch tail) but idle a warp whenever the band pairs
-            // do not divide evenly: everything below the threshold runs one warp per problem
-            if ((int64_t)m * nn < h->team_min_cells) wsel = 0;
+            if (pc < h->team_min_cells) wsel = 0;
             q.cls = (int16_t)(kClsS16 + wsel);
             q.kshift = 3;  // the packed kernels always run 8 rows per lane (trace layout and traceback follow kshift)
         }
-        h->class_cells[q.cls] += (int64_t)m * nn;
+        // concurrent teams: the packed forward phase (one-warp launch + team launches side by side) is timed as ONE interval
+        h->class_cells[(h->teams_concurrent && q.cls > kClsS16) ? kClsS16 : q.cls] += (int64_t)m * nn;
         q.trace_off = 0;
         q.cigar_off = runs_off;
         runs_off += (int64_t)m + nn + 2;
@@ -655,10 +677,11 @@ static int launch_forward(smx_handle *h, const Chunk &c, int cls, int chunk_idx)
 }
 
 template <int W>
-static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_idx)
+static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_idx, cudaStream_t stream = nullptr, bool do_mark = true)
 {
     const int count = c.cls_count[cls];
     if (count == 0) return 0;
+    if (!stream) stream = h->stream;
     const bool TEAM = W > 1;
     const int threads = TEAM ? W * 32 : (h->use_s16h ? 32 * SMX16H_WPC : 128);
     int occ = 0;
@@ -689,10 +712,10 @@ static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_id
     a.n_slots = kLineSlots;
     a.slot_flags = persistent ? nullptr : (int32_t *)h->d_slots.p;
     a.split_last = h->split_last;
-    kern<<<blocks, threads, 0, h->stream>>>(a);
+    kern<<<blocks, threads, 0, stream>>>(a);
     SMX_CUDA(h, cudaGetLastError());
     h->last_launches++;
-    return mark(h, cls);
+    return do_mark ? mark(h, cls) : 0;
 }
 
 static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate);
@@ -729,10 +752,29 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
     for (size_t ci = 0; ci < h->chunks.size(); ++ci) {
         const Chunk &c = h->chunks[ci];
         int rc = 0;
-        if ((rc = launch_forward16<8>(h, c, kClsS16 + 3, (int)ci))) return rc;
-        if ((rc = launch_forward16<4>(h, c, kClsS16 + 2, (int)ci))) return rc;
-        if ((rc = launch_forward16<2>(h, c, kClsS16 + 1, (int)ci))) return rc;
-        if ((rc = launch_forward16<1>(h, c, kClsS16, (int)ci))) return rc;
+        if (h->teams_concurrent && (c.cls_count[kClsS16 + 1] | c.cls_count[kClsS16 + 2] | c.cls_count[kClsS16 + 3])) {
+            // fork: the team launches (few CTAs, long) go first on their own streams and take their SM slots, the
+            // one-warp-per-problem launch fills the rest; join before the next kernel of this stream
+            SMX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+            for (int t = 2; t >= 0; --t) {
+                if (c.cls_count[kClsS16 + 1 + t] == 0) continue;
+                SMX_CUDA(h, cudaStreamWaitEvent(h->stream_team[t], h->ev_fork, 0));
+                if (t == 2) rc = launch_forward16<8>(h, c, kClsS16 + 3, (int)ci, h->stream_team[t], false);
+                else if (t == 1) rc = launch_forward16<4>(h, c, kClsS16 + 2, (int)ci, h->stream_team[t], false);
+                else rc = launch_forward16<2>(h, c, kClsS16 + 1, (int)ci, h->stream_team[t], false);
+                if (rc) return rc;
+                SMX_CUDA(h, cudaEventRecord(h->ev_join[t], h->stream_team[t]));
+            }
+            if ((rc = launch_forward16<1>(h, c, kClsS16, (int)ci, h->stream, false))) return rc;
+            for (int t = 0; t < 3; ++t)
+                if (c.cls_count[kClsS16 + 1 + t]) SMX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[t], 0));
+            if ((rc = mark(h, kClsS16))) return rc;
+        } else {
+            if ((rc = launch_forward16<8>(h, c, kClsS16 + 3, (int)ci))) return rc;
+            if ((rc = launch_forward16<4>(h, c, kClsS16 + 2, (int)ci))) return rc;
+            if ((rc = launch_forward16<2>(h, c, kClsS16 + 1, (int)ci))) return rc;
+            if ((rc = launch_forward16<1>(h, c, kClsS16, (int)ci))) return rc;
+        }
         if ((rc = launch_forward<8, false, true>(h, c, 8, (int)ci))) return rc;
         if ((rc = launch_forward<8, true, true>(h, c, 9, (int)ci))) return rc;
         if ((rc = launch_forward<8, false, false>(h, c, 6, (int)ci))) return rc;
@@ -929,6 +971,81 @@ extern "C" int smx_scan_fetch(smx_handle *h, int32_t *counts, int64_t counts_cap
 }
 
 extern "C" int64_t smx_scan_cells(const smx_handle *h) { return h ? h->scan_cells : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// Row N2: assignment on the device, .ir result blocks from the arrays (smx_outputs.cuh)
+// ------------------------------------------------------------------------------------------------
+extern "C" int smx_assign(smx_handle *h, const int32_t *score, const uint8_t *status, const int32_t *ref_len, int32_t n_reads, int32_t n_refs,
+                          double score_threshold, int32_t *assignment, double *normalized, double *summary)
+{
+    if (!h) return -1;
+    if (n_reads < 0 || n_refs <= 0 || (n_reads > 0 && (!score || !status || !assignment || !normalized || !summary)) || !ref_len)
+        return fail(h, -1, "smx_assign: NULL or empty argument");
+    for (int r = 0; r < n_refs; ++r) if (ref_len[r] <= 0) return fail(h, -1, "smx_assign: reference %d has no length", r);
+    if (n_reads == 0) return 0;
+    SMX_CUDA(h, cudaSetDevice(h->device));
+    const size_t n2 = 2 * (size_t)n_refs, cells = (size_t)n_reads * n2;
+    const size_t o_score = 0, o_norm = (cells * 4 + 7) & ~(size_t)7, o_sum = o_norm + cells * 8, o_asg = o_sum + (size_t)n_reads * n_refs * 8,
+                 o_len = o_asg + (size_t)n_reads * 12, o_status = o_len + (size_t)n_refs * 4, total = o_status + cells;
+    DevBuf buf;
+    if (int rc = ensure(h, buf, total)) return rc;
+    char *d = (char *)buf.p;
+    cudaStream_t s = h->stream_hi;
+    SMX_CUDA(h, cudaMemcpyAsync(d + o_score, score, cells * 4, cudaMemcpyHostToDevice, s));
+    SMX_CUDA(h, cudaMemcpyAsync(d + o_status, status, cells, cudaMemcpyHostToDevice, s));
+    SMX_CUDA(h, cudaMemcpyAsync(d + o_len, ref_len, (size_t)n_refs * 4, cudaMemcpyHostToDevice, s));
+    SmxAssignArgs a;
+    a.score = (const int32_t *)(d + o_score); a.status = (const uint8_t *)(d + o_status); a.ref_len = (const int32_t *)(d + o_len);
+    a.normalized = (double *)(d + o_norm); a.summary = (double *)(d + o_sum); a.assignment = (int32_t *)(d + o_asg);
+    a.n_reads = n_reads; a.n_refs = n_refs; a.threshold = score_threshold;
+    smx_assign_kernel<<<(n_reads + 127) / 128, 128, 0, s>>>(a);
+    SMX_CUDA(h, cudaGetLastError());
+    SMX_CUDA(h, cudaMemcpyAsync(normalized, d + o_norm, cells * 8, cudaMemcpyDeviceToHost, s));
+    SMX_CUDA(h, cudaMemcpyAsync(summary, d + o_sum, (size_t)n_reads * n_refs * 8, cudaMemcpyDeviceToHost, s));
+    SMX_CUDA(h, cudaMemcpyAsync(assignment, d + o_asg, (size_t)n_reads * 12, cudaMemcpyDeviceToHost, s));
+    const cudaError_t e = smx_sync(h, s);
+    release(buf);
+    SMX_CUDA(h, e);
+    return 0;
+}
+
+// out == NULL: returns the number of bytes the blocks result<first_index> .. result<first_index + n - 1> take;
+// otherwise writes them (capacity checked) and returns the bytes written; negative on error.  No handle: pure host code.
+extern "C" int64_t smx_ir_format(const int32_t *score, const int32_t *new_query_seq_offset, const uint8_t *status, const int64_t *cigar_off,
+                                 const uint32_t *cigar_rle, int64_t n, int64_t first_index, int32_t n_threads, char *out, int64_t capacity)
+{
+    using namespace smx_out;
+    if (n < 0 || (n > 0 && (!score || !new_query_seq_offset || !status || !cigar_off || (!cigar_rle && cigar_off[n] > cigar_off[0])))) return -1;
+    if (n == 0) return 0;
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads > 0 ? n_threads : 4, (n + 4095) / 4096));
+    std::vector<int64_t> part((size_t)nt + 1, 0);
+    auto range = [&](int t, int64_t &lo, int64_t &hi) { lo = n * t / nt; hi = n * (t + 1) / nt; };
+    auto each = [&](auto &&fn) {
+        if (nt == 1) { fn(0); return; }
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(fn, t);
+        for (auto &x : th) x.join();
+    };
+    each([&](int t) {
+        int64_t lo, hi, acc = 0;
+        range(t, lo, hi);
+        for (int64_t i = lo; i < hi; ++i)
+            acc += block_len(first_index + i, cigar_rle + cigar_off[i], cigar_off[i + 1] - cigar_off[i], status[i] != 0, score[i], new_query_seq_offset[i]);
+        part[(size_t)t + 1] = acc;
+    });
+    for (int t = 0; t < nt; ++t) part[(size_t)t + 1] += part[(size_t)t];
+    const int64_t total = part[(size_t)nt];
+    if (!out) return total;
+    if (capacity < total) return -2;
+    each([&](int t) {
+        int64_t lo, hi;
+        range(t, lo, hi);
+        char *p = out + part[(size_t)t];
+        for (int64_t i = lo; i < hi; ++i)
+            p = block_put(p, first_index + i, cigar_rle + cigar_off[i], cigar_off[i + 1] - cigar_off[i], status[i] != 0, score[i], new_query_seq_offset[i]);
+    });
+    return total;
+}
 
 // ------------------------------------------------------------------------------------------------
 // int32 / DPX issue-rate microbenchmark (roofline denominator)

@@ -307,93 +307,7 @@ def set_distance_matrix(ref_seq_list, param_dict, engine=None, devices=None) -> 
     return dm
 
 
-class QueryAssignment:
-    """Row A13 / N2: score normalisation and read assignment, msa.QueryAssignment (msa.py:28-64), computed on the
-    engine's arrays (no per-result Python objects).  Same public fields: score_table, normalized_score_table,
-    normalized_score_table_summary, assignment_table (classified_ref_seq_idx, is_reverse_compliment, assigned).
-
-        qa = QueryAssignment(ref_seq_list, query_ids, pipeline_result)       # or .from_tables(...)
-        qa.set_assignment(score_threshold)
-    """
-    query_assignment_version = "qa_0.2.0"
-
-    def __init__(self, ref_seq_list, query_ids, res):
-        ref_lens = [len(_seq_of(r)) for r in ref_seq_list]
-        n2 = 2 * len(ref_lens)
-        score = np.asarray(res.score, dtype=int).reshape(-1, n2)
-        empty = (np.asarray(res.status) != 0).reshape(-1, n2)   # MyResult() <=> my_cigar == "" (msa.py:34)
-        self._init_tables(ref_lens, list(query_ids), score, empty)
-
-    @classmethod
-    def from_tables(cls, ref_lens, query_ids, score_table, empty_mask):
-        self = cls.__new__(cls)
-        self._init_tables(list(ref_lens), list(query_ids), np.asarray(score_table, dtype=int), np.asarray(empty_mask, dtype=bool))
-        return self
-
-    def _init_tables(self, ref_lens, query_ids, score, empty):
-        if score.shape != (len(query_ids), 2 * len(ref_lens)) or empty.shape != score.shape:
-            raise ValueError("score table must be [N_query, 2 * N_ref] (forward, reverse complement per reference)")
-        self.ref_lens, self.query_ids = ref_lens, query_ids
-        self.score_table = score
-        norm = score / np.repeat(np.asarray(ref_lens, dtype=int), 2)[np.newaxis, :]   # float64, :38
-        norm[empty] = np.nan
-        self.normalized_score_table = np.ma.masked_array(norm, mask=empty)
-        summary = self.normalized_score_table.reshape(len(query_ids), len(ref_lens), 2).max(axis=-1)
-        summary[np.ma.getmask(summary)] = 0       # :41-43: reads without any result and negative scores count as 0
-        summary[summary < 0] = 0
-        self.normalized_score_table_summary = summary
-        self.assignment_table = np.empty((len(query_ids), 3), dtype=int)
-        self.score_threshold = None
-
-    @property
-    def N_query(self):
-        return len(self.query_ids)
-
-    @property
-    def N_ref_seq_list(self):
-        return len(self.ref_lens)
-
-    def set_assignment(self, score_threshold):
-        """:52-64 -- a read is assigned iff its best normalised score is unique and above the threshold; reads whose
-        best score is tied (or that have no result at all) get -1 in the first two columns, reads without any
-        result -1 in the third."""
-        self.score_threshold = score_threshold
-        t = self.normalized_score_table
-        best = t.argmax(axis=1)                                   # all-masked rows give 0
-        self.assignment_table[:, 0] = best // 2
-        self.assignment_table[:, 1] = best % 2
-        best_val = t[(range(self.N_query), best)]
-        n_best = (t == best_val[:, np.newaxis]).sum(axis=1)
-        self.assignment_table[(n_best > 1).filled(True), :2] = -1
-        self.assignment_table[:, 2] = (best_val > score_threshold) * (n_best == 1)
-        self.assignment_table[np.ma.getmask(best_val), 2] = -1
-        return self.assignment_table
-
-    def assigned_groups(self):
-        """per reference: [(query_index, is_rc)] of the reads assigned to it, in read order (iter_assignment_info :65-78)"""
-        out = [[] for _ in self.ref_lens]
-        for qi, (ri, rc, ok) in enumerate(self.assignment_table):
-            if ok == 1:
-                out[ri].append((qi, int(rc)))
-        return out
-
-    def save_scores(self, save_dir, ref_names, combined_name_stem):
-        """<stem>.summary_scores.csv in the layout of msa.py:79-92."""
-        import pandas as pd
-        from pathlib import Path
-        cols = [f"{n} (idx={i}{t})" for i, n in enumerate(ref_names) for t in ["", ",rc"]]
-        cols_n = [f"{n} (idx={i}{t}, normalized)" for i, n in enumerate(ref_names) for t in ["", ",rc"]]
-        df = pd.DataFrame(columns=["query_id"] + cols + cols_n + ["classified_ref_seq_idx", "is_reverse_compliment", "assigned"])
-        df["query_id"] = self.query_ids
-        n2 = 2 * self.N_ref_seq_list
-        df.iloc[:, 1:n2 + 1] = self.score_table
-        df.iloc[:, n2 + 1:2 * n2 + 1] = np.ma.getdata(self.normalized_score_table)
-        df.iloc[:, 2 * n2 + 1:] = self.assignment_table
-        df.index.name = "query_idx"
-        df = df.reset_index()
-        path = Path(save_dir) / f"{combined_name_stem}.summary_scores.csv"
-        df.to_csv(path, sep="\t", index=False, na_rep="NaN")
-        return path
+from .outputs import QueryAssignment, IntermediateResults, save_intermediate_results  # noqa: E402,F401  (row N2)
 
 
 class DenseResult:
