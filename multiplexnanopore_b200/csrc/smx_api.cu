@@ -357,7 +357,9 @@ __global__ void __launch_bounds__(256) smx_expand_pool_kernel(const uint8_t *com
     const uint8_t *src = compact + it.src;
     uint8_t *dst = pool + it.dst;
     for (int i = threadIdx.x; i < it.len; i += 256) {
-        const uint8_t b = it.rc ? s_comp[src[it.len - 1 - i]] : src[i];
+        uint8_t b = src[it.rc ? it.len - 1 - i : i];
+        if (b >= 'a' && b <= 'z') b -= 32;   // MySeq upper-cases on construction (my_classes.py:271-272): done here, not in a host pass
+        if (it.rc) b = s_comp[b];
         dst[i] = b;
         dst[it.len + i] = b;
     }
@@ -1344,13 +1346,13 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
                 const SmxSelPair &s = sel_pairs[i];
                 counts_host.resize((size_t)s.max_k);
                 SMX_CUDA(h, cudaMemcpy(counts_host.data(), (const int32_t *)h->d_counts.p + s.counts_off, sizeof(int32_t) * (size_t)s.max_k, cudaMemcpyDeviceToHost));
-                const uint8_t *qp = qry_seqs + qry_off[x.qry];
-                if (x.strand) {  // the reverse-complement strand exists only on the device
-                    redo_rc.resize((size_t)x.nq);
-                    for (int t = 0; t < x.nq; ++t) redo_rc[(size_t)t] = g_comp[qp[x.nq - 1 - t]];
-                    qp = redo_rc.data();
-                }
-                host_regions(ref_seqs + ref_off[x.ref], qp, x.nr, x.nq, topology, counts_host.data(),
+                // upper-casing and the reverse-complement strand exist only on the device: restate them for this pair-strand
+                auto up = [](uint8_t c) { return (uint8_t)(c >= 'a' && c <= 'z' ? c - 32 : c); };
+                const uint8_t *qp = qry_seqs + qry_off[x.qry], *rp = ref_seqs + ref_off[x.ref];
+                redo_rc.resize((size_t)x.nq + (size_t)x.nr);
+                for (int t = 0; t < x.nq; ++t) redo_rc[(size_t)t] = x.strand ? g_comp[up(qp[x.nq - 1 - t])] : up(qp[t]);
+                for (int t = 0; t < x.nr; ++t) redo_rc[(size_t)x.nq + (size_t)t] = up(rp[t]);
+                host_regions(redo_rc.data() + x.nq, redo_rc.data(), x.nr, x.nq, topology, counts_host.data(),
                              s.max_k, s.slice_lo, s.slice_hi, s.sigma, redo);
                 rg = redo.data(); nreg = (int)redo.size();
                 ++st.n_host_redo;

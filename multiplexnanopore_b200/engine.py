@@ -362,12 +362,18 @@ def pack_slice(packed, lo, hi):
 
 
 def _pack(seqs):
-    enc = [s.encode("ascii") if isinstance(s, str) else bytes(s) for s in seqs]
-    lens = np.array([len(e) for e in enc], dtype=np.int32)
-    offs = np.zeros(len(enc), dtype=np.int64)
-    if len(enc) > 1:
+    """sequences back to back as bytes + offsets + lengths (one join and one encode for a list of str)"""
+    if all(isinstance(s, str) for s in seqs):
+        lens = np.fromiter(map(len, seqs), dtype=np.int32, count=len(seqs))
+        buf = "".join(seqs).encode("ascii")
+    else:
+        enc = [s.encode("ascii") if isinstance(s, str) else bytes(s) for s in seqs]
+        lens = np.array([len(e) for e in enc], dtype=np.int32)
+        buf = b"".join(enc)
+    offs = np.zeros(len(lens), dtype=np.int64)
+    if len(lens) > 1:
         offs[1:] = np.cumsum(lens[:-1], dtype=np.int64)
-    return np.frombuffer(b"".join(enc), dtype=np.uint8), offs, lens
+    return np.frombuffer(buf, dtype=np.uint8), offs, lens
 
 
 def pipeline_run(self, refs, queries, sigmas, open_: int, extend: int, match: int, mismatch: int, topology: int,

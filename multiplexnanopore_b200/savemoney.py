@@ -62,8 +62,10 @@ class MyResult:
 
 
 def _seq_of(x) -> str:
-    s = x if isinstance(x, str) else (getattr(x, "_seq", None) or str(x))
-    return s.upper()  # MySeq upper-cases on construction (my_classes.py:271-272)
+    """the bases of a str / MySeq / MyRefSeq.  Case is normalised where the sequences are consumed: the pipeline's pool
+    kernel upper-cases on the device (MySeq upper-cases on construction, my_classes.py:271-272), `Engine.upload_sequences`
+    on upload -- not by a host pass over every read here."""
+    return x if isinstance(x, str) else (getattr(x, "_seq", None) or str(x))
 
 
 def _check_params(p):
@@ -136,8 +138,8 @@ def _align_sharded(refs, queries, param_dict, omit_too_long, pairs, devices, n_t
     index = shard.deal(weights, len(devices))
     if n_threads <= 0:
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
-        # one call per GPU in pair mode, `overlap` handles per GPU in read mode
-        n_threads = max(1, min(8, cores // len(devices))) if pairs is not None else max(1, min(4, cores // (len(devices) * max(1, overlap))))
+        # one call per GPU in pair mode; in read mode the handles in flight of a GPU are not all in their host stages at once
+        n_threads = max(1, min(8, cores // len(devices))) if pairs is not None else max(1, min(4, (cores // len(devices)) // 2))
 
     def work(k):
         if len(index[k]) == 0:
@@ -331,7 +333,7 @@ def legacy_dense_align(ref_seq_list, my_fastq, param_dict, engine=None, batch_ce
     _check_params(param_dict)
     eng = engine or default_engine()
     circular = param_dict["topology_of_dna"] == 0
-    refs = [_seq_of(r) for r in ref_seq_list]
+    refs = [_seq_of(r).upper() for r in ref_seq_list]
     targets = [r + r if circular else r for r in refs]
     ids = list(my_fastq.keys())
     comp = str.maketrans("ACGTMRWSYKVHDBN", "TGCAKYWSRMBDHVN")
@@ -353,7 +355,7 @@ def legacy_dense_align(ref_seq_list, my_fastq, param_dict, engine=None, batch_ce
             end += 1
         seqs = list(targets)
         for qid in ids[pos:end]:
-            q = _seq_of(my_fastq[qid][0])
+            q = _seq_of(my_fastq[qid][0]).upper()
             seqs += [q, q.translate(comp)[::-1]]
         offs, lens = eng.upload_sequences(seqs)
         nt = len(targets)
