@@ -158,6 +158,27 @@ int smx_pipeline_fetch(smx_handle *h, int32_t *score, int32_t *new_query_seq_off
  * out[64] = chain kernel ms */
 int smx_pipeline_stats(smx_handle *h, double *out, int32_t n);
 
+/* ---- row N1: the alignment operations of MyAlignerBase as one batch -------------------------
+ * What MyMSA.exec_chunk_poa (savemoney/modules/msa.py:1249-1355) calls once per read chunk -- collected here over all
+ * chunks of a polish round.  Sequences live in the uploaded pool (smx_pool_upload); `ref` is the chunk consensus.
+ *   SMX_OPKIND_NW          MyAlignerBase.nw_trace             (ref_query_alignment.py:57-59)   -> = X I D
+ *   SMX_OPKIND_SG_QE_DE    my_special_sg_qe_de                (:60-73)   aligned prefix, then S.. H..  (set_soft_clipping "beg")
+ *   SMX_OPKIND_SG_QB_DB    my_special_sg_qb_db                (:74-87)   H.. S.., then the aligned suffix  ("end")
+ *   SMX_OPKIND_SW          my_special_sw                      (:34-56)   H/S flanks around the local alignment, leading-D quirk
+ *   SMX_OPKIND_SPECIAL_DP  my_special_DP(q1, q2, ref)         (:89-163)  sg_qe_de(q1) joined with sg_qb_db(q2) at the best cut;
+ *                          q1_len or q2_len may be 0 (that half is "H" * len(ref))
+ * Result: one column-run CIGAR per operation (ops = X I D S H), fetched with smx_ops_fetch; status 2 = an input on which
+ * the reference itself raises (empty local alignment, failed assertion). */
+#define SMX_OPKIND_NW 0
+#define SMX_OPKIND_SG_QE_DE 1
+#define SMX_OPKIND_SG_QB_DB 2
+#define SMX_OPKIND_SW 3
+#define SMX_OPKIND_SPECIAL_DP 4
+int smx_ops_run(smx_handle *h, const uint8_t *kind, const int64_t *ref_off, const int32_t *ref_len, const int64_t *q1_off,
+                const int32_t *q1_len, const int64_t *q2_off, const int32_t *q2_len, int32_t n, int32_t open, int32_t extend,
+                int32_t match, int32_t mismatch, int32_t n_threads, int64_t *total_runs);
+int smx_ops_fetch(smx_handle *h, int64_t *cigar_off, uint32_t *cigar_rle, int64_t cigar_capacity, uint8_t *status);
+
 /* ---- row N2: what consumes the score matrix and the CIGARs without per-result objects -------
  * smx_assign: msa.QueryAssignment (savemoney/modules/msa.py:31-64) on the device, one thread per read.
  *   score / status: [n_reads, 2 * n_refs] as smx_pipeline_fetch delivers them (status != 0 = empty MyResult());

@@ -111,6 +111,11 @@ struct smx_handle {
     PinBuf pin_regions, pin_cigar, pin_pool, pin_special;
     PinBuf pin_stage[16];  // page-locked staging of the small descriptor / result copies (PinSlot)
     struct SmxPipelineState *pipe = nullptr;
+    // smx_ops_run results (row N1): final column runs per operation
+    std::vector<uint32_t> ops_runs;
+    std::vector<int64_t> ops_off;
+    std::vector<uint8_t> ops_status;
+    bool ops_valid = false;
 };
 
 static const int kLineSlots = 4096;  // boundary-line pairs of the non-persistent forward launches (> resident workers of any class)
@@ -500,7 +505,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         if (mw) { const int v = atoi(mw); h->s16_max_wsel = v >= 8 ? 3 : v >= 4 ? 2 : v >= 2 ? 1 : 0; }
         static const char *const tenv[3] = {"SMX_TEAM2_MCELLS", "SMX_TEAM4_MCELLS", "SMX_TEAM8_MCELLS"};
         static const int64_t tdef[3] = {16, 48, 128};
-        for (int t = 0; t < 3; ++t) { const char *e = getenv(tenv[t]); h->team_cells[t] = (e && atol(e) > 0 ? (int64_t)atol(e) : tdef[t]) << 20; }
+        for (int t = 0; t < 3; ++t) { const char *e = getenv(tenv[t]); h->team_cells[t] = e && atof(e) > 0 ? (int64_t)(atof(e) * 1048576.0) : tdef[t] << 20; }
         const char *tc = getenv("SMX_TEAMS_CONCURRENT");
         h->teams_concurrent = h->use_s16h && !h->persistent_fwd && h->stream_team[0] && h->stream_team[1] && h->stream_team[2] && !(tc && tc[0] == '0');
     }
@@ -1696,6 +1701,133 @@ extern "C" int smx_pipeline_stats(smx_handle *h, double *out, int32_t n)
         else if (i == m + 47) out[i] = st.gpu_chain_ms;
         else out[i] = 0.0;
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row N1: the alignment operations of MyAlignerBase (ref_query_alignment.py:21-163) as one batch -- what
+// MyMSA.exec_chunk_poa (modules/msa.py:1249-1355) calls per read chunk, collected over a whole polish round
+// ------------------------------------------------------------------------------------------------
+extern "C" int smx_ops_run(smx_handle *h, const uint8_t *kind, const int64_t *ref_off, const int32_t *ref_len, const int64_t *q1_off,
+                           const int32_t *q1_len, const int64_t *q2_off, const int32_t *q2_len, int32_t n, int32_t open, int32_t extend,
+                           int32_t match, int32_t mismatch, int32_t n_threads, int64_t *total_runs)
+{
+    using namespace smx;
+    if (!h) return -1;
+    h->ops_valid = false;
+    if (total_runs) *total_runs = 0;
+    if (n < 0 || (n > 0 && (!kind || !ref_off || !ref_len || !q1_off || !q1_len))) return fail(h, -1, "smx_ops_run: NULL argument");
+    if (match <= 0 || mismatch >= 0) return fail(h, -1, "smx_ops_run needs match > 0 and mismatch < 0 (my_classes.py:547-552)");
+    if (n_threads <= 0) n_threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    const Scoring sc{open, extend, match, mismatch};
+    // plan: one DP problem for kinds 0..3, up to two for my_special_DP (an empty half has no problem)
+    std::vector<int64_t> p_s1, p_s2;
+    std::vector<int32_t> p_m, p_n;
+    std::vector<uint8_t> p_mode, p_clip;
+    std::vector<int32_t> first((size_t)n * 2, -1);
+    auto add = [&](int64_t qo, int32_t qn, int64_t ro, int32_t rn, uint8_t mode, uint8_t clip) {
+        p_s1.push_back(qo); p_m.push_back(qn); p_s2.push_back(ro); p_n.push_back(rn); p_mode.push_back(mode); p_clip.push_back(clip);
+        return (int32_t)p_m.size() - 1;
+    };
+    for (int i = 0; i < n; ++i) {
+        if (ref_len[i] <= 0) return fail(h, -1, "operation %d: empty reference", i);
+        switch (kind[i]) {
+        case SMX_OPKIND_NW: case SMX_OPKIND_SG_QE_DE: case SMX_OPKIND_SG_QB_DB: case SMX_OPKIND_SW:
+            if (q1_len[i] <= 0) return fail(h, -1, "operation %d: empty query (callers never pass empty strings)", i);
+            first[(size_t)i * 2] = add(q1_off[i], q1_len[i], ref_off[i], ref_len[i],
+                                       kind[i] == SMX_OPKIND_NW ? SMX_MODE_NW : kind[i] == SMX_OPKIND_SG_QE_DE ? SMX_MODE_SG_QE_DE : kind[i] == SMX_OPKIND_SG_QB_DB ? SMX_MODE_SG_QB_DB : SMX_MODE_SW,
+                                       (kind[i] == SMX_OPKIND_SG_QE_DE || kind[i] == SMX_OPKIND_SG_QB_DB) ? 1 : 0);
+            break;
+        case SMX_OPKIND_SPECIAL_DP:
+            if (!q2_off || !q2_len) return fail(h, -1, "operation %d: my_special_DP needs the second query", i);
+            if (q1_len[i] > 0) first[(size_t)i * 2] = add(q1_off[i], q1_len[i], ref_off[i], ref_len[i], SMX_MODE_SG_QE_DE, 1);
+            if (q2_len[i] > 0) first[(size_t)i * 2 + 1] = add(q2_off[i], q2_len[i], ref_off[i], ref_len[i], SMX_MODE_SG_QB_DB, 1);
+            break;
+        default: return fail(h, -1, "operation %d: unknown kind %d", i, (int)kind[i]);
+        }
+    }
+    const int n_prob = (int)p_m.size();
+    std::vector<int64_t> cg_off((size_t)n_prob + 1, 0);
+    std::vector<uint32_t> cg;
+    if (n_prob > 0) {
+        if (int rc = align_prepare_impl(h, p_s1.data(), p_m.data(), p_s2.data(), p_n.data(), p_mode.data(), p_clip.data(), n_prob, open, extend, match, mismatch)) return rc;
+        int64_t truns = 0;
+        if (int rc = align_run_impl(h, &truns, nullptr)) return rc;
+        cg.resize((size_t)std::max<int64_t>(truns, 1));
+        if (int rc = smx_align_fetch(h, nullptr, nullptr, nullptr, nullptr, nullptr, cg_off.data(), cg.data(), (int64_t)cg.size())) return rc;
+    }
+    const std::vector<SmxResult> &dres = h->h_results;
+    std::vector<Runs> out((size_t)n);
+    h->ops_status.assign((size_t)n, 0);
+    auto clipped = [&](int pid) {
+        ClippedSg c;
+        c.kept = &cg[(size_t)cg_off[(size_t)pid]];
+        c.n_kept = cg_off[(size_t)pid + 1] - cg_off[(size_t)pid];
+        c.n_s = dres[(size_t)pid].n_s; c.n_h = dres[(size_t)pid].n_h;
+        return c;
+    };
+    parallel_for(n, n_threads, [&](int i, int) {
+        Runs &v = out[(size_t)i];
+        const int p0 = first[(size_t)i * 2], p1 = first[(size_t)i * 2 + 1];
+        switch (kind[i]) {
+        case SMX_OPKIND_NW:
+            append_maximal_runs(v, &cg[(size_t)cg_off[(size_t)p0]], cg_off[(size_t)p0 + 1] - cg_off[(size_t)p0]);
+            break;
+        case SMX_OPKIND_SG_QE_DE: {  // my_special_sg_qe_de (:60-73): aligned S.. H..
+            const ClippedSg c = clipped(p0);
+            append_maximal_runs(v, c.kept, c.n_kept); push_run(v, 4, c.n_s); push_run(v, 5, c.n_h);
+            break;
+        }
+        case SMX_OPKIND_SG_QB_DB: {  // my_special_sg_qb_db (:74-87): H.. S.. aligned
+            const ClippedSg c = clipped(p0);
+            push_run(v, 5, c.n_h); push_run(v, 4, c.n_s); append_maximal_runs(v, c.kept, c.n_kept);
+            break;
+        }
+        case SMX_OPKIND_SW: {  // my_special_sw (:34-56)
+            const SmxResult &r = dres[(size_t)p0];
+            const uint32_t *runs = &cg[(size_t)cg_off[(size_t)p0]];
+            const int64_t nr = cg_off[(size_t)p0 + 1] - cg_off[(size_t)p0];
+            if (nr == 0) { h->ops_status[(size_t)i] = 2; break; }  // my_cigar[0] of an empty local alignment raises in the reference
+            if ((runs[0] & 15u) != 2u) {
+                push_run(v, 5, r.beg_r); push_run(v, 4, r.beg_q);
+                append_runs(v, runs, nr);
+            } else {  // a leading D run (parasail quirk, :37-54): becomes H; the reference asserts beg_ref == beg_query == 0
+                if (r.beg_r != 0 || r.beg_q != 0) { h->ops_status[(size_t)i] = 2; break; }
+                push_run(v, 5, runs[0] >> 4);
+                append_runs(v, runs + 1, nr - 1);
+            }
+            push_run(v, 4, (int64_t)q1_len[i] - r.end_q - 1);
+            push_run(v, 5, (int64_t)ref_len[i] - r.end_r - 1);
+            break;
+        }
+        default: {  // my_special_DP (:89-163)
+            ClippedSg r1, r2;
+            if (p0 >= 0) r1 = clipped(p0); else r1.n_h = ref_len[i];   // "H" * len(ref), end_ref = -1
+            if (p1 >= 0) r2 = clipped(p1); else r2.n_h = ref_len[i];   // "H" * len(ref), beg_ref = len(ref)
+            if (!merge_special_runs(r1, r2, ref_len[i], q1_len[i], q2_len[i], sc, v)) h->ops_status[(size_t)i] = 2;
+        }
+        }
+    });
+    h->ops_off.assign((size_t)n + 1, 0);
+    for (int i = 0; i < n; ++i) h->ops_off[(size_t)i + 1] = h->ops_off[(size_t)i] + (int64_t)out[(size_t)i].size();
+    h->ops_runs.resize((size_t)h->ops_off[(size_t)n]);
+    parallel_for(n, n_threads, [&](int i, int) {
+        if (!out[(size_t)i].empty()) memcpy(h->ops_runs.data() + h->ops_off[(size_t)i], out[(size_t)i].data(), sizeof(uint32_t) * out[(size_t)i].size());
+    });
+    h->ops_valid = true;
+    if (total_runs) *total_runs = h->ops_off[(size_t)n];
+    return 0;
+}
+
+extern "C" int smx_ops_fetch(smx_handle *h, int64_t *cigar_off, uint32_t *cigar_rle, int64_t cigar_capacity, uint8_t *status)
+{
+    if (!h) return -1;
+    if (!h->ops_valid) return fail(h, -1, "smx_ops_fetch: no completed smx_ops_run");
+    const int64_t total = h->ops_off.empty() ? 0 : h->ops_off.back();
+    if (cigar_capacity < total) return fail(h, -1, "smx_ops_fetch: cigar buffer too small");
+    if (cigar_off) memcpy(cigar_off, h->ops_off.data(), sizeof(int64_t) * h->ops_off.size());
+    if (cigar_rle && total > 0) memcpy(cigar_rle, h->ops_runs.data(), sizeof(uint32_t) * (size_t)total);
+    if (status && !h->ops_status.empty()) memcpy(status, h->ops_status.data(), h->ops_status.size());
     return 0;
 }
 

@@ -89,3 +89,21 @@ def test_split_last_band_row_counts(engine, split):
                 modes.append(mode)
     with _Env(SMX_S16H_SPLIT=split):
         run_and_compare(engine, probs, np.array(modes), (3, 1, 1, -2))
+
+
+@pytest.mark.parametrize("env", [dict(), dict(SMX_TEAMS_CONCURRENT="0"), dict(SMX_S16_MAXW="2"), dict(SMX_S16_MAXW="4")])
+def test_teams_next_to_the_one_warp_launch(engine, env):
+    """The largest problems of a chunk run as teams of 2 / 4 / 8 warps on their own streams while the one-warp-per-problem
+    launch takes the rest (fork / join by events); with the thresholds lowered every team width gets problems here:
+    2 warps from 4 band pairs, 4 from 8, 8 from 16 (rows 1 600 .. 8 200), semi-global ends included."""
+    rng = np.random.default_rng(71)
+    probs, modes = [], []
+    for m, n in ((1600, 700), (2200, 500), (2300, 900), (3700, 420), (4200, 380), (4100, 610), (7800, 300), (8200, 333), (600, 900), (90, 70), (300, 2000)):
+        ref = util.rand_seq(rng, n)
+        q = util.mutate(rng, (ref * (m // n + 2))[:m], 0.08, 0.03, 0.03)[:m]
+        for mode in (0, 1, 2):
+            probs.append((q, ref)); modes.append(mode)
+    probs += util.make_problems(rng, 30, 500)
+    modes += [int(x) for x in rng.integers(0, 3, size=30)]
+    with _Env(SMX_TEAM2_MCELLS="0.5", SMX_TEAM4_MCELLS="1.2", SMX_TEAM8_MCELLS="2.0", **env):
+        run_and_compare(engine, probs, modes, (3, 1, 1, -2))
