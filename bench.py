@@ -387,7 +387,8 @@ def run_engine(args, rank, world, local_rank):
         dev_s = dense_state["kernel_ms_total"] * 1e-3 * args.steps
         agg = dict(agg, **{f"dp_ms_class{c}": dense_state["class_ms"][c] * args.steps for c in range(14)},
                    **{f"dp_cells_class{c}": dense_state["class_cells"][c] * args.steps for c in range(14)},
-                   **{f"dp_launches_{c}": dense_state["class_launches"][c] * args.steps for c in range(16)})
+                   **{f"dp_launches_{c}": dense_state["class_launches"][c] * args.steps for c in range(16)},
+                   dp_ms_traceback=dense_state["class_ms"][14] * args.steps, dp_ms_compact=dense_state["class_ms"][15] * args.steps)
         value_source = "CUDA events on the engine stream around every forward / traceback / compaction launch of the last timed step, scaled to the K steps"
     else:
         if args.overlap > 1 and wl.kind != "pairs":

@@ -40,6 +40,7 @@ struct Chunk {
     int first = 0, count = 0;            // range in the size-sorted order
     int n_big = 0;                       // traceback: the first n_big problems of the chunk's order_all range get a warp each
     int cls_first[14] = {0}, cls_count[14] = {0};  // per kernel class ranges inside order_cls (see problem_class)
+    int cls_local[14] = {0};             // packed classes: how many problems at the END of the class range are local (sw_trace)
     size_t trace_bytes = 0;
 };
 
@@ -441,13 +442,13 @@ static bool s16h_scoring_ok(const SmxScoring &sc)
 
 static bool s16_eligible(const smx_handle *h, int64_t s2_off, int m, int n, int mode)
 {
-    if (mode == SMX_MODE_SW || m <= (h->use_s16h ? h->s16_min_rows : 256)) return false;
+    if ((mode == SMX_MODE_SW && !h->use_s16h) || m <= (h->use_s16h ? h->s16_min_rows : 256)) return false;  // local mode: diagonal-frame kernel only
     const SmxScoring &sc = h->sc;
     if (h->use_s16h) {
         // biased unsigned halves: BIAS + H^ <= BIAS + max(match, 0) * min(rows, cols) + ge * (rows + cols), with the
         // padded rows and the 96 extra steps a band pair runs past / before the matrix, plus their growth
         const int64_t rows = (int64_t)(((m + 255) / 256 + 1) / 2) * 512, cols = (int64_t)n + 96;
-        const int64_t bias = 3ll * sc.go + std::abs(sc.go - sc.ge) + 16;
+        const int64_t bias = 3ll * sc.go + std::abs(sc.go - sc.ge) + 16 + (mode == SMX_MODE_SW ? 32ll * sc.ge : 0);
         const int64_t top = bias + (int64_t)std::max(sc.match, 0) * std::min(rows, cols) + (int64_t)sc.ge * (rows + cols) +
                             96ll * (std::abs(sc.match) + sc.go + 2 * sc.ge) + 64;
         if (top > 65000) return false;
@@ -542,8 +543,6 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
             q.cls = (int16_t)(kClsS16 + wsel);
             q.kshift = 3;  // the packed kernels always run 8 rows per lane (trace layout and traceback follow kshift)
         }
-        // concurrent teams: the packed forward phase (one-warp launch + team launches side by side) is timed as ONE interval
-        h->class_cells[(h->teams_concurrent && q.cls > kClsS16) ? kClsS16 : q.cls] += (int64_t)m * nn;
         q.trace_off = 0;
         q.cigar_off = runs_off;
         runs_off += (int64_t)m + nn + 2;
@@ -551,6 +550,32 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         h->nmax = std::max(h->nmax, nn);
     }
     h->runs_scratch = runs_off;
+    // Few packed problems (a legacy-dense call holds ~200 problems of 100 M cells; C3 a handful of large pairs) cannot fill
+    // the 148 x 16 resident warps one or even four warps each: widen the teams of the largest problems until the batch
+    // offers about that many warps (at least one band pair per warp).
+    if (h->use_s16 && h->s16_max_wsel > 0) {
+        int64_t warps = 0;
+        std::vector<int32_t> packed;
+        for (int p = 0; p < n; ++p) if (h->probs[(size_t)p].cls >= kClsS16) { warps += 1 << (h->probs[(size_t)p].cls - kClsS16); packed.push_back(p); }
+        const int64_t target = (int64_t)h->sm_count * 16 * 3 / 4;
+        if (!packed.empty() && warps < target) {
+            std::sort(packed.begin(), packed.end(), [&](int32_t x, int32_t y) { return (int64_t)h->probs[x].m * h->probs[x].n > (int64_t)h->probs[y].m * h->probs[y].n; });
+            for (int round = 0; round < 3 && warps < target; ++round)
+                for (int32_t p : packed) {
+                    SmxProblem &q = h->probs[(size_t)p];
+                    const int wsel = q.cls - kClsS16, pairs = ((q.m + 255) / 256 + 1) / 2;
+                    if (wsel >= h->s16_max_wsel || pairs < (2 << wsel) || (int64_t)q.m * q.n < (1 << 20)) continue;
+                    q.cls = (int16_t)(q.cls + 1);
+                    warps += 1 << wsel;
+                    if (warps >= target) break;
+                }
+        }
+    }
+    // concurrent teams: the packed forward phase (one-warp launch + team launches side by side) is timed as ONE interval
+    for (int p = 0; p < n; ++p) {
+        const SmxProblem &q = h->probs[(size_t)p];
+        h->class_cells[(h->teams_concurrent && q.cls > kClsS16) ? kClsS16 : q.cls] += (int64_t)q.m * q.n;
+    }
     // class-major order (largest kernel class first; counting sort), the large classes size-sorted inside so
     // that their longest problems start first; then greedy chunking under the trace budget.  The small classes
     // (86 % of the problems, 1 % of the cells) are left in input order.
@@ -566,6 +591,9 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
             const int cls = kNumFwdClasses - 1 - c;
             if (cls < 6) continue;  // K <= 4 rows per lane: tiny problems
             std::stable_sort(order.begin() + cnt[c], order.begin() + cnt[c + 1], [&](int32_t x, int32_t y) {
+                // packed classes: the local problems form the tail of the class range (they run a kernel of their own)
+                const bool lx = cls >= kClsS16 && (h->probs[x].mode & SMX_MODE_MASK) == SMX_MODE_SW, ly = cls >= kClsS16 && (h->probs[y].mode & SMX_MODE_MASK) == SMX_MODE_SW;
+                if (lx != ly) return ly;
                 return (int64_t)h->probs[x].m * h->probs[x].n > (int64_t)h->probs[y].m * h->probs[y].n;
             });
         }
@@ -579,7 +607,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         Chunk c;
         c.first = pos;
         size_t bytes = 0;
-        for (int cls = 0; cls < kNumFwdClasses; ++cls) { c.cls_first[cls] = pos; c.cls_count[cls] = 0; }
+        for (int cls = 0; cls < kNumFwdClasses; ++cls) { c.cls_first[cls] = pos; c.cls_count[cls] = 0; c.cls_local[cls] = 0; }
         while (pos < n) {
             SmxProblem &q = h->probs[(size_t)order[pos]];
             size_t tb = (size_t)smx_trace_bytes(q.m, q.n, 1 << q.kshift);
@@ -589,6 +617,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
             bytes += tb;
             if (c.cls_count[q.cls] == 0) c.cls_first[q.cls] = pos;
             ++c.cls_count[q.cls];
+            if (q.cls >= kClsS16 && (q.mode & SMX_MODE_MASK) == SMX_MODE_SW) ++c.cls_local[q.cls];
             ++c.count; ++pos;
         }
         c.trace_bytes = bytes;
@@ -609,7 +638,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
     if (int rc = ensure(h, h->d_trace, h->max_chunk_trace + 256)) return rc;
     if (int rc = ensure(h, h->d_runs, sizeof(uint32_t) * (size_t)h->runs_scratch)) return rc;
     if (int rc = ensure(h, h->d_dense_off, sizeof(int64_t) * ((size_t)n + 1))) return rc;
-    if (int rc = ensure(h, h->d_tickets, sizeof(int32_t) * kNumFwdClasses * h->chunks.size())) return rc;
+    if (int rc = ensure(h, h->d_tickets, sizeof(int32_t) * 2 * kNumFwdClasses * h->chunks.size())) return rc;
     if (int rc = h2d(h, PIN_PROBS, h->d_probs.p, h->probs.data(), sizeof(SmxProblem) * (size_t)n, h->stream_hi)) return rc;
     if (int rc = h2d(h, PIN_ORDER_CLS, h->d_order_cls.p, h->order_cls.data(), sizeof(int32_t) * (size_t)n, h->stream_hi)) return rc;
     if (int rc = h2d(h, PIN_ORDER_ALL, h->d_order_all.p, h->order_all.data(), sizeof(int32_t) * (size_t)n, h->stream_hi)) return rc;
@@ -668,7 +697,7 @@ static int launch_forward(smx_handle *h, const Chunk &c, int cls, int chunk_idx)
     a.probs = (const SmxProblem *)h->d_probs.p;
     a.order = (const int32_t *)h->d_order_cls.p + c.cls_first[cls];
     a.n_order = count;
-    a.ticket = (int32_t *)h->d_tickets.p + chunk_idx * kNumFwdClasses + cls;
+    a.ticket = (int32_t *)h->d_tickets.p + (size_t)chunk_idx * 2 * kNumFwdClasses + cls;
     a.trace = (uint8_t *)h->d_trace.p;
     a.boundary = (int2 *)h->d_boundary.p;
     a.nmax = h->nmax;
@@ -686,42 +715,46 @@ static int launch_forward(smx_handle *h, const Chunk &c, int cls, int chunk_idx)
 template <int W>
 static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_idx, cudaStream_t stream = nullptr, bool do_mark = true)
 {
-    const int count = c.cls_count[cls];
-    if (count == 0) return 0;
+    if (c.cls_count[cls] == 0) return 0;
     if (!stream) stream = h->stream;
     const bool TEAM = W > 1;
     const int threads = TEAM ? W * 32 : (h->use_s16h ? 32 * SMX16H_WPC : 128);
-    int occ = 0;
-    void (*kern)(const SmxFwdArgs) = h->use_s16h ? smx_dp_forward16h<W> : smx_dp_forward16<W>;
-    SMX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
-    if (occ < 1) occ = 1;
-    const int per_block = TEAM ? 1 : threads / 32;
-    // smx_dp16h.cuh is launched non-persistent (one problem per worker, boundary lines claimed from a slot pool)
-    const bool persistent = !h->use_s16h || h->persistent_fwd;
-    int blocks = (count + per_block - 1) / per_block;
-    if (persistent) blocks = std::min(h->sm_count * occ, blocks);
-    if (blocks < 1) blocks = 1;
-    const size_t workers = !persistent ? (size_t)kLineSlots : TEAM ? (size_t)blocks : (size_t)blocks * (threads / 32);
-    if (int rc = ensure(h, h->d_boundary, sizeof(int2) * 2 * (size_t)h->nmax * workers)) return rc;
-    SmxFwdArgs a;
-    a.pool = (const uint8_t *)h->pool.p;
-    a.probs = (const SmxProblem *)h->d_probs.p;
-    a.order = (const int32_t *)h->d_order_cls.p + c.cls_first[cls];
-    a.n_order = count;
-    a.ticket = (int32_t *)h->d_tickets.p + chunk_idx * kNumFwdClasses + cls;
-    a.trace = (uint8_t *)h->d_trace.p;
-    a.boundary = (int2 *)h->d_boundary.p;
-    a.nmax = h->nmax;
-    a.results = (SmxResult *)h->d_results.p;
-    a.sc = h->sc;
-    a.one = 1u;
-    a.max_tickets = persistent ? INT32_MAX : 1;
-    a.n_slots = kLineSlots;
-    a.slot_flags = persistent ? nullptr : (int32_t *)h->d_slots.p;
-    a.split_last = h->split_last;
-    kern<<<blocks, threads, 0, stream>>>(a);
-    SMX_CUDA(h, cudaGetLastError());
-    h->last_launches++;
+    // the global / semi-global problems of the class, then its local problems (tail of the class range, own kernel)
+    for (int local = 0; local < 2; ++local) {
+        const int count = local ? c.cls_local[cls] : c.cls_count[cls] - c.cls_local[cls];
+        if (count == 0) continue;
+        int occ = 0;
+        void (*kern)(const SmxFwdArgs) = !h->use_s16h ? smx_dp_forward16<W> : local ? smx_dp_forward16h<W, true> : smx_dp_forward16h<W, false>;
+        SMX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
+        if (occ < 1) occ = 1;
+        const int per_block = TEAM ? 1 : threads / 32;
+        // smx_dp16h.cuh is launched non-persistent (one problem per worker, boundary lines claimed from a slot pool)
+        const bool persistent = !h->use_s16h || h->persistent_fwd;
+        int blocks = (count + per_block - 1) / per_block;
+        if (persistent) blocks = std::min(h->sm_count * occ, blocks);
+        if (blocks < 1) blocks = 1;
+        const size_t workers = !persistent ? (size_t)kLineSlots : TEAM ? (size_t)blocks : (size_t)blocks * (threads / 32);
+        if (int rc = ensure(h, h->d_boundary, sizeof(int2) * 2 * (size_t)h->nmax * workers)) return rc;
+        SmxFwdArgs a;
+        a.pool = (const uint8_t *)h->pool.p;
+        a.probs = (const SmxProblem *)h->d_probs.p;
+        a.order = (const int32_t *)h->d_order_cls.p + c.cls_first[cls] + (local ? c.cls_count[cls] - c.cls_local[cls] : 0);
+        a.n_order = count;
+        a.ticket = (int32_t *)h->d_tickets.p + ((size_t)chunk_idx * 2 + local) * kNumFwdClasses + cls;
+        a.trace = (uint8_t *)h->d_trace.p;
+        a.boundary = (int2 *)h->d_boundary.p;
+        a.nmax = h->nmax;
+        a.results = (SmxResult *)h->d_results.p;
+        a.sc = h->sc;
+        a.one = 1u;
+        a.max_tickets = persistent ? INT32_MAX : 1;
+        a.n_slots = kLineSlots;
+        a.slot_flags = persistent ? nullptr : (int32_t *)h->d_slots.p;
+        a.split_last = h->split_last;
+        kern<<<blocks, threads, 0, stream>>>(a);
+        SMX_CUDA(h, cudaGetLastError());
+        h->last_launches++;
+    }
     return do_mark ? mark(h, cls) : 0;
 }
 
@@ -751,7 +784,7 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
     } guard{gate};
     if (gate) gate->enter();
     SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    SMX_CUDA(h, cudaMemsetAsync(h->d_tickets.p, 0, sizeof(int32_t) * kNumFwdClasses * h->chunks.size(), h->stream));
+    SMX_CUDA(h, cudaMemsetAsync(h->d_tickets.p, 0, sizeof(int32_t) * 2 * kNumFwdClasses * h->chunks.size(), h->stream));
     SMX_CUDA(h, cudaMemsetAsync(h->d_slots.p, 0, sizeof(int32_t) * kLineSlots, h->stream));  // an aborted launch must not leave lines claimed
     h->ev_used = 0;
     for (int c = 0; c < kNumSlots; ++c) { h->kernel_ms[c] = 0.0; h->kernel_launches[c] = 0; }

@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(TEAM ? SMX_TEAM_WARPS * 32 : 128) smx_dp_forwa
                             word |= nib << (4 * k);
                             if (LOCAL) {
                                 const int i = i0 + k;
-                                if (i < m && (h > loc_best || (h == loc_best && h > 0 && (i < loc_i || (i == loc_i && j < loc_j))))) {
+                                if (i < m && (h > loc_best || (h == loc_best && h > 0 && (j < loc_j || (j == loc_j && i < loc_i))))) {
                                     loc_best = h; loc_i = i; loc_j = j;
                                 }
                             }
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(TEAM ? SMX_TEAM_WARPS * 32 : 128) smx_dp_forwa
                 const int ob = __shfl_xor_sync(SMX_FULL_MASK, loc_best, off);
                 const int oi = __shfl_xor_sync(SMX_FULL_MASK, loc_i, off);
                 const int oj = __shfl_xor_sync(SMX_FULL_MASK, loc_j, off);
-                if (ob > loc_best || (ob == loc_best && ob > 0 && (oi < loc_i || (oi == loc_i && oj < loc_j)))) {
+                if (ob > loc_best || (ob == loc_best && ob > 0 && (oj < loc_j || (oj == loc_j && oi < loc_i)))) {
                     loc_best = ob; loc_i = oi; loc_j = oj;
                 }
             }
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(TEAM ? SMX_TEAM_WARPS * 32 : 128) smx_dp_forwa
                 if (threadIdx.x == 0) {
                     for (int w = 1; w < W; ++w) {
                         const int ob = s_red[w][0], oi = s_red[w][1], oj = s_red[w][2];
-                        if (ob > loc_best || (ob == loc_best && ob > 0 && (oi < loc_i || (oi == loc_i && oj < loc_j)))) {
+                        if (ob > loc_best || (ob == loc_best && ob > 0 && (oj < loc_j || (oj == loc_j && oi < loc_i)))) {
                             loc_best = ob; loc_i = oi; loc_j = oj;
                         }
                     }

@@ -70,7 +70,45 @@ struct Smx16hCol {  // per-column scalars threaded through the K cells of a lane
     uint32_t hcu;   // Hc(i-1, j)
     uint32_t w_lo[2], w_hi[2];  // direction-bit accumulators; K = 8: even / odd rows of one word, K = 16: rows 0-7 / 8-15
     uint32_t one;
+    // LOCAL (sw_trace): the zero of the current row in the diagonal frame, its increment per row, best H seen by the lane
+    uint32_t z, ge2, m;
 };
+
+// Local alignment (parasail.sw_trace, ref_query_alignment.py:35) in the diagonal frame.  H = max(0, ...) becomes
+// h = max(h, Z(i, j)) with the per-cell constant Z = BIAS + ge * (i + j): along a lane's column it grows by ge per row,
+// from step to step by ge.  The end cell is the maximum of H = h - Z; per lane and half only the running maximum is kept
+// (one subtraction and one VIMNMX per cell pair), and a step that raises it leaves the lane's K state words and its step
+// number in shared memory, from which the row is read back once per band pair.  Order among equal maxima: smallest
+// reference position, then smallest query position (parasail's sw: `WH > score`, else `WH == score && j - 1 < end_ref`).
+// The ZERO stop of the traceback needs no direction bit: the walker tracks the score of the cell it stands on.
+struct Smx16hLocal {
+    uint32_t zs;      // Z of the lane's row 0 at the current step, both halves
+    uint32_t ge2;     // ge in both halves
+    uint32_t lbest;   // best H of the lane in this band pair, both halves
+    int s_lo, s_hi;   // step of the first time the half reached its lbest
+    uint32_t *snap;   // shared: [half][k][lane] state words Hc[k] of that step, then [half][lane] zs of that step
+};
+template <int K>
+__device__ __forceinline__ void smx16h_local_step(Smx16hLocal &L, const uint32_t (&Hc)[K], uint32_t m, int s, int lane)
+{
+    if (m != L.lbest) {   // some half of this lane reached a new maximum (strictly: m >= lbest in both halves)
+        const bool up_lo = (m & 0xffffu) != (L.lbest & 0xffffu), up_hi = (m >> 16) != (L.lbest >> 16);
+        if (up_lo) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) L.snap[k * 32 + lane] = Hc[k];
+            L.snap[2 * K * 32 + lane] = L.zs;
+            L.s_lo = s;
+        }
+        if (up_hi) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) L.snap[(K + k) * 32 + lane] = Hc[k];
+            L.snap[2 * K * 32 + 32 + lane] = L.zs;
+            L.s_hi = s;
+        }
+        L.lbest = m;
+    }
+    L.zs += L.ge2;
+}
 
 // EDGE: a chunk in which some lane's half is not inside the matrix (column < 0 or >= n).  Such a half HOLDS its state:
 // `hold` has 0xffff in every half that is inside, and the new state is merged as (new & hold) | (old & ~hold) -- one
@@ -83,7 +121,7 @@ __device__ __forceinline__ uint32_t smx16h_merge(uint32_t nv, uint32_t ov, uint3
     return r;
 }
 
-template <int K, int k, bool EDGE = false>
+template <int K, int k, bool EDGE = false, bool LOCAL = false>
 struct Smx16hCell {
     static __device__ __forceinline__ void run(uint32_t (&Hc)[K], uint32_t (&El)[K], const uint32_t (&plo)[K], const uint32_t (&phi)[K],
                                                Smx16hCol &c, uint32_t sel, uint32_t negc2, uint32_t hold = 0xffffffffu)
@@ -96,18 +134,24 @@ struct Smx16hCell {
         const uint32_t f = smx16h_max_tr<(8u << SH), (SMX16H_ALU_FLAGS < 3)>(c.fu, c.hcu, n_lo, n_hi, c.one);
         const uint32_t hdiag = c.hd + smx_subst_u(plo[k], phi[k], sel);  // no carry between the halves: s'' >= 0, no wrap
         const uint32_t t = smx16h_max_tr<(2u << SH), (SMX16H_ALU_FLAGS < 2)>(f, e, n_lo, n_hi, c.one);
-        const uint32_t h = smx16h_max_tr<(1u << SH), (SMX16H_ALU_FLAGS < 4)>(hdiag, t, n_lo, n_hi, c.one);
+        uint32_t h = smx16h_max_tr<(1u << SH), (SMX16H_ALU_FLAGS < 4)>(hdiag, t, n_lo, n_hi, c.one);
+        if (LOCAL) {
+            asm("max.u16x2 %0, %0, %1;" : "+r"(h) : "r"(c.z));            // H = max(H, 0)
+            const uint32_t u = EDGE ? ((h - c.z) & hold) : (h - c.z);     // H itself (>= 0 in both halves: no borrow); a held half does not count
+            asm("max.u16x2 %0, %0, %1;" : "+r"(c.m) : "r"(u));
+            c.z += c.ge2;
+        }
         const uint32_t hc = h + negc2;  // - (go - ge) in both halves; the low half never borrows (bias)
         c.hd = Hc[k];
         Hc[k] = EDGE ? smx16h_merge(hc, Hc[k], hold) : hc;
         El[k] = EDGE ? smx16h_merge(e, El[k], hold) : e;
         c.fu = f;
         c.hcu = hc;
-        Smx16hCell<K, k + 1, EDGE>::run(Hc, El, plo, phi, c, sel, negc2, hold);
+        Smx16hCell<K, k + 1, EDGE, LOCAL>::run(Hc, El, plo, phi, c, sel, negc2, hold);
     }
 };
-template <int K, bool EDGE>
-struct Smx16hCell<K, K, EDGE> {
+template <int K, bool EDGE, bool LOCAL>
+struct Smx16hCell<K, K, EDGE, LOCAL> {
     static __device__ __forceinline__ void run(uint32_t (&)[K], uint32_t (&)[K], const uint32_t (&)[K], const uint32_t (&)[K], Smx16hCol &, uint32_t,
                                                uint32_t, uint32_t = 0) {}
 };
@@ -131,12 +175,12 @@ __device__ __forceinline__ int smx16h_hi(uint32_t v) { return (int)(v >> 16); }
 // stored half of the last query row back into H (semi-global end in the last row): H = half - ge * j + tconst.
 // SPLIT (K = 4, see the kernel): the lane's 4 nibbles per half are one 16-bit word; tp_lo / tp_hi point at the lane's
 // word of step s0 in the half-band's [step][lane] region and advance by one 64-byte line per step.
-template <int K, bool HAS_HI, bool TRACK, bool SPLIT>
+template <int K, bool HAS_HI, bool TRACK, bool SPLIT, bool LOCAL = false>
 __device__ __forceinline__ void smx16h_fast_chunk(uint32_t (&Hc)[K], uint32_t (&El)[K], const uint32_t (&plo)[K], const uint32_t (&phi)[K],
                                                   uint32_t &hd, uint32_t &out_h, uint32_t &out_f, uint32_t &sel_prev, const uint4 *tops,
                                                   uint32_t lane0_mask, uint32_t negc2, uint32_t *tp_lo, uint32_t *tp_hi, uint32_t *bl, uint32_t *bh,
                                                   uint32_t st_flags, uint32_t tmask, int last_k, int jbase, int ge, int tconst, int &row_best,
-                                                  int &row_best_j, uint32_t one)
+                                                  int &row_best_j, uint32_t one, Smx16hLocal *L = nullptr, int s0 = 0, int lane = 0)
 {
     SMX16_PRAGMA(unroll SMX16_UNROLL)
     for (int ss = 0; ss < 32; ++ss) {
@@ -150,7 +194,9 @@ __device__ __forceinline__ void smx16h_fast_chunk(uint32_t (&Hc)[K], uint32_t (&
         sel_prev = sel;
         Smx16hCol c;
         c.hd = hd; c.fu = fu; c.hcu = hu; c.w_lo[0] = 0; c.w_lo[1] = 0; c.w_hi[0] = 0; c.w_hi[1] = 0; c.one = one;
-        Smx16hCell<K, 0>::run(Hc, El, plo, phi, c, sel, negc2);
+        if (LOCAL) { c.z = L->zs; c.ge2 = L->ge2; c.m = L->lbest; }
+        Smx16hCell<K, 0, false, LOCAL>::run(Hc, El, plo, phi, c, sel, negc2);
+        if (LOCAL) smx16h_local_step<K>(*L, Hc, HAS_HI ? c.m : ((c.m & 0xffffu) | (L->lbest & 0xffff0000u)), s0 + ss, lane);
         hd = hu;
         out_h = c.hcu;
         out_f = c.fu;
@@ -184,12 +230,12 @@ __device__ __forceinline__ void smx16h_fast_chunk(uint32_t (&Hc)[K], uint32_t (&
 // One 32-step chunk at an edge of the matrix (see Smx16hCell<EDGE>): the interior chunk plus the hold masks, per-lane
 // predicates on the direction-word and boundary-line stores, and validity on the last-row tracking.  `jl0` = column
 // of this lane's low half at the first step of the chunk (the high half is LAG columns behind).
-template <int K, bool HAS_HI, bool SPLIT>
+template <int K, bool HAS_HI, bool SPLIT, bool LOCAL = false>
 __device__ __forceinline__ void smx16h_edge_chunk(uint32_t (&Hc)[K], uint32_t (&El)[K], const uint32_t (&plo)[K], const uint32_t (&phi)[K],
                                                   uint32_t &hd, uint32_t &out_h, uint32_t &out_f, uint32_t &sel_prev, const uint4 *tops,
                                                   uint32_t lane0_mask, uint32_t negc2, uint32_t *tp_lo, uint32_t *tp_hi, uint32_t *bl, uint32_t *bh,
                                                   uint32_t st_flags, uint32_t tmask, int last_k, int jl0, int n, int ge, int tconst, int &row_best,
-                                                  int &row_best_j, uint32_t one)
+                                                  int &row_best_j, uint32_t one, Smx16hLocal *L = nullptr, int s0 = 0, int lane = 0)
 {
 #pragma unroll 1
     for (int ss = 0; ss < 32; ++ss) {
@@ -207,7 +253,9 @@ __device__ __forceinline__ void smx16h_edge_chunk(uint32_t (&Hc)[K], uint32_t (&
         const uint32_t hold = (v_lo ? 0x0000ffffu : 0u) | (v_hi ? 0xffff0000u : 0u);
         Smx16hCol c;
         c.hd = hd; c.fu = fu; c.hcu = hu; c.w_lo[0] = 0; c.w_lo[1] = 0; c.w_hi[0] = 0; c.w_hi[1] = 0; c.one = one;
-        Smx16hCell<K, 0, true>::run(Hc, El, plo, phi, c, sel, negc2, hold);
+        if (LOCAL) { c.z = L->zs; c.ge2 = L->ge2; c.m = L->lbest; }
+        Smx16hCell<K, 0, true, LOCAL>::run(Hc, El, plo, phi, c, sel, negc2, hold);
+        if (LOCAL) smx16h_local_step<K>(*L, Hc, c.m, s0 + ss, lane);
         hd = smx16h_merge(hu, hd, hold);
         out_h = c.hcu;
         out_f = c.fu;
@@ -235,7 +283,7 @@ __device__ __forceinline__ void smx16h_edge_chunk(uint32_t (&Hc)[K], uint32_t (&
 }
 
 // boundary lines: one uint32 per column = F^ << 16 | Hc (biased unsigned halves)
-template <int W>
+template <int W, bool LOCAL = false>
 __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_WARPS_PER_SM / (W == 1 ? SMX16H_WPC : W)) smx_dp_forward16h(const SmxFwdArgs a)
 {
     constexpr bool TEAM = W > 1;
@@ -262,7 +310,9 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_W
     uint32_t *line1 = line0 + a.nmax;
     const int go = a.sc.go, ge = a.sc.ge;
     const int cc = go - ge;                                   // Hc = H^ - cc
-    const int BIAS = 3 * go + (cc < 0 ? -cc : cc) + 16;       // stored half = value + BIAS > 0
+    // stored half = value + BIAS > 0; local mode keeps the zero level Z = BIAS + ge * (i + j) non-negative for the 31 steps a
+    // lane of band 0 waits left of the matrix
+    const int BIAS = 3 * go + (cc < 0 ? -cc : cc) + 16 + (LOCAL ? 32 * ge : 0);
     const uint32_t negc2 = (uint32_t)(-cc) * 0x00010001u;     // 32-bit add that subtracts cc from both halves
     const int ma2 = a.sc.match + go + ge, mi2 = a.sc.mismatch + go + ge, wild2 = go + ge;
     const uint32_t lane0_mask = lane == 0 ? 0xffffffffu : 0u;
@@ -275,6 +325,7 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_W
     __shared__ volatile int s_prog[W];
     __shared__ int s_red[W][6];
     __shared__ uint4 s_top[W == 1 ? SMX16H_WPC : W][32];
+    __shared__ uint32_t s_snap[LOCAL ? (W == 1 ? SMX16H_WPC : W) : 1][LOCAL ? (2 * 8 + 2) * 32 : 1];  // Smx16hLocal::snap, per warp
 
     for (int served = 0; served < a.max_tickets; ++served) {
         int ticket = 0;
@@ -292,7 +343,7 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_W
         const int pid = a.order[ticket];
         const SmxProblem pr = a.probs[pid];
         const int m = pr.m, n = pr.n, mode = pr.mode & SMX_MODE_MASK;
-        const bool free_beg = mode == 2;  // SMX_MODE_SG_QB_DB
+        const bool free_beg = LOCAL || mode == 2;  // SMX_MODE_SG_QB_DB; local: first row and column are 0 as well
         const uint8_t *s1 = a.pool + pr.s1_off;
         const uint8_t *s2 = a.pool + pr.s2_off;
         uint32_t *trace = reinterpret_cast<uint32_t *>(a.trace + pr.trace_off);
@@ -315,6 +366,7 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_W
         int col_best = SMX_NEG_INF, col_best_i = 0x7fffffff;
         int row_best = SMX_NEG_INF, row_best_j = 0;
         int corner = 0;
+        int loc_best = 0, loc_i = m - 1, loc_j = n - 1;  // LOCAL: best H of this lane's cells, its cell (smallest j, then smallest i)
         const int last_band_idx = nbands - 1;
         const int rr_last = m - 1 - R0;              // last row inside the last band
         const int last_lane = split ? (rr_last & 127) >> 2 : rr_last >> 3;
@@ -343,8 +395,10 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_W
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int il = i0_lo + k, ih = i0_hi + k;
-                plo[k] = smx16h_profile(il < m ? smx_code(s1[il]) : 4, ma2, mi2, wild2);
-                phi[k] = smx16h_profile(ih < m ? smx_code(s1[ih]) : 4, ma2, mi2, wild2);
+                // rows beyond the query: wildcard rows (score 0) in the global modes; in local mode they must never tie the
+                // best real cell, so they mismatch everything
+                plo[k] = il < m ? smx16h_profile(smx_code(s1[il]), ma2, mi2, wild2) : (uint32_t)(LOCAL ? mi2 : wild2) * 0x01010101u;
+                phi[k] = ih < m ? smx16h_profile(smx_code(s1[ih]), ma2, mi2, wild2) : (uint32_t)(LOCAL ? mi2 : wild2) * 0x01010101u;
                 Hc[k] = free_beg ? smx16h_pack(ge * il + u_free, ge * ih + u_free) : smx16h_pack(u_edge, u_edge);  // column -1
                 El[k] = 0u;                                                                                        // E^ = -inf
             }
@@ -352,6 +406,13 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_W
             uint32_t hd = smx16h_pack(i0_lo == 0 ? u_corner : (free_beg ? ge * (i0_lo - 1) + u_free : u_edge),
                                       free_beg ? ge * (i0_hi - 1) + u_free : u_edge);
             uint32_t out_h = 0, out_f = 0, sel_prev = 0;
+            Smx16hLocal L;
+            if (LOCAL) {  // Z of the lane's row 0 at step 0: i + j = i0 - lane (low half), i0_hi - lane - LAG (high half)
+                L.zs = smx16h_pack(BIAS + ge * (i0_lo - lane), BIAS + ge * (i0_hi - lane - LAG));
+                L.ge2 = (uint32_t)ge * 0x00010001u;
+                L.lbest = 0u; L.s_lo = 0; L.s_hi = 0;
+                L.snap = s_snap[wib];
+            }
             int rch1 = 0, rch2 = 0;  // reference codes of the two previous chunks (the high half reads 64 columns back)
             const bool st_lo = lane == 31 && !lo_is_last, st_hi = lane == 31 && has_hi && !hi_is_last;
             const bool track_lo = mode == 1 && lo_is_last, track_hi = mode == 1 && hi_is_last;
@@ -396,11 +457,11 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_W
                         const int jbase = s0 - lane - (track_lo ? 0 : LAG);
                         const uint32_t tmask = lane == last_lane ? (track_lo ? 0x0000ffffu : 0xffff0000u) : 0u;
                         const int tconst = hconst - ge * (m - 1);
-                        if (has_hi) smx16h_fast_chunk<K, true, true, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, ge, tconst, row_best, row_best_j, one);
-                        else smx16h_fast_chunk<K, false, true, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, ge, tconst, row_best, row_best_j, one);
+                        if (has_hi) smx16h_fast_chunk<K, true, true, SPLIT, LOCAL>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, ge, tconst, row_best, row_best_j, one, &L, s0, lane);
+                        else smx16h_fast_chunk<K, false, true, SPLIT, LOCAL>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, ge, tconst, row_best, row_best_j, one, &L, s0, lane);
                     } else {
-                        if (has_hi) smx16h_fast_chunk<K, true, false, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one);
-                        else smx16h_fast_chunk<K, false, false, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one);
+                        if (has_hi) smx16h_fast_chunk<K, true, false, SPLIT, LOCAL>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one, &L, s0, lane);
+                        else smx16h_fast_chunk<K, false, false, SPLIT, LOCAL>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one, &L, s0, lane);
                     }
                 } else {
                     // edge chunk: halves outside the matrix hold their state (smx16h_edge_chunk)
@@ -411,13 +472,32 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_W
                     const uint32_t st_flags = (st_lo ? 1u : 0u) | (st_hi ? 2u : 0u);
                     const uint32_t tmask = (track_lo | track_hi) && lane == last_lane ? (track_lo ? 0x0000ffffu : 0xffff0000u) : 0u;
                     const int tconst = hconst - ge * (m - 1);
-                    if (has_hi) smx16h_edge_chunk<K, true, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, s0 - lane, n, ge, tconst, row_best, row_best_j, one);
-                    else smx16h_edge_chunk<K, false, SPLIT>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, s0 - lane, n, ge, tconst, row_best, row_best_j, one);
+                    if (has_hi) smx16h_edge_chunk<K, true, SPLIT, LOCAL>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, s0 - lane, n, ge, tconst, row_best, row_best_j, one, &L, s0, lane);
+                    else smx16h_edge_chunk<K, false, SPLIT, LOCAL>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, s0 - lane, n, ge, tconst, row_best, row_best_j, one, &L, s0, lane);
                 }
                 rch2 = rch1;
                 rch1 = rch0;
                 if (TEAM) {
                     if (lane == 31) { __threadfence_block(); s_prog[wib] = pair * nchunks + chunk + 1; }
+                }
+            }
+            if (LOCAL) {  // this band pair's best cell per half, read back from the snapshot of the step that reached it
+                __syncwarp();
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int best = half ? (int)(L.lbest >> 16) : (int)(L.lbest & 0xffffu);
+                    if (best <= 0 || (half && !has_hi)) continue;
+                    const uint32_t zsn = L.snap[2 * K * 32 + half * 32 + lane];
+                    const int z0 = half ? (int)(zsn >> 16) : (int)(zsn & 0xffffu);
+                    int kk = 0;
+#pragma unroll
+                    for (int k = K - 1; k >= 0; --k) {  // smallest row holding the maximum
+                        const uint32_t wv = L.snap[(half * K + k) * 32 + lane];
+                        const int hv = (half ? (int)(wv >> 16) : (int)(wv & 0xffffu)) + cc - (z0 + k * ge);
+                        if (hv == best) kk = k;
+                    }
+                    const int bi = (half ? i0_hi : i0_lo) + kk, bj = (half ? L.s_hi - LAG : L.s_lo) - lane;
+                    if (best > loc_best || (best == loc_best && (bj < loc_j || (bj == loc_j && bi < loc_i)))) { loc_best = best; loc_i = bi; loc_j = bj; }
                 }
             }
             // end-cell candidates (last column): every half has held its column n - 1 values since it left the matrix.
@@ -470,7 +550,25 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_W
                 row_best = s_red[0][2]; row_best_j = s_red[0][3]; corner = s_red[0][4];
             }
         }
-        if (mode == 1) {  // SMX_MODE_SG_QE_DE
+        if (LOCAL) {
+            // best cell over the lanes (and the warps of a team): maximum, then smallest reference position, then smallest query position
+            auto better = [](int b, int j, int i, int ob, int oj, int oi) { return ob > b || (ob == b && (oj < j || (oj == j && oi < i))); };
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const int ob = __shfl_xor_sync(SMX_FULL_MASK, loc_best, off), oj = __shfl_xor_sync(SMX_FULL_MASK, loc_j, off), oi = __shfl_xor_sync(SMX_FULL_MASK, loc_i, off);
+                if (better(loc_best, loc_j, loc_i, ob, oj, oi)) { loc_best = ob; loc_j = oj; loc_i = oi; }
+            }
+            if (TEAM) {
+                __syncthreads();
+                if (lane == 0) { s_red[wib][0] = loc_best; s_red[wib][1] = loc_j; s_red[wib][2] = loc_i; }
+                __syncthreads();
+                if (threadIdx.x == 0)
+                    for (int w = 1; w < W; ++w)
+                        if (better(loc_best, loc_j, loc_i, s_red[w][0], s_red[w][1], s_red[w][2])) { loc_best = s_red[w][0]; loc_j = s_red[w][1]; loc_i = s_red[w][2]; }
+            }
+            if (loc_best <= 0) { loc_best = 0; loc_i = m - 1; loc_j = n - 1; }  // parasail: score 0, end cell = last cell, empty CIGAR
+            r.score = loc_best; r.end_q = loc_i; r.end_r = loc_j;
+        } else if (mode == 1) {  // SMX_MODE_SG_QE_DE
             int best = SMX_NEG_INF, bi = m - 1, bj = n - 1;
             if (col_best > best) { best = col_best; bi = col_best_i; bj = n - 1; }
             if (row_best > best) { best = row_best; bi = m - 1; bj = row_best_j; }

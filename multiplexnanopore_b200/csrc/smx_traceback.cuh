@@ -126,6 +126,12 @@ __global__ void __launch_bounds__(128) smx_traceback(const SmxTbArgs a)
         else if (j + 1 == n) w.emit(SMX_OP_I, m - 1 - i);
     }
     int where = 0;  // 0 = DIAG (H), 1 = INS (E, emits 'D'), 2 = DEL (F, emits 'I')
+    // Local problems of the packed kernel carry no ZERO code in their direction bits (two bits are taken by "diagonal
+    // lost" / "E beat F"): the walker tracks the value of the matrix cell it stands on instead -- H of the end cell is
+    // the score, every move subtracts what the forward recurrence added -- and stops in state H on a cell worth 0,
+    // which is exactly the cell parasail marks ZERO.
+    const bool tracked_stop = local && enc16;
+    int cur = r.score;
     // The walk is one dependent 1-byte load per step, so the loop keeps the position incrementally: `wp` points
     // at the lane-step word of the current cell (layout [band][step = j + lane][lane]), `k` is the row inside the
     // lane.  A column move lowers the step by one line, a row move changes k or, every K rows, the lane (one
@@ -172,11 +178,13 @@ __global__ void __launch_bounds__(128) smx_traceback(const SmxTbArgs a)
         const uint32_t nib = ((uint32_t)wp[k >> 1] >> ((k & 1) * 4)) & 15u;
         int di = 0, dj = 0;
         if (where == 0) {
+            if (tracked_stop && cur <= 0) break;  // ZERO: local alignment starts here
             // int32 kernels store the H source as a 2-bit code; the s16x2 kernels (classes >= 10) store
             // "diagonal lost" in bit 0 and "E beat F" in bit 1 (smx_dp16.cuh)
             const uint32_t src = enc16 ? (!(nib & 1u) ? SMX_SRC_DIAG : ((nib & 2u) ? SMX_SRC_INS : SMX_SRC_DEL)) : (nib & 3u);
             if (src == SMX_SRC_DIAG) {
                 w.emit(s1[i] == s2[j] ? SMX_OP_EQ : SMX_OP_X, 1);
+                if (tracked_stop) cur -= (smx_code(s1[i]) > 3 || smx_code(s2[j]) > 3) ? 0 : (s1[i] == s2[j] ? a.sc.match : a.sc.mismatch);
                 di = 1; dj = 1;
             } else if (src == SMX_SRC_INS) where = 1;
             else if (src == SMX_SRC_DEL) where = 2;
@@ -185,10 +193,12 @@ __global__ void __launch_bounds__(128) smx_traceback(const SmxTbArgs a)
             w.emit(SMX_OP_D, 1);
             dj = 1;
             where = (nib & SMX_BIT_EOPEN) ? 0 : 1;
+            if (tracked_stop) cur += where == 0 ? a.sc.go : a.sc.ge;  // E(i, j) = H(i, j-1) - open  or  E(i, j-1) - extend
         } else {
             w.emit(SMX_OP_I, 1);
             di = 1;
             where = (nib & SMX_BIT_FOPEN) ? 0 : 2;
+            if (tracked_stop) cur += where == 0 ? a.sc.go : a.sc.ge;
         }
         if (dj) { --j; wp -= line; }
         if (di) {

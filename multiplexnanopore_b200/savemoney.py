@@ -314,15 +314,23 @@ from .outputs import QueryAssignment, IntermediateResults, save_intermediate_res
 
 class DenseResult:
     """Result of one legacy dense alignment (the fields the legacy MyResult reads off parasail's Result:
-    Modules/1_alignment_consensus_core.py:297-330): score, cigar (RLE text), beg/end on query and reference."""
-    __slots__ = ("score", "cigar", "beg_query", "beg_ref", "end_query", "end_ref")
+    Modules/1_alignment_consensus_core.py:297-330): score, cigar (RLE text, rendered on first use), beg/end on query
+    and reference."""
+    __slots__ = ("score", "_runs", "_cigar", "beg_query", "beg_ref", "end_query", "end_ref")
 
-    def __init__(self, score, cigar, beg_query, beg_ref, end_query, end_ref):
-        self.score, self.cigar = score, cigar
+    def __init__(self, score, runs, beg_query, beg_ref, end_query, end_ref):
+        self.score, self._runs, self._cigar = score, runs, None
         self.beg_query, self.beg_ref, self.end_query, self.end_ref = beg_query, beg_ref, end_query, end_ref
 
+    @property
+    def cigar(self) -> str:
+        if self._cigar is None:
+            from .engine import OP_CHARS
+            self._cigar = "".join(f"{int(x) >> 4}{OP_CHARS[int(x) & 15]}" for x in self._runs)
+        return self._cigar
 
-def legacy_dense_align(ref_seq_list, my_fastq, param_dict, engine=None, batch_cells=int(2e10), stats=None):
+
+def legacy_dense_align(ref_seq_list, my_fastq, param_dict, engine=None, batch_cells=int(3e10), stats=None):
     """Row N4, the pre-0.2 alignment mode kept in the reference under Modules/ (MyAligner.align_all /
     MyAlignerLinear.align_all, Modules/1_alignment_consensus_core.py:219-296): one local alignment
     `parasail.sw_trace(read, reference + reference)` (circular; `reference` alone for linear topology) per read,
@@ -380,7 +388,7 @@ def legacy_dense_align(ref_seq_list, my_fastq, param_dict, engine=None, batch_ce
         for qid in ids[pos:end]:
             row = []
             for _ in range(2 * nt):
-                row.append(DenseResult(int(res.score[p]), res.cigar_string(p), int(res.beg_query[p]), int(res.beg_ref[p]),
+                row.append(DenseResult(int(res.score[p]), res.runs(p), int(res.beg_query[p]), int(res.beg_ref[p]),
                                        int(res.end_query[p]), int(res.end_ref[p])))
                 p += 1
             out[qid] = row

@@ -64,7 +64,7 @@ def lib():
     return _lib
 
 
-def set_tie_rules(gap_prefers_extend: int = 1, h_order_diag_f_e: int = 1, sg_end_order: int = 0, sw_end_order: int = 0):
+def set_tie_rules(gap_prefers_extend: int = 1, h_order_diag_f_e: int = 1, sg_end_order: int = 0, sw_end_order: int = 1):
     """Flip the tie rules of parasail_port.c that could not be checked against a real parasail (defaults = what the
     product implements).  Only oracle/tie_sensitivity.py and its test call this with non-default values."""
     lib().pp_set_tie_rules(int(gap_prefers_extend), int(h_order_diag_f_e), int(sg_end_order), int(sw_end_order))

@@ -43,8 +43,10 @@ static int TIE_H_ORDER_DIAG_F_E = 1;
  *                the corner beats a tied last-row cell)
  *   2          : last row first, then last column (the order of the striped SIMD kernels) */
 static int TIE_SG_END_ORDER = 0;
-/* sw end cell: 0 (default) first maximum in row-major order; 1 smallest end_ref, then smallest end_query */
-static int TIE_SW_END_ORDER = 0;
+/* sw end cell: 1 (default) smallest end_ref, then smallest end_query -- parasail's serial sw keeps `WH > score`, else
+ * `WH == score && j - 1 < end_ref` (the order its striped kernels produce: first column holding the maximum, then its
+ * first row); 0 = first maximum in row-major order (round-1 default of this port) */
+static int TIE_SW_END_ORDER = 1;
 
 void pp_set_tie_rules(int gap_prefers_extend, int h_order_diag_f_e, int sg_end_order, int sw_end_order)
 {

@@ -107,3 +107,27 @@ def test_teams_next_to_the_one_warp_launch(engine, env):
     modes += [int(x) for x in rng.integers(0, 3, size=30)]
     with _Env(SMX_TEAM2_MCELLS="0.5", SMX_TEAM4_MCELLS="1.2", SMX_TEAM8_MCELLS="2.0", **env):
         run_and_compare(engine, probs, modes, (3, 1, 1, -2))
+
+
+def test_packed_local_kernel_sizes_and_teams(engine):
+    """mode 3 (sw_trace) on the packed kernel: every row-count class incl. split last bands, problems with no positive
+    cell, repeats (several cells share the best score: smallest reference position, then smallest query position wins),
+    wildcards in the query, and the team widths."""
+    rng = np.random.default_rng(83)
+    probs = []
+    for m, n in ((33, 40), (64, 64), (65, 300), (128, 77), (129, 500), (256, 256), (257, 90), (300, 1000), (511, 200), (513, 700), (700, 1300),
+                 (1025, 333), (1600, 700), (2300, 900), (4100, 610), (7800, 300)):
+        ref = util.rand_seq(rng, n)
+        q = util.mutate(rng, (ref * (m // n + 2))[:m], 0.06, 0.03, 0.03)[:m]
+        probs.append((q, ref))                       # repeats of the reference inside the query
+        probs.append((util.rand_seq(rng, m), ref))   # unrelated
+    probs.append(("A" * 200, "C" * 300))             # no positive cell: score 0, empty CIGAR
+    probs.append(("ACGT" * 60, "ACGT" * 90))         # many equal maxima
+    probs.append((util.rand_seq(rng, 150, b"ACGTN"), util.rand_seq(rng, 400)))
+    modes = [3] * len(probs)
+    run_and_compare(engine, probs, modes, (3, 1, 1, -2))
+    run_and_compare(engine, probs[:16], modes[:16], (5, 2, 2, -3))
+    with _Env(SMX_TEAM2_MCELLS="0.5", SMX_TEAM4_MCELLS="1.2", SMX_TEAM8_MCELLS="2.0"):
+        run_and_compare(engine, probs, modes, (3, 1, 1, -2))
+    with _Env(SMX_S16="0"):   # the int32 local kernels follow the same end-cell order
+        run_and_compare(engine, probs[-12:], modes[-12:], (3, 1, 1, -2))

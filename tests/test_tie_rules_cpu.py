@@ -23,7 +23,7 @@ def _restore_default_rules():
 
 
 @pytest.mark.parametrize("rules", [dict(gap_prefers_extend=0), dict(h_order_diag_f_e=0), dict(sg_end_order=1),
-                                   dict(sg_end_order=2), dict(sw_end_order=1)])
+                                   dict(sg_end_order=2), dict(sw_end_order=0)])
 def test_every_tie_variant_is_valid_and_optimal(rules):
     rng = np.random.default_rng(11)
     probs = util.make_problems(rng, 120, 70, low_complexity=0.5)
