@@ -194,6 +194,11 @@ int smx_assign(smx_handle *h, const int32_t *score, const uint8_t *status, const
 int64_t smx_ir_format(const int32_t *score, const int32_t *new_query_seq_offset, const uint8_t *status, const int64_t *cigar_off,
                       const uint32_t *cigar_rle, int64_t n, int64_t first_index, int32_t n_threads, char *out, int64_t capacity);
 
+/* Debug aid (compute-sanitizer is not available on every pool): with SMX_GUARD=1 in the environment every problem's
+ * direction-bit region is surrounded by 2 x 256 poisoned bytes that are verified after the traceback; returns the number
+ * of damaged guard words since the handle was created, -1 when the mode is off. */
+int64_t smx_debug_guard_errors(const smx_handle *h);
+
 /* ---- measurement helper: dependency-free int32 / DPX issue-rate microbenchmark ---------------
  * Runs `iters` rounds of independent VIADDMNMX / VIMNMX3 / IADD chains on every SM and returns
  * achieved giga-ops/s (one op = one 32-bit lane instruction) in out_gops[3] = {viaddmax, vimax3, iadd}. */

@@ -31,6 +31,7 @@ _SIGNATURES = {
     "smx_align_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64]),
     "smx_align_kernel_ms": (c_int, [c_void_p, c_void_p, c_void_p]),
     "smx_debug_copy_trace": (c_int, [c_void_p, c_void_p, c_int64]),
+    "smx_debug_guard_errors": (c_int64, [c_void_p]),
     "smx_last_run_ms": (c_float, [c_void_p]),
     "smx_align_cells": (c_int64, [c_void_p]),
     "smx_last_run_launches": (c_int32, [c_void_p]),

@@ -66,6 +66,11 @@ struct smx_handle {
     cudaStream_t stream_team[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     bool teams_concurrent = false;
+    // SMX_GUARD=1 (debug; compute-sanitizer is closed on the pool): 256 poisoned bytes before and after every problem's
+    // direction-bit region, verified after the traceback of every chunk
+    bool guard = false;
+    DevBuf d_guard_err;
+    int64_t guard_errors = -1;
     int64_t team_cells[3] = {16ll << 20, 48ll << 20, 128ll << 20};  // cells from which a problem gets 2 / 4 / 8 warps (SMX_TEAM2/4/8_MCELLS)
     float last_ms = 0.f;
     int last_launches = 0;
@@ -309,7 +314,7 @@ extern "C" void smx_destroy(smx_handle *h)
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->stream_hi);
     DevBuf *bufs[] = {&h->pool, &h->pool2, &h->pool_special, &h->d_probs, &h->d_order_cls, &h->d_order_all, &h->d_results, &h->d_trace, &h->d_boundary,
-                      &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_slots, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts,
+                      &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_slots, &h->d_guard_err, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts,
                       &h->d_sel_pairs, &h->d_sel_out, &h->d_regions, &h->d_chain_tasks, &h->d_chain_regions, &h->d_chain_traces,
                       &h->d_chain_out, &h->d_chain_scratch, &h->d_compact, &h->d_expand_items, &h->d_comp};
     smx_pipeline_free(h);
@@ -507,6 +512,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         static const char *const tenv[3] = {"SMX_TEAM2_MCELLS", "SMX_TEAM4_MCELLS", "SMX_TEAM8_MCELLS"};
         static const int64_t tdef[3] = {16, 48, 128};
         for (int t = 0; t < 3; ++t) { const char *e = getenv(tenv[t]); h->team_cells[t] = e && atof(e) > 0 ? (int64_t)(atof(e) * 1048576.0) : tdef[t] << 20; }
+        { const char *ge_ = getenv("SMX_GUARD"); h->guard = ge_ && ge_[0] == '1'; if (!h->guard) h->guard_errors = -1; else if (h->guard_errors < 0) h->guard_errors = 0; }
         const char *tc = getenv("SMX_TEAMS_CONCURRENT");
         h->teams_concurrent = h->use_s16h && !h->persistent_fwd && h->stream_team[0] && h->stream_team[1] && h->stream_team[2] && !(tc && tc[0] == '0');
     }
@@ -611,9 +617,9 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         while (pos < n) {
             SmxProblem &q = h->probs[(size_t)order[pos]];
             size_t tb = (size_t)smx_trace_bytes(q.m, q.n, 1 << q.kshift);
-            tb = (tb + 255) & ~(size_t)255;
+            tb = ((tb + 255) & ~(size_t)255) + (h->guard ? 512 : 0);
             if (c.count > 0 && bytes + tb > (size_t)h->trace_budget) break;
-            q.trace_off = (int64_t)bytes;
+            q.trace_off = (int64_t)bytes + (h->guard ? 256 : 0);
             bytes += tb;
             if (c.cls_count[q.cls] == 0) c.cls_first[q.cls] = pos;
             ++c.cls_count[q.cls];
@@ -758,6 +764,22 @@ static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_id
     return do_mark ? mark(h, cls) : 0;
 }
 
+// SMX_GUARD: one warp per problem checks the 2 x 256 poisoned bytes around its direction-bit region
+__global__ void __launch_bounds__(128) smx_guard_check(const SmxProblem *probs, const int32_t *order, int n, const uint8_t *trace, unsigned long long *err)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const SmxProblem pr = probs[order[w]];
+    const int64_t bytes = (smx_trace_bytes(pr.m, pr.n, 1 << pr.kshift) + 255) & ~(int64_t)255;
+    const uint32_t *before = reinterpret_cast<const uint32_t *>(trace + pr.trace_off - 256);
+    const uint32_t *after = reinterpret_cast<const uint32_t *>(trace + pr.trace_off + bytes);
+    int bad = 0;
+    for (int x = lane; x < 64; x += 32) bad += (before[x] != 0xA5A5A5A5u) + (after[x] != 0xA5A5A5A5u);
+    if (bad) atomicAdd(err, (unsigned long long)bad);
+}
+
+extern "C" int64_t smx_debug_guard_errors(const smx_handle *h) { return h ? h->guard_errors : -1; }
+
 static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate);
 
 extern "C" int smx_align_run(smx_handle *h, int64_t *total_runs) { return align_run_impl(h, total_runs, nullptr); }
@@ -789,9 +811,14 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
     h->ev_used = 0;
     for (int c = 0; c < kNumSlots; ++c) { h->kernel_ms[c] = 0.0; h->kernel_launches[c] = 0; }
     if (int rc = mark(h, -1)) return rc;
+    if (h->guard) {
+        if (int rc = ensure(h, h->d_guard_err, 8)) return rc;
+        SMX_CUDA(h, cudaMemsetAsync(h->d_guard_err.p, 0, 8, h->stream));
+    }
     for (size_t ci = 0; ci < h->chunks.size(); ++ci) {
         const Chunk &c = h->chunks[ci];
         int rc = 0;
+        if (h->guard) SMX_CUDA(h, cudaMemsetAsync(h->d_trace.p, 0xA5, c.trace_bytes, h->stream));
         if (h->teams_concurrent && (c.cls_count[kClsS16 + 1] | c.cls_count[kClsS16 + 2] | c.cls_count[kClsS16 + 3])) {
             // fork: the team launches (few CTAs, long) go first on their own streams and take their SM slots, the
             // one-warp-per-problem launch fills the rest; join before the next kernel of this stream
@@ -842,6 +869,11 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
         SMX_CUDA(h, cudaGetLastError());
         h->last_launches++;
         if (int rc2 = mark(h, kSlotTraceback)) return rc2;
+        if (h->guard) {
+            smx_guard_check<<<(c.count + 3) / 4, 128, 0, h->stream>>>((const SmxProblem *)h->d_probs.p, (const int32_t *)h->d_order_all.p + c.first, c.count,
+                                                                      (const uint8_t *)h->d_trace.p, (unsigned long long *)h->d_guard_err.p);
+            SMX_CUDA(h, cudaGetLastError());
+        }
     }
     SMX_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     // results header to host: run counts -> dense offsets -> compaction
@@ -850,6 +882,11 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
     if (gate) { SMX_CUDA(h, cudaEventSynchronize(h->ev_fwd)); guard.release(); }
     SMX_CUDA(h, smx_sync(h, h->stream));
     memcpy(h->h_results.data(), h->pin_stage[PIN_RESULTS].p, sizeof(SmxResult) * (size_t)h->n);
+    if (h->guard) {
+        unsigned long long e = 0;
+        SMX_CUDA(h, cudaMemcpy(&e, h->d_guard_err.p, 8, cudaMemcpyDeviceToHost));
+        h->guard_errors += (int64_t)e;
+    }
     SMX_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     h->h_dense_off.resize((size_t)h->n + 1);
     int64_t acc = 0;

@@ -107,6 +107,11 @@ class Engine:
         self._check(self._lib.smx_set_trace_budget(self._h, int(nbytes)), "smx_set_trace_budget")
 
     @property
+    def guard_errors(self) -> int:
+        """SMX_GUARD=1: damaged guard words around the direction-bit regions so far (-1: mode off)"""
+        return int(self._lib.smx_debug_guard_errors(self._h))
+
+    @property
     def trace_budget(self) -> int:
         return int(self._lib.smx_get_trace_budget(self._h))
 

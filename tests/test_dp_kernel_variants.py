@@ -131,3 +131,28 @@ def test_packed_local_kernel_sizes_and_teams(engine):
         run_and_compare(engine, probs, modes, (3, 1, 1, -2))
     with _Env(SMX_S16="0"):   # the int32 local kernels follow the same end-cell order
         run_and_compare(engine, probs[-12:], modes[-12:], (3, 1, 1, -2))
+
+
+def test_guard_bands_around_direction_bits(engine):
+    """compute-sanitizer is closed on this pool (profiles/sanitizer_closed_r02.log); SMX_GUARD=1 surrounds every problem's
+    direction-bit region with poisoned bytes and verifies them after the traceback: no forward kernel family, team width,
+    split last band or local problem writes outside its region, and the results are still the oracle's."""
+    rng = np.random.default_rng(97)
+    probs, modes = _mixed_problems(62, n=60, max_len=900)
+    probs = list(probs); modes = [int(x) for x in modes]
+    for m, n in ((1600, 700), (2300, 500), (4100, 300), (7800, 200), (255, 257), (257, 255), (129, 64), (513, 31)):
+        ref = util.rand_seq(rng, n)
+        q = util.mutate(rng, (ref * (m // n + 2))[:m], 0.08, 0.03, 0.03)[:m]
+        for mode in (0, 1, 2, 3):
+            probs.append((q, ref)); modes.append(mode)
+    for env in (dict(), dict(SMX_S16H="0"), dict(SMX_S16="0"), dict(SMX_S16H_SPLIT="0"), dict(SMX_TEAM2_MCELLS="0.5", SMX_TEAM4_MCELLS="1.2", SMX_TEAM8_MCELLS="2.0")):
+        with _Env(SMX_GUARD="1", **env):
+            run_and_compare(engine, probs, modes, (3, 1, 1, -2))
+            assert engine.guard_errors == 0, env
+    with _Env(SMX_GUARD="1"):
+        engine.set_trace_budget(1 << 20)
+        try:
+            run_and_compare(engine, probs[:80], modes[:80], (3, 1, 1, -2))
+        finally:
+            engine.set_trace_budget(16 << 30)
+        assert engine.guard_errors == 0
