@@ -175,6 +175,9 @@ def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None,
     sig = [sigma_for(len(r)) for r in refs]
     args = (param_dict["gap_open_penalty"], param_dict["gap_extend_penalty"], param_dict["match_score"],
             param_dict["mismatch_score"], param_dict["topology_of_dna"], omit_too_long)
+    if pairs is None and overlap > 1 and 500 < len(queries) < batch_queries * overlap:
+        # few reads for this GPU (one GPU's share of a strong-scaled call): smaller batches keep `overlap` handles busy
+        batch_queries = min(batch_queries, max(250, -(-len(queries) // overlap)))
     if pairs is not None or len(queries) <= batch_queries:
         return eng.pipeline_run(refs, queries, sig, *args, pairs=pairs, n_threads=n_threads)
     from .engine import _pack

@@ -62,3 +62,31 @@ def test_calc_distance_edges(engine):
     assert sm.calc_distance(a, synth.revcomp_bytes(np.frombuffer(a.encode(), np.uint8)).tobytes().decode(), params, engine=engine) == 0
     assert sm.calc_distance(a, b, params, engine=engine) == port.distance(a, b, params)
     assert sm.set_distance_matrix([a], params, engine=engine).tolist() == [[0]]
+
+
+def test_ultra_long_reads_do_not_fail_the_call(engine):
+    """a read of more than 65 535 bases made smx_pipeline_run fail for the whole FASTQ.  Such a read is
+    (1) dropped by omit_too_long like in the reference (empty MyResult(), post_analysis_core.py:76-83) when it is longer
+    than 1.75 references, and (2) aligned normally when it is not: its pair-strands take the host re-decision of the
+    threshold (the select kernel's histogram median holds 16-bit counts).  The other reads of the batch are unaffected."""
+    rng = np.random.default_rng(84)
+    small = synth.plasmid_set(rng, 2, 900, 1300, backbone=300)
+    good, _ = synth.reads_for(rng, small, 3, topology=0)
+    monster = synth.random_bases(rng, 70000).tobytes().decode()
+    fastq = {"good0": [good[0], None], "monster": [monster, None], "good1": [good[1], None]}
+    rd = sm.execute_alignment_core(small, fastq, PARAMS, engine=engine)
+    assert all(r.my_cigar == "" and r.score == 0 for r in rd["monster"])
+    for k, read in (("good0", good[0]), ("good1", good[1])):
+        assert [[r.cigar, r.score, r.new_query_seq_offset] for r in rd[k]] == _want(small, read, PARAMS), k
+    # not omitted: a 66 kb read against a 38 kb plasmid it was copied from (rotated, 1.73 x its length, 0.4 % errors so
+    # that the CPU port's cubic chain search stays at seconds)
+    big = synth.random_bases(rng, 38000).tobytes().decode()
+    src = (big[15000:] + big[:15000]) * 2
+    long_read = synth.mutate_bytes(rng, np.frombuffer(src[:65900].encode(), np.uint8), 0.002, 0.001, 0.001).tobytes().decode()
+    assert 65535 < len(long_read) < 1.75 * len(big)
+    res = sm.align_all([big], [long_read, good[2]], PARAMS, True, engine=engine)
+    assert int(res.stats["n_host_redecisions"]) >= 2 and int(res.stats["n_failed"]) == 0
+    want = _want([big], long_read, PARAMS)
+    got = [[res.cigar_string(j), int(res.score[j]), res.offset(j)] for j in range(2)]
+    assert got == want
+    assert max(w[1] for w in want) > 30000   # it did align
