@@ -85,6 +85,41 @@ def main():
         rd, _ = synth.reads_for(rng, pl, 10, topology=topo, frac_full=0.6, frac_partial=0.25, homopolymer_rate=1.0)
         cases.append(run_case(ns, f"fresh_{seed}_topology{topo}", pl, rd, dict(base, topology_of_dna=topo)))
 
+    # round 2: wider goldens -- linear topology on the demo maps, full-size synthetic plasmids, IUPAC codes in the plasmid
+    # maps (allowed since ver_0.3.1: wildcards score 0 inside parasail but are rescored as = / X), fragment-rich reads,
+    # and a third scoring
+    rng = np.random.default_rng(11)
+    reads, _ = synth.reads_for(rng, demo, 8, topology=1)
+    cases.append(run_case(ns, "c1_demo_linear", demo, reads, dict(base, topology_of_dna=1)))
+
+    rng = np.random.default_rng(12)
+    full = synth.plasmid_set(rng, 4, 5000, 9000, backbone=2500)
+    reads, _ = synth.reads_for(rng, full, 10, topology=0)
+    cases.append(run_case(ns, "c2_fullsize_circular", full, reads, dict(base)))
+
+    rng = np.random.default_rng(13)
+    iupac = []
+    for p in synth.plasmid_set(rng, 4, 1500, 2600, backbone=700):
+        a = np.frombuffer(p.encode(), dtype=np.uint8).copy()
+        pos = rng.choice(a.size, size=12, replace=False)
+        a[pos] = np.frombuffer(b"NRYKMSWBDHVN", dtype=np.uint8)
+        iupac.append(a.tobytes().decode())
+    reads, _ = synth.reads_for(rng, iupac, 12, topology=0, frac_full=0.6, frac_partial=0.3)
+    reads = [r.replace("N", "A").replace("R", "G").replace("Y", "C").replace("K", "T").replace("M", "A").replace("S", "C").replace("W", "T")
+             .replace("B", "C").replace("D", "G").replace("H", "A").replace("V", "G") for r in reads]   # reads are plain ACGT
+    reads[0] = reads[0][:200] + "N" * 3 + reads[0][203:]                                               # ... but one carries N calls
+    cases.append(run_case(ns, "iupac_maps_circular", iupac, reads, dict(base)))
+
+    rng = np.random.default_rng(14)
+    reads, _ = synth.reads_for(rng, small, 16, topology=0, frac_full=0.2, frac_partial=0.7)
+    cases.append(run_case(ns, "c2_small_fragments", small, reads, dict(base)))
+    p3 = dict(base, gap_open_penalty=2, gap_extend_penalty=2, match_score=1, mismatch_score=-1)
+    cases.append(run_case(ns, "c2_small_circular_scoring3", small, reads[:6], p3))
+
+    rng = np.random.default_rng(15)
+    reads, _ = synth.reads_for(rng, lin, 12, topology=1, homopolymer_rate=2.0)
+    cases.append(run_case(ns, "c4_small_linear_homopolymers", lin, reads, dict(base, topology_of_dna=1)))
+
     # pre_survey distances: demo maps (7 of the 15 pairs are the legacy known answers) + a synthetic family
     dist = {"demo_names": list(maps.keys()), "demo": {}, "family_maps": [], "family": {}}
     t0 = time.time()

@@ -21,4 +21,6 @@ def case(name):
 
 CASE_NAMES = ["c1_demo_circular", "c2_small_circular", "c2_small_circular_scoring2",
               "c2_small_circular_homopolymers", "c4_small_linear",
-              "fresh_31_topology0", "fresh_32_topology0", "fresh_33_topology1"]
+              "fresh_31_topology0", "fresh_32_topology0", "fresh_33_topology1",
+              "c1_demo_linear", "c2_fullsize_circular", "iupac_maps_circular", "c2_small_fragments",
+              "c2_small_circular_scoring3", "c4_small_linear_homopolymers"]
