@@ -165,27 +165,6 @@ __global__ void __launch_bounds__(128) smx_traceback(const SmxTbArgs a)
     while (local ? (i >= 0 && j >= 0) : (i >= 0 || j >= 0)) {
         if (i < 0) { w.emit(SMX_OP_D, j + 1); j = -1; break; }
         if (j < 0) { w.emit(SMX_OP_I, i + 1); i = -1; break; }
-#ifndef SMX_TB_NO_DIAG_LOOP
-        // Fast path for what a walk mostly does: diagonal moves in state H inside one lane's word column (k > 0, so the next
-        // cell is the same lane one line back).  Nothing but the H-source test, the base comparison and a run-length
-        // count per step; everything else (gap states, lane / band changes, matrix edges, run boundaries with re-clipping
-        // candidates) leaves through the general step below.
-        if (where == 0 && w.cur_len) {
-            while (k > 0 && i > 0 && j > 0) {
-                if (tracked_stop && cur <= 0) break;
-                const uint32_t nb = ((uint32_t)wp[k >> 1] >> ((k & 1) * 4)) & 15u;
-                if (enc16 ? (nb & 1u) != 0u : (nb & 3u) != SMX_SRC_DIAG) break;
-                const uint32_t op = s1[i] == s2[j] ? SMX_OP_EQ : SMX_OP_X;
-                if (op != w.cur_op) break;   // a run ends here: the general step flushes it
-                ++w.cur_len;
-                if (tracked_stop) cur -= (smx_code(s1[i]) > 3 || smx_code(s2[j]) > 3) ? 0 : (op == SMX_OP_EQ ? a.sc.match : a.sc.mismatch);
-                --i; --j; --k; wp -= line;
-#if SMX_TB_PF == 3
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(wp - SMX_TB_AHEAD * line));
-#endif
-            }
-        }
-#endif
 #if SMX_TB_PF == 1
         asm volatile("prefetch.global.L2 [%0];" ::"l"(wp - SMX_TB_AHEAD * line));
 #elif SMX_TB_PF == 2
