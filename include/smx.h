@@ -179,6 +179,17 @@ int smx_ops_run(smx_handle *h, const uint8_t *kind, const int64_t *ref_off, cons
                 int32_t match, int32_t mismatch, int32_t n_threads, int64_t *total_runs);
 int smx_ops_fetch(smx_handle *h, int64_t *cigar_off, uint32_t *cigar_rle, int64_t cigar_capacity, uint8_t *status);
 
+/* ---- row N3, first pass: MyMSA.generate_msa (savemoney/modules/msa.py:882-982) -----------------
+ * The reads assigned to one plasmid, each with its column CIGAR (run-length, ops = X I D S H) against the same reference,
+ * laid out as one multiple alignment.  Inputs are host arrays; the query bases and their Q-scores (int8, one per base)
+ * share the offsets.  Output: n_cols columns; smx_msa_fetch delivers ref_seq_aligned [n_cols] ('-' in extra columns) and
+ * row-major [n_reads, n_cols] matrices: query_seq_list_aligned (bases, '-' for D / N columns, ' ' for H / O columns),
+ * q_scores_list_aligned (-1 in every column without a base) and my_cigar_list_aligned (= X I D S H and the fillers N, O).
+ * A CIGAR that does not consume exactly the reference and its query is an error (the reference's final assertions). */
+int smx_msa_run(smx_handle *h, const uint8_t *ref, int32_t ref_len, int32_t n_reads, const uint8_t *qry, const int8_t *qscore,
+                const int64_t *qry_off, const int32_t *qry_len, const uint32_t *cigar_rle, const int64_t *cigar_off, int64_t *n_cols);
+int smx_msa_fetch(smx_handle *h, uint8_t *ref_aligned, uint8_t *seq_aligned, int8_t *qs_aligned, uint8_t *cigar_aligned);
+
 /* ---- row N2: what consumes the score matrix and the CIGARs without per-result objects -------
  * smx_assign: msa.QueryAssignment (savemoney/modules/msa.py:31-64) on the device, one thread per read.
  *   score / status: [n_reads, 2 * n_refs] as smx_pipeline_fetch delivers them (status != 0 = empty MyResult());

@@ -21,6 +21,7 @@
 #include "smx_scan.cuh"
 #include "smx_traceback.cuh"
 #include "smx_outputs.cuh"
+#include "smx_msa.cuh"
 
 namespace {
 
@@ -122,6 +123,10 @@ struct smx_handle {
     std::vector<int64_t> ops_off;
     std::vector<uint8_t> ops_status;
     bool ops_valid = false;
+    // smx_msa_run results (row N3): column matrices on the device until fetched
+    DevBuf d_msa_in, d_msa_work, d_msa_out;
+    int64_t msa_cols = -1;
+    int32_t msa_reads = 0;
 };
 
 static const int kLineSlots = 4096;  // boundary-line pairs of the non-persistent forward launches (> resident workers of any class)
@@ -314,7 +319,7 @@ extern "C" void smx_destroy(smx_handle *h)
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->stream_hi);
     DevBuf *bufs[] = {&h->pool, &h->pool2, &h->pool_special, &h->d_probs, &h->d_order_cls, &h->d_order_all, &h->d_results, &h->d_trace, &h->d_boundary,
-                      &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_slots, &h->d_guard_err, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts,
+                      &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_slots, &h->d_guard_err, &h->d_msa_in, &h->d_msa_work, &h->d_msa_out, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts,
                       &h->d_sel_pairs, &h->d_sel_out, &h->d_regions, &h->d_chain_tasks, &h->d_chain_regions, &h->d_chain_traces,
                       &h->d_chain_out, &h->d_chain_scratch, &h->d_compact, &h->d_expand_items, &h->d_comp};
     smx_pipeline_free(h);
@@ -1048,6 +1053,192 @@ extern "C" int smx_scan_fetch(smx_handle *h, int32_t *counts, int64_t counts_cap
 }
 
 extern "C" int64_t smx_scan_cells(const smx_handle *h) { return h ? h->scan_cells : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// Row N3, first pass: MyMSA.generate_msa (modules/msa.py:882-982) on the device (smx_msa.cuh)
+// ------------------------------------------------------------------------------------------------
+extern "C" int smx_msa_run(smx_handle *h, const uint8_t *ref, int32_t ref_len, int32_t n_reads, const uint8_t *qry, const int8_t *qscore,
+                           const int64_t *qry_off, const int32_t *qry_len, const uint32_t *cigar_rle, const int64_t *cigar_off, int64_t *n_cols)
+{
+    if (!h) return -1;
+    h->msa_cols = -1;
+    if (n_cols) *n_cols = 0;
+    if (!ref || ref_len < 0 || n_reads < 0 || (n_reads > 0 && (!qry || !qscore || !qry_off || !qry_len || !cigar_rle || !cigar_off)))
+        return fail(h, -1, "smx_msa_run: NULL argument");
+    SMX_CUDA(h, cudaSetDevice(h->device));
+    const int R = ref_len;
+    // host pass over the runs: letters per read, and the gaps in which some block holds an 'I' before an 'S' (their column
+    // order needs the serial simulation of the reference's loop)
+    std::vector<int64_t> let_off((size_t)n_reads + 1, 0);
+    std::vector<int32_t> complex_gaps;
+    for (int i = 0; i < n_reads; ++i) {
+        int64_t letters = 0;
+        int refc = 0;
+        bool seen_i = false, flagged = false;
+        for (int64_t x = cigar_off[i]; x < cigar_off[i + 1]; ++x) {
+            const uint32_t op = cigar_rle[x] & 15u;
+            const int64_t len = cigar_rle[x] >> 4;
+            letters += len;
+            if (op == 1u) seen_i = true;
+            else if (op == 4u) { if (seen_i && !flagged) { complex_gaps.push_back(refc); flagged = true; } }
+            else { refc += (int)std::min<int64_t>(len, (int64_t)R + 1); seen_i = false; flagged = false; }
+        }
+        let_off[(size_t)i + 1] = let_off[(size_t)i] + letters;
+    }
+    std::sort(complex_gaps.begin(), complex_gaps.end());
+    complex_gaps.erase(std::unique(complex_gaps.begin(), complex_gaps.end()), complex_gaps.end());
+    std::vector<int32_t> type_off((size_t)R + 2, 0);
+    std::vector<uint8_t> types;
+    if (!complex_gaps.empty()) {
+        // blocks of every read in the complex gaps, then the reference's loop on them (msa.py:905-969): an 'S' column while any
+        // read stands at 'S', else an 'I' column while any read stands at 'I'
+        std::vector<std::vector<std::string>> blocks(complex_gaps.size());
+        for (int i = 0; i < n_reads; ++i) {
+            int refc = 0;
+            std::string cur;
+            auto close = [&](int gap) {
+                if (cur.empty()) return;
+                auto it = std::lower_bound(complex_gaps.begin(), complex_gaps.end(), gap);
+                if (it != complex_gaps.end() && *it == gap) blocks[(size_t)(it - complex_gaps.begin())].push_back(cur);
+                cur.clear();
+            };
+            for (int64_t x = cigar_off[i]; x < cigar_off[i + 1]; ++x) {
+                const uint32_t op = cigar_rle[x] & 15u;
+                const int64_t len = cigar_rle[x] >> 4;
+                if (op == 1u || op == 4u) cur.append((size_t)len, op == 1u ? 'I' : 'S');
+                else { close(refc); refc += (int)std::min<int64_t>(len, (int64_t)R + 1); }
+            }
+            close(refc);
+        }
+        std::vector<std::string> seq(complex_gaps.size());
+        for (size_t g = 0; g < complex_gaps.size(); ++g) {
+            std::vector<size_t> p(blocks[g].size(), 0);
+            for (;;) {
+                bool any_s = false, any_i = false;
+                for (size_t b = 0; b < blocks[g].size(); ++b)
+                    if (p[b] < blocks[g][b].size()) { if (blocks[g][b][p[b]] == 'S') any_s = true; else any_i = true; }
+                if (!any_s && !any_i) break;
+                const char T = any_s ? 'S' : 'I';
+                for (size_t b = 0; b < blocks[g].size(); ++b) if (p[b] < blocks[g][b].size() && blocks[g][b][p[b]] == T) ++p[b];
+                seq[g].push_back(T);
+            }
+        }
+        size_t g = 0;
+        for (int r = 0; r <= R; ++r) {
+            type_off[(size_t)r] = (int32_t)types.size();
+            if (g < complex_gaps.size() && complex_gaps[g] == r) { types.insert(types.end(), seq[g].begin(), seq[g].end()); ++g; }
+        }
+        type_off[(size_t)R + 1] = (int32_t)types.size();
+    }
+    // device input block: ref | qry | qscore | qry_off | qry_len | runs | cigar_off | let_off
+    const int64_t n_q = n_reads ? qry_off[n_reads - 1] + qry_len[n_reads - 1] : 0, n_runs = n_reads ? cigar_off[n_reads] : 0;
+    auto up8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
+    size_t o = 0;
+    const size_t o_ref = o; o += up8((size_t)R + 1);
+    const size_t o_qry = o; o += up8((size_t)n_q + 1);
+    const size_t o_qs = o; o += up8((size_t)n_q + 1);
+    const size_t o_qoff = o; o += 8 * ((size_t)n_reads + 1);
+    const size_t o_qlen = o; o += up8(4 * ((size_t)n_reads + 1));
+    const size_t o_runs = o; o += up8(4 * ((size_t)n_runs + 1));
+    const size_t o_coff = o; o += 8 * ((size_t)n_reads + 1);
+    const size_t o_loff = o; o += 8 * ((size_t)n_reads + 1);
+    if (int rc = ensure(h, h->d_msa_in, o)) return rc;
+    char *din = (char *)h->d_msa_in.p;
+    cudaStream_t st = h->stream_hi;
+    if (R) SMX_CUDA(h, cudaMemcpyAsync(din + o_ref, ref, (size_t)R, cudaMemcpyHostToDevice, st));
+    if (n_reads) {
+        SMX_CUDA(h, cudaMemcpyAsync(din + o_qry, qry, (size_t)n_q, cudaMemcpyHostToDevice, st));
+        SMX_CUDA(h, cudaMemcpyAsync(din + o_qs, qscore, (size_t)n_q, cudaMemcpyHostToDevice, st));
+        SMX_CUDA(h, cudaMemcpyAsync(din + o_qoff, qry_off, 8 * (size_t)n_reads, cudaMemcpyHostToDevice, st));
+        SMX_CUDA(h, cudaMemcpyAsync(din + o_qlen, qry_len, 4 * (size_t)n_reads, cudaMemcpyHostToDevice, st));
+        SMX_CUDA(h, cudaMemcpyAsync(din + o_runs, cigar_rle, 4 * (size_t)n_runs, cudaMemcpyHostToDevice, st));
+        SMX_CUDA(h, cudaMemcpyAsync(din + o_coff, cigar_off, 8 * ((size_t)n_reads + 1), cudaMemcpyHostToDevice, st));
+    }
+    SMX_CUDA(h, cudaMemcpyAsync(din + o_loff, let_off.data(), 8 * ((size_t)n_reads + 1), cudaMemcpyHostToDevice, st));
+    // work block: let | pos | qcnt | n_s | n_i | err | col_off | type_off | types
+    const size_t per = (size_t)R + 1;
+    size_t w = 0;
+    const size_t w_let = w; w += up8((size_t)let_off[(size_t)n_reads] + 1);
+    const size_t w_pos = w; w += up8(4 * per * (size_t)std::max(n_reads, 1));
+    const size_t w_qc = w; w += up8(4 * per * (size_t)std::max(n_reads, 1));
+    const size_t w_ns = w; w += up8(4 * per);
+    const size_t w_ni = w; w += up8(4 * per);
+    const size_t w_err = w; w += up8(4 * ((size_t)n_reads + 1));
+    const size_t w_col = w; w += 8 * (per + 1);
+    const size_t w_toff = w; w += up8(4 * (per + 1));
+    const size_t w_types = w; w += up8(types.size() + 1);
+    if (int rc = ensure(h, h->d_msa_work, w)) return rc;
+    char *dw = (char *)h->d_msa_work.p;
+    SmxMsaArgs a;
+    memset(&a, 0, sizeof a);
+    a.ref = (const uint8_t *)(din + o_ref); a.R = R; a.n_reads = n_reads;
+    a.qry = (const uint8_t *)(din + o_qry); a.qscore = (const int8_t *)(din + o_qs);
+    a.qry_off = (const int64_t *)(din + o_qoff); a.qry_len = (const int32_t *)(din + o_qlen);
+    a.cigar_rle = (const uint32_t *)(din + o_runs); a.cigar_off = (const int64_t *)(din + o_coff);
+    a.let = (uint8_t *)(dw + w_let); a.let_off = (const int64_t *)(din + o_loff);
+    a.pos = (int32_t *)(dw + w_pos); a.qcnt = (int32_t *)(dw + w_qc);
+    a.n_s = (int32_t *)(dw + w_ns); a.n_i = (int32_t *)(dw + w_ni); a.err = (int32_t *)(dw + w_err);
+    a.col_off = (const int64_t *)(dw + w_col); a.type_off = (const int32_t *)(dw + w_toff); a.types = (const uint8_t *)(dw + w_types);
+    std::vector<int32_t> ns(per, 0), ni(per, 0), err((size_t)n_reads + 1, 0);
+    if (n_reads > 0) {
+        smx_msa_expand<<<(n_reads + 3) / 4, 128, 0, st>>>(a);
+        SMX_CUDA(h, cudaGetLastError());
+        // a CIGAR that does not consume exactly the reference leaves position entries unset: checked before anything reads them
+        SMX_CUDA(h, cudaMemcpyAsync(err.data(), a.err, 4 * (size_t)n_reads, cudaMemcpyDeviceToHost, st));
+        SMX_CUDA(h, smx_sync(h, st));
+        for (int i = 0; i < n_reads; ++i)
+            if (err[(size_t)i]) return fail(h, -6, "smx_msa_run: the CIGAR of read %d does not consume exactly the reference (%d) and its query (%d) "
+                                                   "(generate_msa's final assertions, msa.py:913-916)", i, R, qry_len[i]);
+        smx_msa_gaps<<<(unsigned)((per + 3) / 4), 128, 0, st>>>(a);
+        SMX_CUDA(h, cudaGetLastError());
+        SMX_CUDA(h, cudaMemcpyAsync(ns.data(), a.n_s, 4 * per, cudaMemcpyDeviceToHost, st));
+        SMX_CUDA(h, cudaMemcpyAsync(ni.data(), a.n_i, 4 * per, cudaMemcpyDeviceToHost, st));
+        SMX_CUDA(h, smx_sync(h, st));
+    }
+    // columns: gap r holds its extra columns, then (r < R) the reference column
+    std::vector<int64_t> col_off(per + 1, 0);
+    for (size_t r = 0; r < per; ++r) {
+        const int64_t extra = type_off[r + 1] > type_off[r] ? type_off[r + 1] - type_off[r] : (int64_t)ns[r] + ni[r];
+        col_off[r + 1] = col_off[r] + extra + (r < (size_t)R ? 1 : 0);
+    }
+    const int64_t C = col_off[per];
+    SMX_CUDA(h, cudaMemcpyAsync(dw + w_col, col_off.data(), 8 * (per + 1), cudaMemcpyHostToDevice, st));
+    SMX_CUDA(h, cudaMemcpyAsync(dw + w_toff, type_off.data(), 4 * (per + 1), cudaMemcpyHostToDevice, st));
+    if (!types.empty()) SMX_CUDA(h, cudaMemcpyAsync(dw + w_types, types.data(), types.size(), cudaMemcpyHostToDevice, st));
+    const size_t rows = (size_t)n_reads;
+    if (int rc = ensure(h, h->d_msa_out, (size_t)C * (1 + 3 * rows) + 64)) return rc;
+    char *dout = (char *)h->d_msa_out.p;
+    a.n_cols = C;
+    a.out_ref = (uint8_t *)dout; a.out_seq = (uint8_t *)dout + (size_t)C; a.out_cig = a.out_seq + (size_t)C * rows; a.out_qs = (int8_t *)(a.out_cig + (size_t)C * rows);
+    if (C > 0) {
+        dim3 grid((unsigned)((per + 255) / 256), (unsigned)std::min<int64_t>((int64_t)n_reads + 1, 32768));
+        smx_msa_fill<<<grid, 256, 0, st>>>(a);
+        SMX_CUDA(h, cudaGetLastError());
+    }
+    SMX_CUDA(h, smx_sync(h, st));
+    h->msa_cols = C; h->msa_reads = n_reads;
+    if (n_cols) *n_cols = C;
+    return 0;
+}
+
+extern "C" int smx_msa_fetch(smx_handle *h, uint8_t *ref_aligned, uint8_t *seq_aligned, int8_t *qs_aligned, uint8_t *cigar_aligned)
+{
+    if (!h) return -1;
+    if (h->msa_cols < 0) return fail(h, -1, "smx_msa_fetch: no completed smx_msa_run");
+    SMX_CUDA(h, cudaSetDevice(h->device));
+    const size_t C = (size_t)h->msa_cols, rows = (size_t)h->msa_reads;
+    const char *d = (const char *)h->d_msa_out.p;
+    cudaStream_t st = h->stream_hi;
+    if (C == 0) return 0;
+    if (ref_aligned) SMX_CUDA(h, cudaMemcpyAsync(ref_aligned, d, C, cudaMemcpyDeviceToHost, st));
+    if (rows) {
+        if (seq_aligned) SMX_CUDA(h, cudaMemcpyAsync(seq_aligned, d + C, C * rows, cudaMemcpyDeviceToHost, st));
+        if (cigar_aligned) SMX_CUDA(h, cudaMemcpyAsync(cigar_aligned, d + C + C * rows, C * rows, cudaMemcpyDeviceToHost, st));
+        if (qs_aligned) SMX_CUDA(h, cudaMemcpyAsync(qs_aligned, d + C + 2 * C * rows, C * rows, cudaMemcpyDeviceToHost, st));
+    }
+    SMX_CUDA(h, smx_sync(h, st));
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Row N2: assignment on the device, .ir result blocks from the arrays (smx_outputs.cuh)
