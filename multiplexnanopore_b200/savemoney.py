@@ -333,13 +333,19 @@ class DenseResult:
         return self._cigar
 
 
-def legacy_dense_align(ref_seq_list, my_fastq, param_dict, engine=None, batch_cells=int(3e10), stats=None):
+def legacy_dense_align(ref_seq_list, my_fastq, param_dict, engine=None, batch_cells=int(7e10), stats=None, overlap=2,
+                       trace_budget=40 << 30):
     """Row N4, the pre-0.2 alignment mode kept in the reference under Modules/ (MyAligner.align_all /
     MyAlignerLinear.align_all, Modules/1_alignment_consensus_core.py:219-296): one local alignment
     `parasail.sw_trace(read, reference + reference)` (circular; `reference` alone for linear topology) per read,
     plasmid and strand, no seeding.  Returns {query_id: [DenseResult(ref0), DenseResult(ref0, rc), DenseResult(ref1), ...]}.
-    Runs through `Engine.align_batch` (mode 3), `batch_cells` DP cells per call.  `stats` (a dict) receives the
-    cells, launches and CUDA-event kernel times of the call (bench.py --config legacy_dense)."""
+    Runs through `Engine.align_batch` (mode 3, the packed local kernel), `batch_cells` DP cells per call, `overlap` calls in
+    flight on handles of their own (the latency-bound traceback and the host side of one call under the forward phase of
+    the next).  Dense problems are large (100 M cells, 56 MB of direction bits each): the handles get `trace_budget` bytes
+    of arena for the call so that a launch holds enough problems to fill the GPU with narrow teams.  `stats` (a dict) receives the cells, launches and CUDA-event kernel times (bench.py --config legacy_dense)."""
+    import threading
+    from concurrent.futures import ThreadPoolExecutor
+    import queue
     from .engine import MODE_SW
     _check_params(param_dict)
     eng = engine or default_engine()
@@ -348,52 +354,74 @@ def legacy_dense_align(ref_seq_list, my_fastq, param_dict, engine=None, batch_ce
     targets = [r + r if circular else r for r in refs]
     ids = list(my_fastq.keys())
     comp = str.maketrans("ACGTMRWSYKVHDBN", "TGCAKYWSRMBDHVN")
-    out = {}
     go, ge = param_dict["gap_open_penalty"], param_dict["gap_extend_penalty"]
     ma, mi = param_dict["match_score"], param_dict["mismatch_score"]
     if stats is not None:
         stats.update(cells=0, launches=0, problems=0, out_bytes=0, kernel_ms_total=0.0, class_ms=[0.0] * 16, class_cells=[0] * 14,
                      class_launches=[0] * 16)
-    pos = 0
-    while pos < len(ids):
-        # reads of this call: as many as fit the cell budget (at least one)
+    lock = threading.Lock()
+    nt, target_len = len(targets), sum(len(t) for t in targets)
+    ranges, pos = [], 0
+    while pos < len(ids):   # reads of a call: as many as fit the cell budget (at least one)
         end, cells = pos, 0
         while end < len(ids):
-            c = 2 * len(_seq_of(my_fastq[ids[end]][0])) * sum(len(t) for t in targets)
+            c = 2 * len(_seq_of(my_fastq[ids[end]][0])) * target_len
             if end > pos and cells + c > batch_cells:
                 break
             cells += c
             end += 1
-        seqs = list(targets)
-        for qid in ids[pos:end]:
-            q = _seq_of(my_fastq[qid][0]).upper()
-            seqs += [q, q.translate(comp)[::-1]]
-        offs, lens = eng.upload_sequences(seqs)
-        nt = len(targets)
-        s1, s2 = [], []
-        for k in range(end - pos):
-            for t in range(nt):
-                for strand in range(2):
-                    s1.append(nt + 2 * k + strand)
-                    s2.append(t)
-        s1 = np.array(s1); s2 = np.array(s2)
-        res = eng.align_batch(offs[s1], lens[s1], offs[s2], lens[s2], np.full(len(s1), MODE_SW, np.uint8), go, ge, ma, mi)
-        if stats is not None:
-            kms, kcells = eng.align_kernel_ms()
-            stats["cells"] += eng.align_cells; stats["launches"] += eng.last_run_launches; stats["problems"] += len(s1)
-            stats["out_bytes"] += int(res.cigar_rle.nbytes + 5 * res.score.nbytes + res.cigar_off.nbytes)
-            stats["kernel_ms_total"] += float(kms.sum())
-            for c in range(16):
-                stats["class_ms"][c] += float(kms[c]); stats["class_launches"][c] += int(kms[c] > 0)
-            for c in range(14):
-                stats["class_cells"][c] += int(kcells[c])
-        p = 0
-        for qid in ids[pos:end]:
+        ranges.append((pos, end))
+        pos = end
+    engines = [eng] + (eng.siblings(min(overlap, len(ranges)) - 1) if overlap > 1 and len(ranges) > 1 else [])
+    free = queue.SimpleQueue()
+    budgets = [e.trace_budget for e in engines]
+    for e in engines:
+        e.set_trace_budget(max(e.trace_budget, int(trace_budget)))
+        free.put(e)
+
+    def one_call(rng_):
+        lo, hi = rng_
+        e = free.get()
+        try:
+            seqs = list(targets)
+            for qid in ids[lo:hi]:
+                q = _seq_of(my_fastq[qid][0]).upper()
+                seqs += [q, q.translate(comp)[::-1]]
+            offs, lens = e.upload_sequences(seqs)
+            k = np.arange(hi - lo)
+            s1 = (nt + 2 * k[:, None, None] + np.arange(2)[None, None, :] + np.zeros((1, nt, 1), np.int64)).ravel()
+            s2 = (np.zeros((hi - lo, 1, 1), np.int64) + np.arange(nt)[None, :, None] + np.zeros((1, 1, 2), np.int64)).ravel()
+            res = e.align_batch(offs[s1], lens[s1], offs[s2], lens[s2], np.full(len(s1), MODE_SW, np.uint8), go, ge, ma, mi)
+            if stats is not None:
+                kms, kcells = e.align_kernel_ms()
+                with lock:
+                    stats["cells"] += e.align_cells; stats["launches"] += e.last_run_launches; stats["problems"] += len(s1)
+                    stats["out_bytes"] += int(res.cigar_rle.nbytes + 5 * res.score.nbytes + res.cigar_off.nbytes)
+                    stats["kernel_ms_total"] += float(kms.sum())
+                    for c in range(16):
+                        stats["class_ms"][c] += float(kms[c]); stats["class_launches"][c] += int(kms[c] > 0)
+                    for c in range(14):
+                        stats["class_cells"][c] += int(kcells[c])
+        finally:
+            free.put(e)
+        part, p = {}, 0
+        for qid in ids[lo:hi]:
             row = []
             for _ in range(2 * nt):
                 row.append(DenseResult(int(res.score[p]), res.runs(p), int(res.beg_query[p]), int(res.beg_ref[p]),
                                        int(res.end_query[p]), int(res.end_ref[p])))
                 p += 1
-            out[qid] = row
-        pos = end
+            part[qid] = row
+        return part
+
+    out = {}
+    if len(engines) == 1:
+        parts = [one_call(r) for r in ranges]
+    else:
+        with ThreadPoolExecutor(max_workers=len(engines)) as ex:
+            parts = list(ex.map(one_call, ranges))
+    for e, b in zip(engines, budgets):
+        e.set_trace_budget(b)
+    for part in parts:
+        out.update(part)
     return out
