@@ -38,6 +38,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before torch / the engine create the CUDA context (multiplexnanopore_b200/_lib.py)
 
 PARAMS = dict(gap_open_penalty=3, gap_extend_penalty=1, match_score=1, mismatch_score=-2, topology_of_dna=0)
 # Algorithmic integer lane-instructions per DP cell WITH direction bits:

@@ -423,7 +423,7 @@ static int pool_finish(smx_handle *h, int64_t n)
 // 10..13 for the packed s16x2 kernel with 1, 2, 4, 8 warps per problem
 enum { kClsS16 = 10, kNumFwdClasses = 14, kSlotTraceback = 14, kSlotCompact = 15, kNumSlots = 16 };
 static const int kTeamMinRows = 513;
-static const int kTbBigWalk = 768;  // m + n from which a traceback walk gets its own warp
+static const int kTbBigWalk = [] { const char *e = getenv("SMX_TB_BIGWALK"); const int v = e ? atoi(e) : 768; return v < 64 ? 64 : v; }();  // m + n from which a traceback walk gets its own warp
 static int problem_class(int m, int mode);
 static int pick_kshift(int m)
 {
