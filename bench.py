@@ -15,7 +15,7 @@ reference algorithm counts them (sum of len(s1) * len(s2) over every parasail ca
                DP, traceback, CIGAR compaction), measured in one extra pass with the batches serialised (with several
                batches in flight the event intervals of one handle contain the other handles' kernels).  Serialised
                launches cannot fill each other's tails, so value can come out BELOW e2e.  `value_source` says so.
-  e2e.value    through the C-ABI call with HOST buffers (six 1000-read batches in flight), host<->device copies and
+  e2e.value    through the C-ABI call with HOST buffers (eight 1000-read batches in flight), host<->device copies and
                host stages inside the timed region: the headline
   ms_per_step  wall clock per step (the e2e path), max over ranks
 Multi-GPU: one process per GPU.  weak: every rank aligns its own draw of the workload; strong: the units (reads, plasmid
@@ -517,7 +517,7 @@ def main():
     ap.add_argument("--maps", type=int, default=0, help="plasmid maps of c3 (96)")
     ap.add_argument("--mixtures", type=int, default=0, help="mixtures of c5 (96 at 8 GPUs, else 12 per GPU)")
     ap.add_argument("--batch", type=int, default=1000, help="reads per smx_pipeline_run call")
-    ap.add_argument("--overlap", type=int, default=6, help="batches in flight per rank (engine handles)")
+    ap.add_argument("--overlap", type=int, default=8, help="batches in flight per rank (engine handles)")
     ap.add_argument("--cpu-reads", type=int, default=0, help=f"units of the CPU sample (engine arm: {CPU_SAMPLE_READS}; reference arm: max(4 * cores, 16) per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--threads", type=int, default=0, help="host threads per rank (default: cores / ranks)")

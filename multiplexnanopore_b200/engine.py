@@ -342,8 +342,19 @@ class ShardedPipelineResult(_PipelineResultOps):
 
     @property
     def cigar_rle(self) -> np.ndarray:
+        """all runs in the caller's order (one block copy per unit: the pair-strands of a unit are consecutive on both sides)"""
         if self._flat is None:
-            self._flat = np.concatenate([self.runs(i) for i in range(len(self.score))]) if len(self.score) else np.empty(0, np.uint32)
+            flat = np.empty(int(self.cigar_off[-1]), np.uint32)
+            per = self.per_unit
+            for k, p in enumerate(self.parts):
+                src, soff = p.cigar_rle, p.cigar_off
+                units = np.nonzero(self._shard == k)[0]
+                for u in units:
+                    j = int(self._local[u])
+                    a, b = int(soff[j * per]), int(soff[(j + 1) * per])
+                    g = int(self.cigar_off[u * per])
+                    flat[g:g + (b - a)] = src[a:b]
+            self._flat = flat
         return self._flat
 
     @property

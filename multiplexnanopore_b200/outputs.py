@@ -148,10 +148,8 @@ def format_result_blocks(res, first_index=0, n_threads=4) -> bytes:
     """the `# resultK(dict)` blocks of one (Segmented / Sharded)PipelineResult, K counted from `first_index`"""
     lib = _lib.load()
     parts = getattr(res, "parts", None)
-    if parts is not None and hasattr(res, "_shard"):      # sharded: blocks must follow the caller's read order
-        return b"".join(_format_arrays(lib, res.score[i:i + 1], res.new_query_seq_offset[i:i + 1], res.status[i:i + 1],
-                                       np.array([0, len(res.runs(i))], np.int64), np.ascontiguousarray(res.runs(i)), first_index + i, 1)
-                        for i in range(len(res.score)))
+    if parts is not None and hasattr(res, "_shard"):      # sharded over GPUs: the blocks follow the caller's read order
+        return _format_arrays(lib, res.score, res.new_query_seq_offset, res.status, res.cigar_off, res.cigar_rle, first_index, n_threads)
     if parts is not None:                                  # batches of one GPU, already in order
         out, k = [], first_index
         for p in parts:

@@ -99,7 +99,7 @@ def _engines_for(engine, n):
     """`n` engines on the device of `engine`: the caller's engine plus lazily created siblings, owned by that engine
     (`engine.close()` closes them).  Several handles in flight let the host stages (planning, stitching) of one batch
     overlap the GPU stages of the others, and let kernels of different batches fill each other's tails (measured best
-    on B200: 6 x 1000 reads)."""
+    on B200: 6 to 8 x 1000 reads; 8 tolerates a host with few cores per GPU better)."""
     pool = engine.siblings(n - 1)
     pool = [engine] + pool
     if n > 6:
@@ -157,7 +157,7 @@ def _align_sharded(refs, queries, param_dict, omit_too_long, pairs, devices, n_t
 
 
 def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None, n_threads=0, batch_queries=1000,
-              overlap=6, devices=None):
+              overlap=8, devices=None):
     """The alignment stage for every (query, reference) pair and both strands (or the explicit `pairs`).
     Queries are processed in batches of `batch_queries` so that device workspaces stay bounded; `overlap`
     batches are in flight at once (one engine handle and one Python thread each; ctypes drops the GIL).
