@@ -11,6 +11,7 @@ calls into this module; kwargs, result_dict layout and output f
 """
 from __future__ import annotations
 
+import os
 import re
 from itertools import combinations
 
@@ -121,7 +122,6 @@ def _align_sharded(refs, queries, param_dict, omit_too_long, pairs, devices, n_t
     thread (ctypes releases the GIL), and the results come back in the caller's order.  No collective: the only
     inter-GPU step is this host-side gather.  Replaces multiprocessing.Pool(n_cpu).imap
     (post_analysis_core.py:58-61, pre_survey_core.py:240-244)."""
-    import os
     from concurrent.futures import ThreadPoolExecutor
     from . import shard
     from .engine import ShardedPipelineResult
@@ -175,9 +175,9 @@ def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None,
     sig = [sigma_for(len(r)) for r in refs]
     args = (param_dict["gap_open_penalty"], param_dict["gap_extend_penalty"], param_dict["match_score"],
             param_dict["mismatch_score"], param_dict["topology_of_dna"], omit_too_long)
-    if pairs is None and overlap > 1 and 500 < len(queries) < batch_queries * overlap:
-        # few reads for this GPU (one GPU's share of a strong-scaled call): smaller batches keep `overlap` handles busy
-        batch_queries = min(batch_queries, max(250, -(-len(queries) // overlap)))
+    if pairs is None and overlap > 1 and batch_queries < len(queries) < batch_queries * overlap and os.environ.get("SMX_ADAPT_BATCH", "1") != "0":
+        # few reads for this GPU (one GPU's share of a strong-scaled call): smaller batches keep more handles busy
+        batch_queries = min(batch_queries, max(int(os.environ.get("SMX_ADAPT_MIN", "500")), -(-len(queries) // overlap)))
     if pairs is not None or len(queries) <= batch_queries:
         return eng.pipeline_run(refs, queries, sig, *args, pairs=pairs, n_threads=n_threads)
     from .engine import _pack
@@ -192,7 +192,6 @@ def align_all(refs, queries, param_dict, omit_too_long, pairs=None, engine=None,
     from concurrent.futures import ThreadPoolExecutor
     engines = _engines_for(eng, min(overlap, len(bounds) - 1))
     if n_threads <= 0:  # host stages need about three cores per GPU; every handle in flight runs its own pool
-        import os
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
         n_threads = max(1, min(4, cores // len(engines)))
     free = queue.SimpleQueue()
@@ -233,7 +232,6 @@ def _batch_bounds(n, batch, overlap):
     """Batch boundaries for `n` queries.  With several batches in flight the first and the last batches are smaller
     (a quarter, then half a batch): the first forward-DP launch starts sooner and the last handles drain together
     instead of one full batch after the other."""
-    import os
     head = [batch // 4] * min(overlap // 2, 3) + [batch // 2] * min(overlap // 2, 3)
     tail = head[::-1]
     if n < sum(head) + sum(tail) + batch or min(head, default=0) < 1 or os.environ.get("SMX_RAMP", "1") == "0":

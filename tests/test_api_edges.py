@@ -90,3 +90,16 @@ def test_ultra_long_reads_do_not_fail_the_call(engine):
     got = [[res.cigar_string(j), int(res.score[j]), res.offset(j)] for j in range(2)]
     assert got == want
     assert max(w[1] for w in want) > 30000   # it did align
+
+
+def test_mid_size_call_takes_the_adaptive_batches(engine):
+    """1 000 < reads < batch x overlap: the call is cut into smaller batches so that more handles are busy (one GPU's share
+    of a strong-scaled run); results and order are those of one big batch."""
+    rng = np.random.default_rng(85)
+    plasmids = synth.plasmid_set(rng, 2, 300, 420, backbone=120)
+    reads, _ = synth.reads_for(rng, plasmids, 1300, topology=0, frac_full=0.3, frac_partial=0.6)
+    res = sm.align_all(plasmids, reads, PARAMS, True, engine=engine)          # 1300 reads -> 3 batches of 500
+    assert len(getattr(res, "parts", [])) >= 3
+    one = sm.align_all(plasmids, reads, PARAMS, True, engine=engine, batch_queries=2000)   # one pipeline call
+    assert np.array_equal(res.score, one.score) and np.array_equal(res.status, one.status) and np.array_equal(res.cigar_off, one.cigar_off)
+    assert all(np.array_equal(res.runs(i), one.runs(i)) for i in range(0, len(res.score), 37))
