@@ -413,13 +413,15 @@ def legacy_dense_align(ref_seq_list, my_fastq, param_dict, engine=None, batch_ce
         return part
 
     out = {}
-    if len(engines) == 1:
-        parts = [one_call(r) for r in ranges]
-    else:
-        with ThreadPoolExecutor(max_workers=len(engines)) as ex:
-            parts = list(ex.map(one_call, ranges))
-    for e, b in zip(engines, budgets):
-        e.set_trace_budget(b)
+    try:
+        if len(engines) == 1:
+            parts = [one_call(r) for r in ranges]
+        else:
+            with ThreadPoolExecutor(max_workers=len(engines)) as ex:
+                parts = list(ex.map(one_call, ranges))
+    finally:
+        for e, b in zip(engines, budgets):
+            e.set_trace_budget(b)
     for part in parts:
         out.update(part)
     return out
