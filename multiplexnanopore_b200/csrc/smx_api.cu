@@ -1867,11 +1867,14 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
     std::atomic<int> n_bad(0);
     const std::vector<SmxResult> &dres = h->h_results;
     const bool merge_chars = [] { const char *e = getenv("SMX_MERGE"); return e && std::string(e) == "chars"; }();  // cross-check switch
+    const bool sub_timers = plog.on && n_threads == 1;   // SMX_PHASE_LOG with one host thread: where the stitch stage spends its time
+    double t_sub[4] = {0, 0, 0, 0};                      // assemble, my_special_DP merge, rotate, score
     parallel_for((int)todo.size(), n_threads, [&](int ti, int) {
         PairStrand &x = st.ps[(size_t)todo[(size_t)ti]];
         if (x.failed) return;
         Runs &cig = x.runs;
         cig.clear();
+        double ts0 = sub_timers ? now_s() : 0.0, t_merge = 0.0;
         auto n_runs_of = [&](int pid) { return pid >= 0 ? cg_off[(size_t)pid + 1] - cg_off[(size_t)pid] : (int64_t)0; };
         {
             int64_t need = 4;
@@ -1903,16 +1906,23 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
                 ClippedSg r1, r2;
                 if (pc.prob[0] >= 0) r1 = clipped(pc.prob[0]); else r1.n_h = pc.n_ref;   // "H" * len(ref), end_ref = -1
                 if (pc.prob[1] >= 0) r2 = clipped(pc.prob[1]); else r2.n_h = pc.n_ref;   // "H" * len(ref), beg_ref = len(ref)
-                if (!merge_special_runs(r1, r2, pc.n_ref, pc.nq1, pc.nq2, sc, cig, merge_chars)) { x.failed = true; n_bad++; return; }
+                const double tm0 = sub_timers ? now_s() : 0.0;
+                const bool ok = merge_special_runs(r1, r2, pc.n_ref, pc.nq1, pc.nq2, sc, cig, merge_chars);
+                if (sub_timers) t_merge += now_s() - tm0;
+                if (!ok) { x.failed = true; n_bad++; return; }
                 break;
             }
             }
         }
         int64_t new_off = 0;
+        const double ts1 = sub_timers ? now_s() : 0.0;
         if (topology == 0) new_off = rotate_to_ref0_runs(cig, x.ref_off, x.q_off);
+        const double ts2 = sub_timers ? now_s() : 0.0;
         x.score = (int32_t)cigar_score_runs(cig, sc);
         x.new_q_off = (int32_t)new_off;
+        if (sub_timers) { const double ts3 = now_s(); t_sub[0] += ts1 - ts0 - t_merge; t_sub[1] += t_merge; t_sub[2] += ts2 - ts1; t_sub[3] += ts3 - ts2; }
     });
+    if (sub_timers) fprintf(stderr, "STITCH %p assemble %.4f merge %.4f rotate %.4f score %.4f\n", (void *)h, t_sub[0], t_sub[1], t_sub[2], t_sub[3]);
     st.n_failed += n_bad.load();
     st.t_stitch = now_s() - t0;
     plog.cpu(h, "stitch");

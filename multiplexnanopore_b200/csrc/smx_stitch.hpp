@@ -323,44 +323,71 @@ inline int64_t aligned_offset_runs(const Runs &v, int64_t off, uint32_t mask)
 // Suffix sums over a run array: columns, I/S columns and D/H columns of runs[i..).  The fixed-point iterations of
 // get_aligned_ref_seq_offset / get_aligned_query_seq_offset ask for "how many I/S (D/H) columns among the last `a`
 // columns" about a dozen times per pair-strand; scanning the tail each time was most of the stitch stage (12 ns per run
-// and pair-strand), with the sums one pass and a binary search per question.
+// and pair-strand).  Round 1 kept the three sums for EVERY run (24 bytes written per run: the heaviest pass of the
+// stage); now one checkpoint per 64 runs: a question is a binary search over the checkpoints plus at most 64 runs.
 struct TailSums {
-    std::vector<int64_t> cols, is, dh;  // size n + 1, entry n = 0
+    static constexpr size_t B = 64;
+    std::vector<int64_t> ck;  // 3 per checkpoint c: columns, I/S columns, D/H columns of runs[c * B ..); last checkpoint = (0, 0, 0)
     const Runs *v = nullptr;
+    size_t n = 0, n_ck = 0;
+    int64_t total[3] = {0, 0, 0};
+    static inline void add(uint32_t run, int64_t (&acc)[3])
+    {
+        const int64_t len = run >> 4;
+        const uint32_t op = run & 15u;
+        acc[0] += len;
+        acc[1] += (op == 1u || op == 4u) ? len : 0;
+        acc[2] += (op == 2u || op == 5u) ? len : 0;
+    }
     void build(const Runs &runs)
     {
         v = &runs;
-        const size_t n = runs.size();
-        cols.resize(n + 1); is.resize(n + 1); dh.resize(n + 1);
-        int64_t c = 0, a = 0, b = 0;
-        cols[n] = 0; is[n] = 0; dh[n] = 0;
+        n = runs.size();
+        n_ck = (n + B - 1) / B + 1;
+        ck.resize(3 * n_ck);
+        int64_t acc[3] = {0, 0, 0};
+        size_t c = n_ck - 1;
+        ck[3 * c] = 0; ck[3 * c + 1] = 0; ck[3 * c + 2] = 0;
         for (size_t i = n; i-- > 0;) {
-            const int64_t len = runs[i] >> 4;
-            const uint32_t op = runs[i] & 15u;
-            c += len;
-            if (op == 1u || op == 4u) a += len;
-            else if (op == 2u || op == 5u) b += len;
-            cols[i] = c; is[i] = a; dh[i] = b;
+            add(runs[i], acc);
+            if (i % B == 0) { c = i / B; ck[3 * c] = acc[0]; ck[3 * c + 1] = acc[1]; ck[3 * c + 2] = acc[2]; }
         }
+        total[0] = acc[0]; total[1] = acc[1]; total[2] = acc[2];
+    }
+    int64_t cols0() const { return total[0]; }
+    // smallest run index i whose suffix runs[i..) holds at most `limit` columns (strict: fewer than `limit`), with the sums of that suffix
+    size_t first_suffix_within(int64_t limit, bool strict, int64_t (&sum)[3]) const
+    {
+        auto ok = [&](int64_t c) { return strict ? c < limit : c <= limit; };
+        size_t lo = 0, hi = n_ck - 1;   // smallest checkpoint whose suffix is within the limit (the last one always is: 0 columns)
+        while (lo < hi) {
+            const size_t mid = (lo + hi) >> 1;
+            if (ok(ck[3 * mid])) hi = mid; else lo = mid + 1;
+        }
+        size_t i = std::min(lo * B, n);
+        sum[0] = ck[3 * lo]; sum[1] = ck[3 * lo + 1]; sum[2] = ck[3 * lo + 2];
+        const size_t floor_i = lo == 0 ? 0 : (lo - 1) * B;
+        while (i > floor_i) {   // extend backwards run by run inside the block before the checkpoint
+            int64_t t[3] = {sum[0], sum[1], sum[2]};
+            add((*v)[i - 1], t);
+            if (!ok(t[0])) break;
+            sum[0] = t[0]; sum[1] = t[1]; sum[2] = t[2];
+            --i;
+        }
+        return i;
     }
     // columns among the last `a` columns that are I/S (which = 0) or D/H (which = 1); a beyond the length clamps
     int64_t count(int64_t a, int which) const
     {
         if (a <= 0) return 0;
-        const std::vector<int64_t> &w = which ? dh : is;
-        const size_t n = v->size();
-        if (a >= cols[0]) return w[0];
-        // smallest i with cols[i] <= a (cols is non-increasing in i): runs i.. lie inside the tail entirely
-        size_t lo = 0, hi = n;
-        while (lo < hi) {
-            const size_t mid = (lo + hi) >> 1;
-            if (cols[mid] <= a) hi = mid; else lo = mid + 1;
-        }
-        int64_t cnt = w[lo];
+        if (a >= total[0]) return total[1 + which];
+        int64_t sum[3];
+        const size_t lo = first_suffix_within(a, false, sum);   // runs lo.. lie inside the tail entirely
+        int64_t cnt = sum[1 + which];
         if (lo > 0) {  // the run before contributes its last a - cols[lo] columns
             const uint32_t op = (*v)[lo - 1] & 15u;
             const bool hit = which ? (op == 2u || op == 5u) : (op == 1u || op == 4u);
-            if (hit) cnt += a - cols[lo];
+            if (hit) cnt += a - sum[0];
         }
         return cnt;
     }
@@ -392,18 +419,16 @@ inline int64_t rotate_to_ref0_runs(Runs &v, int64_t ref_off, int64_t q_off)
     else if (a_r != 0) new_off = diff + ts.count(a_r, 1);
     else new_off = 0;
     if (a_r > 0) {
-        const int64_t n = ts.cols[0];
+        const int64_t n = ts.cols0();
         const int64_t head = a_r >= n ? 0 : n - a_r;  // columns that move to the back
         // v is maximal, so after cutting at column `head` only the wrap-around junction (old last run, old first
         // run) can merge; everything else moves as blocks
-        // idx = leading runs that lie before the cut entirely: the largest i with n - cols[i] <= head
-        size_t lo = 0, hi = v.size();
-        while (lo < hi) {  // smallest i with cols[i] < n - head
-            const size_t mid = (lo + hi) >> 1;
-            if (ts.cols[mid] < n - head) hi = mid; else lo = mid + 1;
-        }
+        // idx = leading runs that lie before the cut entirely: one before the smallest i whose suffix holds fewer than n - head columns
+        int64_t sum[3];
+        const size_t lo = ts.first_suffix_within(n - head, true, sum);
         const size_t idx = lo > 0 ? lo - 1 : 0;
-        const int64_t acc = n - ts.cols[idx];
+        const int64_t cols_idx = lo > 0 ? sum[0] + (int64_t)(v[idx] >> 4) : sum[0];
+        const int64_t acc = n - cols_idx;
         const int64_t part = head - acc;  // leading columns of v[idx] that still lie before the cut (they move to the back)
         if (idx > 0 || part > 0) {
             thread_local Runs tl_rot;
@@ -418,7 +443,7 @@ inline int64_t rotate_to_ref0_runs(Runs &v, int64_t ref_off, int64_t q_off)
                 t.insert(t.end(), v.begin() + 1, v.begin() + (std::ptrdiff_t)idx);
             }
             if (part > 0) push_run(t, v[idx] & 15u, part);
-            v.assign(t.begin(), t.end());
+            v.swap(t);   // the old array becomes the next call's scratch
         }
     }
     return new_off;
@@ -426,16 +451,12 @@ inline int64_t rotate_to_ref0_runs(Runs &v, int64_t ref_off, int64_t q_off)
 
 inline int64_t cigar_score_runs(const Runs &v, const Scoring &sc)
 {
+    // per op: score = per_col[op] * len + per_run[op]  ('=' 7, 'X' 8, gaps 1 / 2: -(go + ge (len - 1)); S, H, N free)
+    int64_t per_col[16] = {0}, per_run[16] = {0};
+    per_col[7] = sc.ma; per_col[8] = sc.mi;
+    per_col[1] = per_col[2] = -sc.ge; per_run[1] = per_run[2] = -(sc.go - sc.ge);
     int64_t s = 0;
-    for (uint32_t r : v) {
-        const int64_t len = r >> 4;
-        switch (r & 15u) {
-        case 7: s += sc.ma * len; break;
-        case 8: s += sc.mi * len; break;
-        case 1: case 2: s -= sc.go + sc.ge * (len - 1); break;
-        default: break;
-        }
-    }
+    for (uint32_t r : v) s += per_col[r & 15u] * (int64_t)(r >> 4) + per_run[r & 15u];
     return s;
 }
 

@@ -34,3 +34,10 @@ extern "C" long long smx_test_rotate(uint32_t *runs, long long n, long long cap,
     if (!v.empty()) memcpy(runs, v.data(), sizeof(uint32_t) * v.size());
     return (long long)v.size();
 }
+
+// set_cigar_score on runs
+extern "C" long long smx_test_score(const uint32_t *runs, long long n, int go, int ge, int ma, int mi)
+{
+    smx::Runs v(runs, runs + n);
+    return (long long)smx::cigar_score_runs(v, smx::Scoring{go, ge, ma, mi});
+}

@@ -162,3 +162,32 @@ def test_rotation_on_runs_matches_column_strings(harness):
         assert got[0][0] == want_cig and got[0][1] == want_off, (cig, ref_off, q_off)
         n_rot += want_cig != cig
     assert n_rot > 300
+
+
+def test_rotation_at_checkpoint_boundaries_and_score(harness):
+    """The suffix sums behind the rotation keep one checkpoint per 64 runs: run counts around the multiples of 64 with
+    every cut position, and the branch-free score, against the oracle port."""
+    ll = ctypes.c_longlong
+    harness.smx_test_rotate.restype = ll
+    harness.smx_test_rotate.argtypes = [ctypes.POINTER(ctypes.c_uint32), ll, ll, ll, ll, ctypes.c_int, ctypes.POINTER(ll)]
+    harness.smx_test_score.restype = ll
+    harness.smx_test_score.argtypes = [ctypes.POINTER(ctypes.c_uint32), ll, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    rng = np.random.default_rng(12)
+    for n_runs in (1, 2, 63, 64, 65, 127, 128, 129, 191, 192, 193, 300):
+        ops = "=X=I=D=X"
+        cig = "".join(ops[k % len(ops)] * int(rng.integers(1, 4)) for k in range(n_runs))
+        if n_runs > 2:
+            cig = "HH" + "S" + cig[3:] if cig[3:] else cig
+        enc = encode(cig)
+        n_r = sum(cig.count(x) for x in "=XDH"); n_q = sum(cig.count(x) for x in "=XIS")
+        for sc in ((3, 1, 1, -2), (5, 2, 2, -3)):
+            got = harness.smx_test_score(np.asarray(enc, np.uint32).ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(enc), *sc)
+            assert got == port.cigar_score(cig, port.Scoring(go=sc[0], ge=sc[1], ma=sc[2], mi=sc[3]))
+        for ref_off in sorted(set([0, 1, n_r // 3, n_r // 2, max(n_r - 1, 0), n_r] + [int(x) for x in rng.integers(0, n_r + 1, size=6)])):
+            q_off = int(rng.integers(0, n_q + 1))
+            runs = np.zeros(len(enc) + 4, np.uint32)
+            runs[:len(enc)] = enc
+            off = ll(0)
+            n = harness.smx_test_rotate(runs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), len(enc), len(runs), ref_off, q_off, 0, ctypes.byref(off))
+            want_cig, want_off = port.rotate_to_ref0(cig, ref_off, q_off)
+            assert decode(runs[:n]) == want_cig and int(off.value) == want_off, (n_runs, ref_off, q_off)
