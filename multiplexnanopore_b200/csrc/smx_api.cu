@@ -20,6 +20,7 @@
 #include "smx_dp16h.cuh"
 #include "smx_scan.cuh"
 #include "smx_traceback.cuh"
+#include "smx_traceback_ck.cuh"
 #include "smx_outputs.cuh"
 #include "smx_msa.cuh"
 
@@ -40,8 +41,10 @@ struct PinBuf {
 struct Chunk {
     int first = 0, count = 0;            // range in the size-sorted order
     int n_big = 0;                       // traceback: the first n_big problems of the chunk's order_all range get a warp each
+    int n_ck = 0;                        // the last n_ck problems of that range are checkpointed (smx_traceback_ck)
     int cls_first[14] = {0}, cls_count[14] = {0};  // per kernel class ranges inside order_cls (see problem_class)
     int cls_local[14] = {0};             // packed classes: how many problems at the END of the class range are local (sw_trace)
+    int cls_ck[14] = {0};                // packed classes: how many problems before the local ones are checkpointed (SMX_MODE_CKPT)
     size_t trace_bytes = 0;
 };
 
@@ -101,6 +104,10 @@ struct smx_handle {
     int64_t total_runs = -1;
     DevBuf d_probs, d_order_cls, d_order_all, d_results, d_trace, d_boundary, d_runs, d_dense, d_dense_off, d_tickets, d_slots;
     int split_last = 1;  // SMX_S16H_SPLIT=0: lone last bands at K = 8 (cross-check)
+    // checkpointed traceback (smx_traceback_ck.cuh) for packed global / semi-global problems of at least this size;
+    // SMX_CKPT=0 switches it off, SMX_CKPT_MINROWS / SMX_CKPT_MINCOLS move the thresholds (rows > 512)
+    bool ckpt = true;
+    int ck_min_rows = 1025, ck_min_cols = 1500;
     DevBuf d_compact, d_expand_items, d_comp;  // pipeline pool: sequences as given, expansion list, complement table
     std::vector<SmxResult> h_results;
     std::vector<int64_t> h_dense_off;
@@ -509,6 +516,9 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         if (const char *tm = getenv("SMX_TEAM_MIN_MCELLS")) h->team_min_cells = (int64_t)atol(tm) << 20;
         { const char *pe = getenv("SMX_PERSISTENT"); h->persistent_fwd = pe && pe[0] == '1'; }
         { const char *se = getenv("SMX_S16H_SPLIT"); h->split_last = !(se && se[0] == '0'); }
+        { const char *ce = getenv("SMX_CKPT"); h->ckpt = !(ce && ce[0] == '0'); }
+        if (const char *e = getenv("SMX_CKPT_MINROWS")) { const int v = atoi(e); if (v > 512) h->ck_min_rows = v; }
+        if (const char *e = getenv("SMX_CKPT_MINCOLS")) { const int v = atoi(e); if (v >= 1) h->ck_min_cols = v; }
         const char *envh = getenv("SMX_S16H");
         h->use_s16h = !(envh && envh[0] == '0') && s16h_scoring_ok(h->sc);
         const char *mw = getenv("SMX_S16_MAXW");
@@ -582,6 +592,14 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
                 }
         }
     }
+    // checkpointed traceback for the large packed problems: the forward pass runs score-only (1.7x faster) and the walk
+    // recomputes the direction bits of the blocks it crosses (~15 % of the cells of a 2 500 x 4 000 problem); pays from
+    // about 1 500 columns on (the recomputed share of a band pair is ~600 of its n + 95 steps)
+    if (h->ckpt && h->use_s16 && h->use_s16h)
+        for (int p = 0; p < n; ++p) {
+            SmxProblem &q = h->probs[(size_t)p];
+            if (q.cls >= kClsS16 && (q.mode & SMX_MODE_MASK) != SMX_MODE_SW && q.m >= h->ck_min_rows && q.n >= h->ck_min_cols) q.mode |= SMX_MODE_CKPT;
+        }
     // concurrent teams: the packed forward phase (one-warp launch + team launches side by side) is timed as ONE interval
     for (int p = 0; p < n; ++p) {
         const SmxProblem &q = h->probs[(size_t)p];
@@ -603,8 +621,10 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
             if (cls < 6) continue;  // K <= 4 rows per lane: tiny problems
             std::stable_sort(order.begin() + cnt[c], order.begin() + cnt[c + 1], [&](int32_t x, int32_t y) {
                 // packed classes: the local problems form the tail of the class range (they run a kernel of their own)
-                const bool lx = cls >= kClsS16 && (h->probs[x].mode & SMX_MODE_MASK) == SMX_MODE_SW, ly = cls >= kClsS16 && (h->probs[y].mode & SMX_MODE_MASK) == SMX_MODE_SW;
-                if (lx != ly) return ly;
+                // and before them the checkpointed ones: [direction bits][checkpointed][local]
+                const int lx = cls < kClsS16 ? 0 : (h->probs[x].mode & SMX_MODE_MASK) == SMX_MODE_SW ? 2 : (h->probs[x].mode & SMX_MODE_CKPT) ? 1 : 0;
+                const int ly = cls < kClsS16 ? 0 : (h->probs[y].mode & SMX_MODE_MASK) == SMX_MODE_SW ? 2 : (h->probs[y].mode & SMX_MODE_CKPT) ? 1 : 0;
+                if (lx != ly) return lx < ly;
                 return (int64_t)h->probs[x].m * h->probs[x].n > (int64_t)h->probs[y].m * h->probs[y].n;
             });
         }
@@ -618,10 +638,10 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         Chunk c;
         c.first = pos;
         size_t bytes = 0;
-        for (int cls = 0; cls < kNumFwdClasses; ++cls) { c.cls_first[cls] = pos; c.cls_count[cls] = 0; c.cls_local[cls] = 0; }
+        for (int cls = 0; cls < kNumFwdClasses; ++cls) { c.cls_first[cls] = pos; c.cls_count[cls] = 0; c.cls_local[cls] = 0; c.cls_ck[cls] = 0; }
         while (pos < n) {
             SmxProblem &q = h->probs[(size_t)order[pos]];
-            size_t tb = (size_t)smx_trace_bytes(q.m, q.n, 1 << q.kshift);
+            size_t tb = (size_t)smx_region_bytes(q.m, q.n, 1 << q.kshift, q.mode);
             tb = ((tb + 255) & ~(size_t)255) + (h->guard ? 512 : 0);
             if (c.count > 0 && bytes + tb > (size_t)h->trace_budget) break;
             q.trace_off = (int64_t)bytes + (h->guard ? 256 : 0);
@@ -629,6 +649,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
             if (c.cls_count[q.cls] == 0) c.cls_first[q.cls] = pos;
             ++c.cls_count[q.cls];
             if (q.cls >= kClsS16 && (q.mode & SMX_MODE_MASK) == SMX_MODE_SW) ++c.cls_local[q.cls];
+            if (q.mode & SMX_MODE_CKPT) ++c.cls_ck[q.cls];
             ++c.count; ++pos;
         }
         c.trace_bytes = bytes;
@@ -636,7 +657,10 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         // traceback order of the chunk: long walks first (one warp each, see smx_traceback), the rest one thread each
         {
             auto big = [&](int32_t p) { return h->probs[(size_t)p].m + h->probs[(size_t)p].n >= kTbBigWalk; };
-            auto mid = std::stable_partition(h->order_all.begin() + c.first, h->order_all.begin() + c.first + c.count, big);
+            auto plain = [&](int32_t p) { return !(h->probs[(size_t)p].mode & SMX_MODE_CKPT); };
+            auto ck0 = std::stable_partition(h->order_all.begin() + c.first, h->order_all.begin() + c.first + c.count, plain);
+            c.n_ck = (int)((h->order_all.begin() + c.first + c.count) - ck0);
+            auto mid = std::stable_partition(h->order_all.begin() + c.first, ck0, big);
             c.n_big = (int)(mid - (h->order_all.begin() + c.first));
         }
         h->chunks.push_back(c);
@@ -649,7 +673,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
     if (int rc = ensure(h, h->d_trace, h->max_chunk_trace + 256)) return rc;
     if (int rc = ensure(h, h->d_runs, sizeof(uint32_t) * (size_t)h->runs_scratch)) return rc;
     if (int rc = ensure(h, h->d_dense_off, sizeof(int64_t) * ((size_t)n + 1))) return rc;
-    if (int rc = ensure(h, h->d_tickets, sizeof(int32_t) * 2 * kNumFwdClasses * h->chunks.size())) return rc;
+    if (int rc = ensure(h, h->d_tickets, sizeof(int32_t) * 3 * kNumFwdClasses * h->chunks.size())) return rc;
     if (int rc = h2d(h, PIN_PROBS, h->d_probs.p, h->probs.data(), sizeof(SmxProblem) * (size_t)n, h->stream_hi)) return rc;
     if (int rc = h2d(h, PIN_ORDER_CLS, h->d_order_cls.p, h->order_cls.data(), sizeof(int32_t) * (size_t)n, h->stream_hi)) return rc;
     if (int rc = h2d(h, PIN_ORDER_ALL, h->d_order_all.p, h->order_all.data(), sizeof(int32_t) * (size_t)n, h->stream_hi)) return rc;
@@ -708,7 +732,7 @@ static int launch_forward(smx_handle *h, const Chunk &c, int cls, int chunk_idx)
     a.probs = (const SmxProblem *)h->d_probs.p;
     a.order = (const int32_t *)h->d_order_cls.p + c.cls_first[cls];
     a.n_order = count;
-    a.ticket = (int32_t *)h->d_tickets.p + (size_t)chunk_idx * 2 * kNumFwdClasses + cls;
+    a.ticket = (int32_t *)h->d_tickets.p + (size_t)chunk_idx * 3 * kNumFwdClasses + cls;
     a.trace = (uint8_t *)h->d_trace.p;
     a.boundary = (int2 *)h->d_boundary.p;
     a.nmax = h->nmax;
@@ -730,12 +754,15 @@ static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_id
     if (!stream) stream = h->stream;
     const bool TEAM = W > 1;
     const int threads = TEAM ? W * 32 : (h->use_s16h ? 32 * SMX16H_WPC : 128);
-    // the global / semi-global problems of the class, then its local problems (tail of the class range, own kernel)
-    for (int local = 0; local < 2; ++local) {
-        const int count = local ? c.cls_local[cls] : c.cls_count[cls] - c.cls_local[cls];
+    // the global / semi-global problems of the class that keep direction bits, then its checkpointed and its local problems
+    // (middle and tail of the class range, kernels of their own)
+    for (int sub = 0; sub < 3; ++sub) {
+        const bool local = sub == 2, ck = sub == 1;
+        const int n_plain = c.cls_count[cls] - c.cls_local[cls] - c.cls_ck[cls];
+        const int count = local ? c.cls_local[cls] : ck ? c.cls_ck[cls] : n_plain;
         if (count == 0) continue;
         int occ = 0;
-        void (*kern)(const SmxFwdArgs) = !h->use_s16h ? smx_dp_forward16<W> : local ? smx_dp_forward16h<W, true> : smx_dp_forward16h<W, false>;
+        void (*kern)(const SmxFwdArgs) = !h->use_s16h ? smx_dp_forward16<W> : local ? smx_dp_forward16h<W, true, false> : ck ? smx_dp_forward16h<W, false, true> : smx_dp_forward16h<W, false, false>;
         SMX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
         if (occ < 1) occ = 1;
         const int per_block = TEAM ? 1 : threads / 32;
@@ -749,9 +776,9 @@ static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_id
         SmxFwdArgs a;
         a.pool = (const uint8_t *)h->pool.p;
         a.probs = (const SmxProblem *)h->d_probs.p;
-        a.order = (const int32_t *)h->d_order_cls.p + c.cls_first[cls] + (local ? c.cls_count[cls] - c.cls_local[cls] : 0);
+        a.order = (const int32_t *)h->d_order_cls.p + c.cls_first[cls] + (local ? c.cls_count[cls] - c.cls_local[cls] : ck ? n_plain : 0);
         a.n_order = count;
-        a.ticket = (int32_t *)h->d_tickets.p + ((size_t)chunk_idx * 2 + local) * kNumFwdClasses + cls;
+        a.ticket = (int32_t *)h->d_tickets.p + ((size_t)chunk_idx * 3 + sub) * kNumFwdClasses + cls;
         a.trace = (uint8_t *)h->d_trace.p;
         a.boundary = (int2 *)h->d_boundary.p;
         a.nmax = h->nmax;
@@ -760,7 +787,7 @@ static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_id
         a.one = 1u;
         a.max_tickets = persistent ? INT32_MAX : 1;
         a.n_slots = kLineSlots;
-        a.slot_flags = persistent ? nullptr : (int32_t *)h->d_slots.p;
+        a.slot_flags = persistent || ck ? nullptr : (int32_t *)h->d_slots.p;  // checkpointed problems write lines of their own
         a.split_last = h->split_last;
         kern<<<blocks, threads, 0, stream>>>(a);
         SMX_CUDA(h, cudaGetLastError());
@@ -775,7 +802,7 @@ __global__ void __launch_bounds__(128) smx_guard_check(const SmxProblem *probs, 
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n) return;
     const SmxProblem pr = probs[order[w]];
-    const int64_t bytes = (smx_trace_bytes(pr.m, pr.n, 1 << pr.kshift) + 255) & ~(int64_t)255;
+    const int64_t bytes = (smx_region_bytes(pr.m, pr.n, 1 << pr.kshift, pr.mode) + 255) & ~(int64_t)255;
     const uint32_t *before = reinterpret_cast<const uint32_t *>(trace + pr.trace_off - 256);
     const uint32_t *after = reinterpret_cast<const uint32_t *>(trace + pr.trace_off + bytes);
     int bad = 0;
@@ -811,7 +838,7 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
     } guard{gate};
     if (gate) gate->enter();
     SMX_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    SMX_CUDA(h, cudaMemsetAsync(h->d_tickets.p, 0, sizeof(int32_t) * 2 * kNumFwdClasses * h->chunks.size(), h->stream));
+    SMX_CUDA(h, cudaMemsetAsync(h->d_tickets.p, 0, sizeof(int32_t) * 3 * kNumFwdClasses * h->chunks.size(), h->stream));
     SMX_CUDA(h, cudaMemsetAsync(h->d_slots.p, 0, sizeof(int32_t) * kLineSlots, h->stream));  // an aborted launch must not leave lines claimed
     h->ev_used = 0;
     for (int c = 0; c < kNumSlots; ++c) { h->kernel_ms[c] = 0.0; h->kernel_launches[c] = 0; }
@@ -862,17 +889,32 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
         t.pool = (const uint8_t *)h->pool.p;
         t.probs = (const SmxProblem *)h->d_probs.p;
         t.order = (const int32_t *)h->d_order_all.p + c.first;
-        t.n_order = c.count;
+        t.n_order = c.count - c.n_ck;
         t.n_big = c.n_big;
         t.trace = (const uint8_t *)h->d_trace.p;
         t.results = (SmxResult *)h->d_results.p;
         t.runs = (uint32_t *)h->d_runs.p;
         t.sc = h->sc;
         t.split_last = h->use_s16h ? h->split_last : 0;
-        const long long tb_threads = 32ll * c.n_big + (c.count - c.n_big);
-        smx_traceback<<<(unsigned)((tb_threads + 127) / 128), 128, 0, h->stream>>>(t);
-        SMX_CUDA(h, cudaGetLastError());
-        h->last_launches++;
+        const long long tb_threads = 32ll * c.n_big + (c.count - c.n_ck - c.n_big);
+        if (tb_threads > 0) {
+            smx_traceback<<<(unsigned)((tb_threads + 127) / 128), 128, 0, h->stream>>>(t);
+            SMX_CUDA(h, cudaGetLastError());
+            h->last_launches++;
+        }
+        if (c.n_ck > 0) {
+            SmxTbCkArgs k;
+            k.pool = t.pool; k.probs = t.probs; k.trace = t.trace; k.results = t.results; k.runs = t.runs; k.sc = t.sc; k.split_last = t.split_last;
+            k.order = (const int32_t *)h->d_order_all.p + c.first + (c.count - c.n_ck);
+            k.n_order = c.n_ck;
+            k.one = 1u;
+            const size_t smem = sizeof(uint32_t) * SMX_TBCK_WARPS * SMX_TBCK_TILE_WORDS;
+            static std::once_flag once[16];
+            std::call_once(once[h->device & 15], [&] { cudaFuncSetAttribute(smx_traceback_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+            smx_traceback_ck<<<(unsigned)((c.n_ck + SMX_TBCK_WARPS - 1) / SMX_TBCK_WARPS), 32 * SMX_TBCK_WARPS, smem, h->stream>>>(k);
+            SMX_CUDA(h, cudaGetLastError());
+            h->last_launches++;
+        }
         if (int rc2 = mark(h, kSlotTraceback)) return rc2;
         if (h->guard) {
             smx_guard_check<<<(c.count + 3) / 4, 128, 0, h->stream>>>((const SmxProblem *)h->d_probs.p, (const int32_t *)h->d_order_all.p + c.first, c.count,

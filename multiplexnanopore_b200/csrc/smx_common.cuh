@@ -29,6 +29,7 @@ struct SmxResult {
 
 #define SMX_MODE_MASK 0xff
 #define SMX_MODE_CLIP 0x100  // semi-global problem whose CIGAR is re-clipped on the device (MyResult.set_soft_clipping)
+#define SMX_MODE_CKPT 0x200  // packed problem whose forward pass keeps checkpoints instead of direction bits (smx_traceback_ck.cuh)
 
 struct SmxScoring {
     int32_t go, ge, match, mismatch;

@@ -32,6 +32,34 @@ __host__ __device__ inline int64_t smx_trace_bytes(int m, int n, int K)
     return bands * (int64_t)(n + 31) * 32 * w;
 }
 
+// Checkpointed problems (SMX_MODE_CKPT, smx_dp16h.cuh / smx_traceback_ck.cuh): instead of direction bits the problem's
+// region of the arena holds the bottom line of every band (one uint32 = F^ << 16 | Hc per column) and, for every band
+// pair, the lane state at the top of every SMX_CK_CHUNKS-th 32-step chunk; the traceback recomputes the direction bits
+// of the 64-step blocks its path crosses.
+#define SMX_CK_CHUNKS 2   // 32-step chunks between two checkpoints = the block the traceback recomputes at a time
+#define SMX_CK_WORDS 22   // words per lane of a checkpoint: Hc[8], El[8], hd, out_h, out_f, sel_prev, rch1, rch2
+struct SmxCkLayout {
+    int32_t nbands, npairs, nal, nchunks, nck;
+    int64_t ck_off, bytes;
+};
+__host__ __device__ inline SmxCkLayout smx_ck_layout(int m, int n)
+{
+    SmxCkLayout l;
+    l.nbands = (m + 255) / 256;
+    l.npairs = (l.nbands + 1) / 2;
+    l.nal = (n + 31) & ~31;
+    l.nchunks = (n + 31 + 64 + 31) >> 5;  // steps of a band pair: n + 31 + the 64-step lag of its high band
+    l.nck = (l.nchunks + SMX_CK_CHUNKS - 1) / SMX_CK_CHUNKS;
+    l.ck_off = (int64_t)l.nbands * l.nal * 4;
+    l.bytes = l.ck_off + (int64_t)l.npairs * l.nck * SMX_CK_WORDS * 128;
+    return l;
+}
+// bytes of a problem's region of the arena
+__host__ __device__ inline int64_t smx_region_bytes(int m, int n, int K, int mode)
+{
+    return (mode & SMX_MODE_CKPT) ? smx_ck_layout(m, n).bytes : smx_trace_bytes(m, n, K);
+}
+
 // per-row substitution profile: byte c = score(query base, reference code c), c = 0..3; code 4 -> 0
 __device__ __forceinline__ uint32_t smx_profile(int qcode, int match, int mismatch)
 {

@@ -121,7 +121,15 @@ __device__ __forceinline__ uint32_t smx16h_merge(uint32_t nv, uint32_t ov, uint3
     return r;
 }
 
-template <int K, int k, bool EDGE = false, bool LOCAL = false>
+__device__ __forceinline__ uint32_t smx16h_max(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+
+// NOTR: score only (checkpointed problems, SMX_MODE_CKPT): the four maxima without their direction flags
+template <int K, int k, bool EDGE = false, bool LOCAL = false, bool NOTR = false>
 struct Smx16hCell {
     static __device__ __forceinline__ void run(uint32_t (&Hc)[K], uint32_t (&El)[K], const uint32_t (&plo)[K], const uint32_t (&phi)[K],
                                                Smx16hCol &c, uint32_t sel, uint32_t negc2, uint32_t hold = 0xffffffffu)
@@ -130,11 +138,18 @@ struct Smx16hCell {
         constexpr int SH = 4 * (k & 7);
         uint32_t &n_lo = c.w_lo[A];
         uint32_t &n_hi = c.w_hi[A];
-        const uint32_t e = smx16h_max_tr<(4u << SH), (SMX16H_ALU_FLAGS < 1)>(El[k], Hc[k], n_lo, n_hi, c.one);   // extend | open
-        const uint32_t f = smx16h_max_tr<(8u << SH), (SMX16H_ALU_FLAGS < 3)>(c.fu, c.hcu, n_lo, n_hi, c.one);
         const uint32_t hdiag = c.hd + smx_subst_u(plo[k], phi[k], sel);  // no carry between the halves: s'' >= 0, no wrap
-        const uint32_t t = smx16h_max_tr<(2u << SH), (SMX16H_ALU_FLAGS < 2)>(f, e, n_lo, n_hi, c.one);
-        uint32_t h = smx16h_max_tr<(1u << SH), (SMX16H_ALU_FLAGS < 4)>(hdiag, t, n_lo, n_hi, c.one);
+        uint32_t e, f, h;
+        if (NOTR) {
+            e = smx16h_max(El[k], Hc[k]);
+            f = smx16h_max(c.fu, c.hcu);
+            h = smx16h_max(hdiag, smx16h_max(f, e));
+        } else {
+            e = smx16h_max_tr<(4u << SH), (SMX16H_ALU_FLAGS < 1)>(El[k], Hc[k], n_lo, n_hi, c.one);   // extend | open
+            f = smx16h_max_tr<(8u << SH), (SMX16H_ALU_FLAGS < 3)>(c.fu, c.hcu, n_lo, n_hi, c.one);
+            const uint32_t t = smx16h_max_tr<(2u << SH), (SMX16H_ALU_FLAGS < 2)>(f, e, n_lo, n_hi, c.one);
+            h = smx16h_max_tr<(1u << SH), (SMX16H_ALU_FLAGS < 4)>(hdiag, t, n_lo, n_hi, c.one);
+        }
         if (LOCAL) {
             asm("max.u16x2 %0, %0, %1;" : "+r"(h) : "r"(c.z));            // H = max(H, 0)
             const uint32_t u = EDGE ? ((h - c.z) & hold) : (h - c.z);     // H itself (>= 0 in both halves: no borrow); a held half does not count
@@ -147,11 +162,11 @@ struct Smx16hCell {
         El[k] = EDGE ? smx16h_merge(e, El[k], hold) : e;
         c.fu = f;
         c.hcu = hc;
-        Smx16hCell<K, k + 1, EDGE, LOCAL>::run(Hc, El, plo, phi, c, sel, negc2, hold);
+        Smx16hCell<K, k + 1, EDGE, LOCAL, NOTR>::run(Hc, El, plo, phi, c, sel, negc2, hold);
     }
 };
-template <int K, bool EDGE, bool LOCAL>
-struct Smx16hCell<K, K, EDGE, LOCAL> {
+template <int K, bool EDGE, bool LOCAL, bool NOTR>
+struct Smx16hCell<K, K, EDGE, LOCAL, NOTR> {
     static __device__ __forceinline__ void run(uint32_t (&)[K], uint32_t (&)[K], const uint32_t (&)[K], const uint32_t (&)[K], Smx16hCol &, uint32_t,
                                                uint32_t, uint32_t = 0) {}
 };
@@ -175,7 +190,7 @@ __device__ __forceinline__ int smx16h_hi(uint32_t v) { return (int)(v >> 16); }
 // stored half of the last query row back into H (semi-global end in the last row): H = half - ge * j + tconst.
 // SPLIT (K = 4, see the kernel): the lane's 4 nibbles per half are one 16-bit word; tp_lo / tp_hi point at the lane's
 // word of step s0 in the half-band's [step][lane] region and advance by one 64-byte line per step.
-template <int K, bool HAS_HI, bool TRACK, bool SPLIT, bool LOCAL = false>
+template <int K, bool HAS_HI, bool TRACK, bool SPLIT, bool LOCAL = false, bool NOTR = false>
 __device__ __forceinline__ void smx16h_fast_chunk(uint32_t (&Hc)[K], uint32_t (&El)[K], const uint32_t (&plo)[K], const uint32_t (&phi)[K],
                                                   uint32_t &hd, uint32_t &out_h, uint32_t &out_f, uint32_t &sel_prev, const uint4 *tops,
                                                   uint32_t lane0_mask, uint32_t negc2, uint32_t *tp_lo, uint32_t *tp_hi, uint32_t *bl, uint32_t *bh,
@@ -195,12 +210,13 @@ __device__ __forceinline__ void smx16h_fast_chunk(uint32_t (&Hc)[K], uint32_t (&
         Smx16hCol c;
         c.hd = hd; c.fu = fu; c.hcu = hu; c.w_lo[0] = 0; c.w_lo[1] = 0; c.w_hi[0] = 0; c.w_hi[1] = 0; c.one = one;
         if (LOCAL) { c.z = L->zs; c.ge2 = L->ge2; c.m = L->lbest; }
-        Smx16hCell<K, 0, false, LOCAL>::run(Hc, El, plo, phi, c, sel, negc2);
+        Smx16hCell<K, 0, false, LOCAL, NOTR>::run(Hc, El, plo, phi, c, sel, negc2);
         if (LOCAL) smx16h_local_step<K>(*L, Hc, HAS_HI ? c.m : ((c.m & 0xffffu) | (L->lbest & 0xffff0000u)), s0 + ss, lane);
         hd = hu;
         out_h = c.hcu;
         out_f = c.fu;
-        if (SPLIT) {
+        if (NOTR) {
+        } else if (SPLIT) {
             reinterpret_cast<unsigned short *>(tp_lo)[ss * 32] = (unsigned short)c.w_lo[0];
             if (HAS_HI) reinterpret_cast<unsigned short *>(tp_hi)[ss * 32] = (unsigned short)c.w_hi[0];
         } else {
@@ -230,7 +246,7 @@ __device__ __forceinline__ void smx16h_fast_chunk(uint32_t (&Hc)[K], uint32_t (&
 // One 32-step chunk at an edge of the matrix (see Smx16hCell<EDGE>): the interior chunk plus the hold masks, per-lane
 // predicates on the direction-word and boundary-line stores, and validity on the last-row tracking.  `jl0` = column
 // of this lane's low half at the first step of the chunk (the high half is LAG columns behind).
-template <int K, bool HAS_HI, bool SPLIT, bool LOCAL = false>
+template <int K, bool HAS_HI, bool SPLIT, bool LOCAL = false, bool NOTR = false>
 __device__ __forceinline__ void smx16h_edge_chunk(uint32_t (&Hc)[K], uint32_t (&El)[K], const uint32_t (&plo)[K], const uint32_t (&phi)[K],
                                                   uint32_t &hd, uint32_t &out_h, uint32_t &out_f, uint32_t &sel_prev, const uint4 *tops,
                                                   uint32_t lane0_mask, uint32_t negc2, uint32_t *tp_lo, uint32_t *tp_hi, uint32_t *bl, uint32_t *bh,
@@ -254,12 +270,13 @@ __device__ __forceinline__ void smx16h_edge_chunk(uint32_t (&Hc)[K], uint32_t (&
         Smx16hCol c;
         c.hd = hd; c.fu = fu; c.hcu = hu; c.w_lo[0] = 0; c.w_lo[1] = 0; c.w_hi[0] = 0; c.w_hi[1] = 0; c.one = one;
         if (LOCAL) { c.z = L->zs; c.ge2 = L->ge2; c.m = L->lbest; }
-        Smx16hCell<K, 0, true, LOCAL>::run(Hc, El, plo, phi, c, sel, negc2, hold);
+        Smx16hCell<K, 0, true, LOCAL, NOTR>::run(Hc, El, plo, phi, c, sel, negc2, hold);
         if (LOCAL) smx16h_local_step<K>(*L, Hc, c.m, s0 + ss, lane);
         hd = smx16h_merge(hu, hd, hold);
         out_h = c.hcu;
         out_f = c.fu;
-        if (SPLIT) {
+        if (NOTR) {
+        } else if (SPLIT) {
             if (v_lo) reinterpret_cast<unsigned short *>(tp_lo)[ss * 32] = (unsigned short)c.w_lo[0];
             if (v_hi) reinterpret_cast<unsigned short *>(tp_hi)[ss * 32] = (unsigned short)c.w_hi[0];
         } else {
@@ -283,9 +300,12 @@ __device__ __forceinline__ void smx16h_edge_chunk(uint32_t (&Hc)[K], uint32_t (&
 }
 
 // boundary lines: one uint32 per column = F^ << 16 | Hc (biased unsigned halves)
-template <int W, bool LOCAL = false>
+// CK: the problems carry SMX_MODE_CKPT -- score-only cells, every band's bottom line and the pair checkpoints go to the
+// problem's region of the arena (smx_ck_layout) instead of direction bits; no claimed boundary lines.
+template <int W, bool LOCAL = false, bool CK = false>
 __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_WARPS_PER_SM / (W == 1 ? SMX16H_WPC : W)) smx_dp_forward16h(const SmxFwdArgs a)
 {
+    static_assert(!(LOCAL && CK), "local problems keep their direction bits");
     constexpr bool TEAM = W > 1;
     constexpr bool SPLIT_OK = W == 1;  // the K = 4 code for a lone last band exists in the one-warp-per-problem kernel only
     constexpr int LAG = SMX16_LAG;
@@ -347,6 +367,9 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_W
         const uint8_t *s1 = a.pool + pr.s1_off;
         const uint8_t *s2 = a.pool + pr.s2_off;
         uint32_t *trace = reinterpret_cast<uint32_t *>(a.trace + pr.trace_off);
+        const SmxCkLayout ckl = smx_ck_layout(m, n);
+        uint32_t *const ck_lines = trace;                    // CK: [band][nal] bottom lines
+        uint32_t *const ck_state = trace + (ckl.ck_off >> 2);  // CK: [pair][checkpoint][word][lane]
         const int nbands = (m + 255) / 256;       // bands of the trace layout: 32 lanes x 8 rows
         const int npairs = (nbands + 1) >> 1;
         const int steps = n + 31;          // steps of one band (trace layout)
@@ -379,10 +402,12 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_W
             const bool has_hi = SPLIT ? split_hi : band_hi < nbands;
             const int i0_lo = SPLIT ? R0 + lane * K : band_lo * 32 * K + lane * K;
             const int i0_hi = SPLIT ? R0 + 128 + lane * K : band_hi * 32 * K + lane * K;
-            const uint32_t *top_lo = line0;  // band_lo is even: reads line0, writes line1; band_hi the other way round
-            uint32_t *bot_lo = line1;
-            const uint32_t *top_hi = line1;
-            uint32_t *bot_hi = line0;
+            // band_lo is even: reads line0, writes line1; band_hi the other way round.  CK: band b writes line b of the problem's
+            // own lines (a split last band: its lower half-band writes the otherwise unused line of the last band)
+            const uint32_t *top_lo = CK ? ck_lines + (long long)(band_lo > 0 ? band_lo - 1 : 0) * ckl.nal : line0;
+            uint32_t *bot_lo = CK ? ck_lines + (long long)band_lo * ckl.nal : line1;
+            const uint32_t *top_hi = CK ? ck_lines + (long long)band_lo * ckl.nal : line1;
+            uint32_t *bot_hi = CK ? ck_lines + (long long)band_hi * ckl.nal : line0;
             const bool lo_is_last = SPLIT ? !has_hi : band_lo == last_band_idx, hi_is_last = SPLIT ? has_hi : band_hi == last_band_idx;
             // SPLIT: the last band's region of the arena ([step][lane] 32-bit words at K = 8) holds two half-band regions of
             // 16-bit words instead, [half-band][step][lane]: the K = 4 layout of smx_traceback, every warp store one
@@ -425,6 +450,13 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_W
                     __threadfence_block();
                 }
                 __syncwarp();
+                if (CK && (chunk % SMX_CK_CHUNKS) == 0) {  // checkpoint: the loop-carried lane state at the top of this chunk
+                    uint32_t *cp = ck_state + ((long long)pair * ckl.nck + chunk / SMX_CK_CHUNKS) * (SMX_CK_WORDS * 32) + lane;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { cp[k * 32] = Hc[k]; cp[(8 + k) * 32] = El[k]; }
+                    cp[16 * 32] = hd; cp[17 * 32] = out_h; cp[18 * 32] = out_f; cp[19 * 32] = sel_prev;
+                    cp[20 * 32] = (uint32_t)rch1; cp[21 * 32] = (uint32_t)rch2;
+                }
                 // chunk prefetch: lane l holds column s0 + l (low band inputs) and column s0 + l - LAG (high band top line)
                 const int jc = s0 + lane;
                 const int jb = jc - LAG;
@@ -457,11 +489,11 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_W
                         const int jbase = s0 - lane - (track_lo ? 0 : LAG);
                         const uint32_t tmask = lane == last_lane ? (track_lo ? 0x0000ffffu : 0xffff0000u) : 0u;
                         const int tconst = hconst - ge * (m - 1);
-                        if (has_hi) smx16h_fast_chunk<K, true, true, SPLIT, LOCAL>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, ge, tconst, row_best, row_best_j, one, &L, s0, lane);
-                        else smx16h_fast_chunk<K, false, true, SPLIT, LOCAL>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, ge, tconst, row_best, row_best_j, one, &L, s0, lane);
+                        if (has_hi) smx16h_fast_chunk<K, true, true, SPLIT, LOCAL, CK>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, ge, tconst, row_best, row_best_j, one, &L, s0, lane);
+                        else smx16h_fast_chunk<K, false, true, SPLIT, LOCAL, CK>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, jbase, ge, tconst, row_best, row_best_j, one, &L, s0, lane);
                     } else {
-                        if (has_hi) smx16h_fast_chunk<K, true, false, SPLIT, LOCAL>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one, &L, s0, lane);
-                        else smx16h_fast_chunk<K, false, false, SPLIT, LOCAL>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one, &L, s0, lane);
+                        if (has_hi) smx16h_fast_chunk<K, true, false, SPLIT, LOCAL, CK>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one, &L, s0, lane);
+                        else smx16h_fast_chunk<K, false, false, SPLIT, LOCAL, CK>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, 0u, 0, 0, 0, 0, row_best, row_best_j, one, &L, s0, lane);
                     }
                 } else {
                     // edge chunk: halves outside the matrix hold their state (smx16h_edge_chunk)
@@ -472,8 +504,8 @@ __global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_W
                     const uint32_t st_flags = (st_lo ? 1u : 0u) | (st_hi ? 2u : 0u);
                     const uint32_t tmask = (track_lo | track_hi) && lane == last_lane ? (track_lo ? 0x0000ffffu : 0xffff0000u) : 0u;
                     const int tconst = hconst - ge * (m - 1);
-                    if (has_hi) smx16h_edge_chunk<K, true, SPLIT, LOCAL>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, s0 - lane, n, ge, tconst, row_best, row_best_j, one, &L, s0, lane);
-                    else smx16h_edge_chunk<K, false, SPLIT, LOCAL>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, s0 - lane, n, ge, tconst, row_best, row_best_j, one, &L, s0, lane);
+                    if (has_hi) smx16h_edge_chunk<K, true, SPLIT, LOCAL, CK>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, s0 - lane, n, ge, tconst, row_best, row_best_j, one, &L, s0, lane);
+                    else smx16h_edge_chunk<K, false, SPLIT, LOCAL, CK>(Hc, El, plo, phi, hd, out_h, out_f, sel_prev, s_top[wib], lane0_mask, negc2, tp_lo, tp_hi, bl, bh, st_flags, tmask, last_k, s0 - lane, n, ge, tconst, row_best, row_best_j, one, &L, s0, lane);
                 }
                 rch2 = rch1;
                 rch1 = rch0;

@@ -156,3 +156,57 @@ def test_guard_bands_around_direction_bits(engine):
         finally:
             engine.set_trace_budget(16 << 30)
         assert engine.guard_errors == 0
+
+
+def _ck_problems(rng, shapes, modes=(0, 1, 2), low=False):
+    probs, ms = [], []
+    for m, n in shapes:
+        if low:
+            unit = util.rand_seq(rng, int(rng.integers(1, 4)))
+            ref = (unit * (n // len(unit) + 1))[:n]
+        else:
+            ref = util.rand_seq(rng, n)
+        q = util.mutate(rng, (ref * (m // n + 2))[:m + 40], 0.06, 0.04, 0.04)
+        q = (q * (m // max(1, len(q)) + 1))[:m]
+        for mode in modes:
+            probs.append((q, ref)); ms.append(mode)
+    return probs, ms
+
+
+@pytest.mark.parametrize("env", [dict(), dict(SMX_S16H_SPLIT="0"), dict(SMX_TEAM2_MCELLS="0.5", SMX_TEAM4_MCELLS="1.2", SMX_TEAM8_MCELLS="2.0"),
+                                 dict(SMX_GUARD="1")])
+def test_checkpointed_traceback_shapes(engine, env):
+    """Large packed problems keep checkpoints instead of direction bits (SMX_MODE_CKPT, smx_traceback_ck.cuh): with the
+    thresholds lowered to 513 rows x 1 column every shape goes through that path -- odd and even band counts (split last
+    bands with one and two half-bands), references shorter than a chunk, than the 64-step lag and than a block, team
+    widths, tie-heavy low-complexity pairs -- and must give the oracle's score, end cell and CIGAR."""
+    rng = np.random.default_rng(131)
+    shapes = [(m, n) for m in (513, 640, 641, 767, 768, 769, 1024, 1025, 1153, 1281, 1537, 2049, 2300) for n in (1, 33, 64, 65, 97, 130, 700, 2100)]
+    probs, modes = _ck_problems(rng, shapes)
+    p2, m2 = _ck_problems(rng, [(700, 900), (1300, 1100), (1700, 300), (2600, 2800)], low=True)
+    probs += p2; modes += m2
+    probs += [(util.rand_seq(rng, 1400), util.rand_seq(rng, 1700)), (util.rand_seq(rng, 900), util.rand_seq(rng, 60))]  # unrelated
+    modes += [0, 1]
+    with _Env(SMX_CKPT_MINROWS="513", SMX_CKPT_MINCOLS="1", **env):
+        run_and_compare(engine, probs, modes, (3, 1, 1, -2))
+        run_and_compare(engine, probs[::7], modes[::7], (5, 2, 2, -3))
+        if "SMX_GUARD" in env:
+            assert engine.guard_errors == 0
+
+
+def test_checkpointed_traceback_default_thresholds(engine):
+    """At the default thresholds (>= 1 025 rows, >= 1 500 columns) next to problems that keep their direction bits; the
+    same problems with SMX_CKPT=0 give the same answer (both are checked against the oracle)."""
+    rng = np.random.default_rng(137)
+    shapes = [(1025, 1500), (1100, 1499), (1024, 3000), (2500, 4000), (3100, 2900), (5200, 6100), (600, 2500), (300, 300), (4000, 1501)]
+    probs, modes = _ck_problems(rng, shapes)
+    probs += util.make_problems(rng, 40, 800)
+    modes += [int(x) for x in rng.integers(0, 4, size=40)]
+    run_and_compare(engine, probs, modes, (3, 1, 1, -2))
+    with _Env(SMX_CKPT="0"):
+        run_and_compare(engine, probs, modes, (3, 1, 1, -2))
+    engine.set_trace_budget(8 << 20)   # several chunks, checkpointed and plain problems in each
+    try:
+        run_and_compare(engine, probs, modes, (3, 1, 1, -2))
+    finally:
+        engine.set_trace_budget(16 << 30)
