@@ -155,7 +155,8 @@ int smx_pipeline_fetch(smx_handle *h, int32_t *score, int32_t *new_query_seq_off
  * gpu_select_ms, gpu_dp_ms, scan_cells, dp_cells, n_dp_problems, n_host_redecisions, n_failed,
  * kernel_launches, n_pair_strands, then out[17..32] = smx_align_kernel_ms ms16 of the DP run,
  * out[33..46] = its cells14, out[47..62] = launches per kernel (same order as ms16), out[63] = select kernel ms,
- * out[64] = chain kernel ms */
+ * out[64] = chain kernel ms, out[65] / out[66] = cells / problems of the packed classes that ran checkpointed
+ * (score-only forward pass, smx_traceback_ck) */
 int smx_pipeline_stats(smx_handle *h, double *out, int32_t n);
 
 /* ---- row N1: the alignment operations of MyAlignerBase as one batch -------------------------

@@ -67,8 +67,8 @@ struct smx_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fwd = nullptr, ev_sync_lo = nullptr, ev_sync_hi = nullptr;
     // the largest problems of a chunk run as teams of 2 / 4 / 8 warps NEXT TO the one-warp-per-problem launch (own low-priority
     // streams, forked and joined by events) so that their critical path does not become the tail of the forward phase
-    cudaStream_t stream_team[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t stream_team[4] = {nullptr, nullptr, nullptr, nullptr};  // 2 / 4 / 8-warp teams; [3]: the checkpointed one-warp launch
+    cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
     bool teams_concurrent = false;
     // SMX_GUARD=1 (debug; compute-sanitizer is closed on the pool): 256 poisoned bytes before and after every problem's
     // direction-bit region, verified after the traceback of every chunk
@@ -85,6 +85,7 @@ struct smx_handle {
     double kernel_ms[16] = {0};
     int kernel_launches[16] = {0};
     int64_t class_cells[14] = {0};
+    int64_t ck_cells = 0, ck_problems = 0;  // of them checkpointed (SMX_MODE_CKPT)
 
     DevBuf pool, pool2, pool_special;  // ASCII pool, its two bit planes and per-word non-ACGT flags (smx_scan.cuh)
     int64_t pool_len = 0;
@@ -107,7 +108,8 @@ struct smx_handle {
     // checkpointed traceback (smx_traceback_ck.cuh) for packed global / semi-global problems of at least this size;
     // SMX_CKPT=0 switches it off, SMX_CKPT_MINROWS / SMX_CKPT_MINCOLS move the thresholds (rows > 512)
     bool ckpt = true;
-    int ck_min_rows = 1025, ck_min_cols = 1500;
+    bool ck_side = true;  // SMX_CK_SIDE=0: the checkpointed launches queue on the handle's stream instead of running beside the others
+    int ck_min_rows = 513, ck_min_cols = 1500;
     DevBuf d_compact, d_expand_items, d_comp;  // pipeline pool: sequences as given, expansion list, complement table
     std::vector<SmxResult> h_results;
     std::vector<int64_t> h_dense_off;
@@ -294,7 +296,7 @@ extern "C" int smx_create(smx_handle **out, int device_ordinal, void *stream)
         if ((e = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_least)) != cudaSuccess) { delete h; return fail(nullptr, -2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         if ((e = cudaStreamCreateWithPriority(&h->stream_hi, cudaStreamNonBlocking, prio_greatest)) != cudaSuccess) { cudaStreamDestroy(h->stream); delete h; return fail(nullptr, -2, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
         h->owns_stream = true;
-        for (int t = 0; t < 3; ++t) {
+        for (int t = 0; t < 4; ++t) {
             if (cudaStreamCreateWithPriority(&h->stream_team[t], cudaStreamNonBlocking, prio_least) != cudaSuccess) h->stream_team[t] = nullptr;
             cudaEventCreateWithFlags(&h->ev_join[t], cudaEventDisableTiming);
         }
@@ -340,7 +342,7 @@ extern "C" void smx_destroy(smx_handle *h)
     if (h->ev_sync_lo) cudaEventDestroy(h->ev_sync_lo);
     if (h->ev_sync_hi) cudaEventDestroy(h->ev_sync_hi);
     if (h->owns_stream) { cudaStreamDestroy(h->stream); cudaStreamDestroy(h->stream_hi); }
-    for (int t = 0; t < 3; ++t) { if (h->stream_team[t]) cudaStreamDestroy(h->stream_team[t]); if (h->ev_join[t]) cudaEventDestroy(h->ev_join[t]); }
+    for (int t = 0; t < 4; ++t) { if (h->stream_team[t]) cudaStreamDestroy(h->stream_team[t]); if (h->ev_join[t]) cudaEventDestroy(h->ev_join[t]); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     delete h;
 }
@@ -517,6 +519,7 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         { const char *pe = getenv("SMX_PERSISTENT"); h->persistent_fwd = pe && pe[0] == '1'; }
         { const char *se = getenv("SMX_S16H_SPLIT"); h->split_last = !(se && se[0] == '0'); }
         { const char *ce = getenv("SMX_CKPT"); h->ckpt = !(ce && ce[0] == '0'); }
+        { const char *ce = getenv("SMX_CK_SIDE"); h->ck_side = !(ce && ce[0] == '0'); }
         if (const char *e = getenv("SMX_CKPT_MINROWS")) { const int v = atoi(e); if (v > 512) h->ck_min_rows = v; }
         if (const char *e = getenv("SMX_CKPT_MINCOLS")) { const int v = atoi(e); if (v >= 1) h->ck_min_cols = v; }
         const char *envh = getenv("SMX_S16H");
@@ -593,12 +596,17 @@ static int align_prepare_impl(smx_handle *h, const int64_t *s1_off, const int32_
         }
     }
     // checkpointed traceback for the large packed problems: the forward pass runs score-only (1.7x faster) and the walk
-    // recomputes the direction bits of the blocks it crosses (~15 % of the cells of a 2 500 x 4 000 problem); pays from
-    // about 1 500 columns on (the recomputed share of a band pair is ~600 of its n + 95 steps)
+    // recomputes the direction bits of the blocks it crosses (~14 % of the cells of a 2 500 x 4 000 problem); pays from
+    // about 1 500 columns on (the recomputed share of a band pair is ~560 of its n + 95 steps) and from two band pairs
+    // on (C2: 1 025 rows 409 ms per 20 000 reads in the forward phase, 769 rows 405, 513 rows 401)
+    h->ck_cells = 0; h->ck_problems = 0;
     if (h->ckpt && h->use_s16 && h->use_s16h)
         for (int p = 0; p < n; ++p) {
             SmxProblem &q = h->probs[(size_t)p];
-            if (q.cls >= kClsS16 && (q.mode & SMX_MODE_MASK) != SMX_MODE_SW && q.m >= h->ck_min_rows && q.n >= h->ck_min_cols) q.mode |= SMX_MODE_CKPT;
+            if (q.cls >= kClsS16 && (q.mode & SMX_MODE_MASK) != SMX_MODE_SW && q.m >= h->ck_min_rows && q.n >= h->ck_min_cols) {
+                q.mode |= SMX_MODE_CKPT;
+                h->ck_cells += (int64_t)q.m * q.n; ++h->ck_problems;
+            }
         }
     // concurrent teams: the packed forward phase (one-warp launch + team launches side by side) is timed as ONE interval
     for (int p = 0; p < n; ++p) {
@@ -748,7 +756,7 @@ static int launch_forward(smx_handle *h, const Chunk &c, int cls, int chunk_idx)
 }
 
 template <int W>
-static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_idx, cudaStream_t stream = nullptr, bool do_mark = true)
+static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_idx, cudaStream_t stream = nullptr, bool do_mark = true, int sub_mask = 7)
 {
     if (c.cls_count[cls] == 0) return 0;
     if (!stream) stream = h->stream;
@@ -760,7 +768,7 @@ static int launch_forward16(smx_handle *h, const Chunk &c, int cls, int chunk_id
         const bool local = sub == 2, ck = sub == 1;
         const int n_plain = c.cls_count[cls] - c.cls_local[cls] - c.cls_ck[cls];
         const int count = local ? c.cls_local[cls] : ck ? c.cls_ck[cls] : n_plain;
-        if (count == 0) continue;
+        if (count == 0 || !(sub_mask & (1 << sub))) continue;
         int occ = 0;
         void (*kern)(const SmxFwdArgs) = !h->use_s16h ? smx_dp_forward16<W> : local ? smx_dp_forward16h<W, true, false> : ck ? smx_dp_forward16h<W, false, true> : smx_dp_forward16h<W, false, false>;
         SMX_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0));
@@ -851,7 +859,9 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
         const Chunk &c = h->chunks[ci];
         int rc = 0;
         if (h->guard) SMX_CUDA(h, cudaMemsetAsync(h->d_trace.p, 0xA5, c.trace_bytes, h->stream));
-        if (h->teams_concurrent && (c.cls_count[kClsS16 + 1] | c.cls_count[kClsS16 + 2] | c.cls_count[kClsS16 + 3])) {
+        // the checkpointed one-warp problems (the large ones) and the ones that keep direction bits run side by side as well
+        const bool side_ck = h->ck_side && h->stream_team[3] && c.cls_ck[kClsS16] > 0 && c.cls_count[kClsS16] > c.cls_ck[kClsS16];
+        if (h->teams_concurrent && ((c.cls_count[kClsS16 + 1] | c.cls_count[kClsS16 + 2] | c.cls_count[kClsS16 + 3]) || side_ck)) {
             // fork: the team launches (few CTAs, long) go first on their own streams and take their SM slots, the
             // one-warp-per-problem launch fills the rest; join before the next kernel of this stream
             SMX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
@@ -864,9 +874,15 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
                 if (rc) return rc;
                 SMX_CUDA(h, cudaEventRecord(h->ev_join[t], h->stream_team[t]));
             }
-            if ((rc = launch_forward16<1>(h, c, kClsS16, (int)ci, h->stream, false))) return rc;
+            if (side_ck) {
+                SMX_CUDA(h, cudaStreamWaitEvent(h->stream_team[3], h->ev_fork, 0));
+                if ((rc = launch_forward16<1>(h, c, kClsS16, (int)ci, h->stream_team[3], false, 2))) return rc;
+                SMX_CUDA(h, cudaEventRecord(h->ev_join[3], h->stream_team[3]));
+            }
+            if ((rc = launch_forward16<1>(h, c, kClsS16, (int)ci, h->stream, false, side_ck ? 5 : 7))) return rc;
             for (int t = 0; t < 3; ++t)
                 if (c.cls_count[kClsS16 + 1 + t]) SMX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[t], 0));
+            if (side_ck) SMX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[3], 0));
             if ((rc = mark(h, kClsS16))) return rc;
         } else {
             if ((rc = launch_forward16<8>(h, c, kClsS16 + 3, (int)ci))) return rc;
@@ -897,10 +913,12 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
         t.sc = h->sc;
         t.split_last = h->use_s16h ? h->split_last : 0;
         const long long tb_threads = 32ll * c.n_big + (c.count - c.n_ck - c.n_big);
-        if (tb_threads > 0) {
-            smx_traceback<<<(unsigned)((tb_threads + 127) / 128), 128, 0, h->stream>>>(t);
-            SMX_CUDA(h, cudaGetLastError());
-            h->last_launches++;
+        // the recomputing walks of the checkpointed problems next to the walks that read direction bits (latency-bound)
+        const bool side_tb = h->ck_side && h->teams_concurrent && h->stream_team[3] && c.n_ck > 0 && tb_threads > 0;
+        cudaStream_t ck_stream = side_tb ? h->stream_team[3] : h->stream;
+        if (side_tb) {
+            SMX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+            SMX_CUDA(h, cudaStreamWaitEvent(ck_stream, h->ev_fork, 0));
         }
         if (c.n_ck > 0) {
             SmxTbCkArgs k;
@@ -911,9 +929,18 @@ static int align_run_impl(smx_handle *h, int64_t *total_runs, DpGate *gate)
             const size_t smem = sizeof(uint32_t) * SMX_TBCK_WARPS * SMX_TBCK_TILE_WORDS;
             static std::once_flag once[16];
             std::call_once(once[h->device & 15], [&] { cudaFuncSetAttribute(smx_traceback_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
-            smx_traceback_ck<<<(unsigned)((c.n_ck + SMX_TBCK_WARPS - 1) / SMX_TBCK_WARPS), 32 * SMX_TBCK_WARPS, smem, h->stream>>>(k);
+            smx_traceback_ck<<<(unsigned)((c.n_ck + SMX_TBCK_WARPS - 1) / SMX_TBCK_WARPS), 32 * SMX_TBCK_WARPS, smem, ck_stream>>>(k);
             SMX_CUDA(h, cudaGetLastError());
             h->last_launches++;
+        }
+        if (tb_threads > 0) {
+            smx_traceback<<<(unsigned)((tb_threads + 127) / 128), 128, 0, h->stream>>>(t);
+            SMX_CUDA(h, cudaGetLastError());
+            h->last_launches++;
+        }
+        if (side_tb) {
+            SMX_CUDA(h, cudaEventRecord(h->ev_join[3], ck_stream));
+            SMX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join[3], 0));
         }
         if (int rc2 = mark(h, kSlotTraceback)) return rc2;
         if (h->guard) {
@@ -1895,6 +1922,7 @@ extern "C" int smx_pipeline_run(smx_handle *h, const uint8_t *ref_seqs, const in
         st.gpu_dp_ms = h->last_ms; st.dp_cells = h->cells; st.launches += h->last_launches;
         for (int c = 0; c < 16; ++c) st.dp_kernel_ms[c] = h->kernel_ms[c];
         for (int c = 0; c < 14; ++c) st.dp_class_cells[c] = h->class_cells[c];
+        st.dp_ck_cells = h->ck_cells; st.dp_ck_problems = h->ck_problems;
         for (int c = 0; c < 16; ++c) st.dp_kernel_launches[c] = h->kernel_launches[c];
         if (int rc = ensure_pinned(h, h->pin_cigar, sizeof(uint32_t) * (size_t)std::max<int64_t>(truns, 1))) return rc;
         cg = (uint32_t *)h->pin_cigar.p;
@@ -2012,6 +2040,8 @@ extern "C" int smx_pipeline_stats(smx_handle *h, double *out, int32_t n)
         else if (i < m + 46) out[i] = (double)st.dp_kernel_launches[i - m - 30];
         else if (i == m + 46) out[i] = st.gpu_select_ms;
         else if (i == m + 47) out[i] = st.gpu_chain_ms;
+        else if (i == m + 48) out[i] = (double)st.dp_ck_cells;
+        else if (i == m + 49) out[i] = (double)st.dp_ck_problems;
         else out[i] = 0.0;
     }
     return 0;

@@ -35,8 +35,13 @@ __host__ __device__ inline int64_t smx_trace_bytes(int m, int n, int K)
 // Checkpointed problems (SMX_MODE_CKPT, smx_dp16h.cuh / smx_traceback_ck.cuh): instead of direction bits the problem's
 // region of the arena holds the bottom line of every band (one uint32 = F^ << 16 | Hc per column) and, for every band
 // pair, the lane state at the top of every SMX_CK_CHUNKS-th 32-step chunk; the traceback recomputes the direction bits
-// of the 64-step blocks its path crosses.
-#define SMX_CK_CHUNKS 2   // 32-step chunks between two checkpoints = the block the traceback recomputes at a time
+// of the blocks (SMX_CK_CHUNKS * 32 steps) its path crosses.
+#ifndef SMX_CK_CHUNKS
+// 32-step chunks between two checkpoints = the block the traceback recomputes at a time.  1: an 8 KB tile per walking
+// warp, 20 warps per SM (2 with 16 KB tiles and 12 warps: smx_traceback_ck 202 -> 156 ms per 20 000 reads of C2, the
+// forward pass +1 % for twice the checkpoint stores)
+#define SMX_CK_CHUNKS 1
+#endif
 #define SMX_CK_WORDS 22   // words per lane of a checkpoint: Hc[8], El[8], hd, out_h, out_f, sel_prev, rch1, rch2
 struct SmxCkLayout {
     int32_t nbands, npairs, nal, nchunks, nck;

@@ -60,6 +60,11 @@ __device__ __forceinline__ uint32_t smx16h_max_tr(uint32_t a, uint32_t b, uint32
 #ifndef SMX16H_WPC
 #define SMX16H_WPC 4  // warps (= problems) per CTA of the one-warp-per-problem kernel
 #endif
+#ifndef SMX16H_CK_WARPS_PER_SM
+// resident warps per SM the score-only (checkpointed) instantiations are built for: without the direction-word accumulators
+// they fit 96 registers (C2 forward phase: 16 warps 402 ms per 20 000 reads, 20 warps 389, 24 warps / 80 registers 433)
+#define SMX16H_CK_WARPS_PER_SM 20
+#endif
 #ifndef SMX16H_ALU_FLAGS
 #define SMX16H_ALU_FLAGS 1  // how many of the four flag kinds of a cell go through the ALU pipe
 #endif
@@ -303,7 +308,7 @@ __device__ __forceinline__ void smx16h_edge_chunk(uint32_t (&Hc)[K], uint32_t (&
 // CK: the problems carry SMX_MODE_CKPT -- score-only cells, every band's bottom line and the pair checkpoints go to the
 // problem's region of the arena (smx_ck_layout) instead of direction bits; no claimed boundary lines.
 template <int W, bool LOCAL = false, bool CK = false>
-__global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, SMX16_MIN_WARPS_PER_SM / (W == 1 ? SMX16H_WPC : W)) smx_dp_forward16h(const SmxFwdArgs a)
+__global__ void __launch_bounds__(W == 1 ? 32 * SMX16H_WPC : W * 32, (CK ? SMX16H_CK_WARPS_PER_SM : SMX16_MIN_WARPS_PER_SM) / (W == 1 ? SMX16H_WPC : W)) smx_dp_forward16h(const SmxFwdArgs a)
 {
     static_assert(!(LOCAL && CK), "local problems keep their direction bits");
     constexpr bool TEAM = W > 1;

@@ -130,6 +130,7 @@ struct SmxPipelineState {
     int launches = 0;
     double dp_kernel_ms[16] = {0};
     int64_t dp_class_cells[14] = {0};
+    int64_t dp_ck_cells = 0, dp_ck_problems = 0;  // cells / problems of the packed classes that ran checkpointed
     int dp_kernel_launches[16] = {0};
     bool valid = false;
 };

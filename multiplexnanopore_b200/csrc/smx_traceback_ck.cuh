@@ -1,19 +1,23 @@
 // Traceback of the checkpointed problems (SMX_MODE_CKPT): the forward pass (smx_dp_forward16h<W, false, true>) kept no
 // direction bits, only every band's bottom line and the lane state of every band pair at the top of every
-// SMX_CK_CHUNKS-th chunk.  One warp per problem: for the cell the walk stands on it restores the checkpoint of the 64-step
-// block that holds the cell's step, re-runs the chunks of that block up to the cell with the SAME chunk code the full-trace
-// forward kernel runs (smx16h_fast_chunk / smx16h_edge_chunk: identical comparisons, identical direction bits), the
-// direction words going to a 16 KB tile in shared memory, and lane 0 walks inside the tile until the path leaves the block
-// or the band pair.  The walk itself is the state machine of smx_traceback (parasail's cigar_template.c through
+// SMX_CK_CHUNKS-th chunk.  One warp per problem: for the cell the walk stands on it restores the checkpoint of the block
+// (SMX_CK_CHUNKS * 32 steps) that holds the cell's step, re-runs the chunks of that block up to the cell with the SAME chunk
+// code the full-trace forward kernel runs (smx16h_fast_chunk / smx16h_edge_chunk: identical comparisons, identical direction
+// bits), the direction words going to an 8 KB tile in shared memory, and lane 0 walks inside the tile until the path leaves
+// the block or the band pair.  The walk itself is the state machine of smx_traceback (parasail's cigar_template.c through
 // MyResult.__init__, ref_query_alignment.py:426-433), including the device-side re-clipping.
 //
-// A path crosses a band pair (512 rows) in about 543 steps of the skewed frame, i.e. 9-10 blocks of 64 steps out of the
-// (n + 95) / 64 the pair has: for a 2 500 x 4 000 problem about 15 % of the cells are computed a second time.
+// A path crosses a band pair (512 rows) in about 543 steps of the skewed frame out of the n + 95 the pair has: for a
+// 2 500 x 4 000 problem about 14 % of the cells are computed a second time.  The kernel is latency-bound (one warp per
+// problem, lane 0 alone while walking), so it is built for residency: 96 registers, five CTAs of four warps per SM.
 #pragma once
 #include "smx_dp16h.cuh"
 #include "smx_traceback.cuh"
 
 #define SMX_TBCK_WARPS 4                                      // problems per CTA
+#ifndef SMX_TBCK_MINBLOCKS
+#define SMX_TBCK_MINBLOCKS 5                                  // CTAs per SM the register budget is set for (6: 80 registers, spills, 1.7x slower)
+#endif
 #define SMX_TBCK_TILE_WORDS (2 * SMX_CK_CHUNKS * 32 * 32)     // [half][step in block][lane] 32-bit words (K = 4: 16-bit words, half used)
 
 struct SmxTbCkArgs {
@@ -29,7 +33,7 @@ struct SmxTbCkArgs {
     uint32_t one;
 };
 
-__global__ void __launch_bounds__(32 * SMX_TBCK_WARPS, 3) smx_traceback_ck(const SmxTbCkArgs a)
+__global__ void __launch_bounds__(32 * SMX_TBCK_WARPS, SMX_TBCK_MINBLOCKS) smx_traceback_ck(const SmxTbCkArgs a)
 {
     constexpr int LAG = SMX16_LAG;
     constexpr int BLK = SMX_CK_CHUNKS * 32;  // steps of a block

@@ -366,7 +366,7 @@ _STAT_KEYS = ("t_total", "t_pool", "t_scan", "t_select", "t_chain", "t_dp", "t_s
               "gpu_dp_ms", "scan_cells", "dp_cells", "n_dp_problems", "n_host_redecisions", "n_failed", "kernel_launches",
               "n_pair_strands") + tuple(f"dp_ms_class{c}" for c in range(14)) + ("dp_ms_traceback", "dp_ms_compact") \
     + tuple(f"dp_cells_class{c}" for c in range(14)) + tuple(f"dp_launches_{c}" for c in range(16)) \
-    + ("gpu_select_only_ms", "gpu_chain_ms")
+    + ("gpu_select_only_ms", "gpu_chain_ms", "dp_cells_ck", "n_dp_problems_ck")
 
 
 def pack_slice(packed, lo, hi):

@@ -195,10 +195,10 @@ def test_checkpointed_traceback_shapes(engine, env):
 
 
 def test_checkpointed_traceback_default_thresholds(engine):
-    """At the default thresholds (>= 1 025 rows, >= 1 500 columns) next to problems that keep their direction bits; the
+    """At the default thresholds (>= 513 rows, >= 1 500 columns) next to problems that keep their direction bits; the
     same problems with SMX_CKPT=0 give the same answer (both are checked against the oracle)."""
     rng = np.random.default_rng(137)
-    shapes = [(1025, 1500), (1100, 1499), (1024, 3000), (2500, 4000), (3100, 2900), (5200, 6100), (600, 2500), (300, 300), (4000, 1501)]
+    shapes = [(513, 1500), (512, 1600), (1100, 1499), (1024, 3000), (2500, 4000), (3100, 2900), (5200, 6100), (600, 2500), (300, 300), (4000, 1501)]
     probs, modes = _ck_problems(rng, shapes)
     probs += util.make_problems(rng, 40, 800)
     modes += [int(x) for x in rng.integers(0, 4, size=40)]
