@@ -1,5 +1,5 @@
 """one-off randomized DP parity campaign (all four modes, sizes up to 6 k x 6 k, several scorings, team thresholds lowered,
-guard bands on): CUDA engine vs the C oracle.  Run on the GPU box:  python scratch/fuzz_dp.py [seed] [n_rounds]"""
+guard bands on, the column threshold of the checkpointed traceback cycling 1 500 / 1 / 200): CUDA engine vs the C oracle.  Run on the GPU box:  python scratch/fuzz_dp.py [seed] [n_rounds]"""
 import os, sys, time
 sys.path.insert(0, '.')
 os.environ["SMX_GUARD"] = "1"
@@ -29,6 +29,7 @@ def main():
         else:
             for k in ("SMX_TEAM2_MCELLS", "SMX_TEAM4_MCELLS", "SMX_TEAM8_MCELLS"):
                 os.environ.pop(k, None)
+        os.environ["SMX_CKPT_MINCOLS"] = ["1500", "1", "200"][rd % 3]   # checkpointed traceback: default, every packed problem of >= 513 rows, most
         probs, modes = [], []
         for _ in range(260):
             m = int(rng.choice([rng.integers(1, 40), rng.integers(33, 300), rng.integers(250, 1100), rng.integers(1000, 6000)], p=[0.2, 0.35, 0.3, 0.15]))
