@@ -50,6 +50,7 @@ DPX_PER_CELL_PACKED = 2.0  # VIMNMX.U16x2 per cell (4 per cell pair)
 # checkpointed problems (SMX_MODE_CKPT): the forward launch computes scores only -- per cell PAIR 2 max + 1 max3 + 1 subst + 2 add = 6
 OPS_PER_CELL_SCORE_ONLY = 3.0
 DPX_PER_CELL_SCORE_ONLY = 1.5
+CK_BYTES_PER_CELL = 0.19   # 22 words x 32 lanes per 32-step chunk and 512-row band pair + one bottom-line entry per 256 cells
 TRACE_BYTES_PER_CELL = 0.5
 CPU_SAMPLE_READS = 200     # seeded 200-read subset for the cpu_baseline of the engine arm
 
@@ -476,7 +477,8 @@ def run_engine(args, rank, world, local_rank):
                      "frac": k8_tcups * dpx_blend / dpx_peak_tops if dpx_peak_tops else None,
                      "note": "VIMNMX(3).U16x2 lane-instructions against the measured DPX rate of the ALU pipe (64 lanes/clk/SM); the score-only launches are bound by "
                              "that pipe (ncu: ALU pipe 78 % busy, FMA pipe 19 %, profiles/dp_forward16h_ck_r02_summary.json)"},
-        "hbm_view": {"achieved": k8_tcups * 1e3 * TRACE_BYTES_PER_CELL * (1.0 - ck_share), "peak": hbm_peak, "unit": "GB/s", "frac": k8_tcups * 1e3 * TRACE_BYTES_PER_CELL * (1.0 - ck_share) / hbm_peak,
+        "hbm_view": {"achieved": k8_tcups * 1e3 * (TRACE_BYTES_PER_CELL * (1.0 - ck_share) + CK_BYTES_PER_CELL * ck_share), "peak": hbm_peak, "unit": "GB/s",
+                     "frac": k8_tcups * 1e3 * (TRACE_BYTES_PER_CELL * (1.0 - ck_share) + CK_BYTES_PER_CELL * ck_share) / hbm_peak,
                      "peak_source": f"MEASURED_PEAKS.json ({hbm_src})"},
         "traffic": None,
         "int_peak_detail_gops": peak,
