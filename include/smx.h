@@ -65,7 +65,9 @@ const char *smx_last_error(const smx_handle *h);
 
 /* Upper bound for the device bytes of packed traceback kept in flight at once (default min(16 GiB, an eighth of
  * the free device memory at creation); SMX_TRACE_BUDGET_GB in the environment overrides);
- * larger batches are cut into chunks that are processed back to back. */
+ * larger batches are cut into chunks that are processed back to back.  A problem takes 0.5 byte per cell of
+ * direction bits, or -- packed global / semi-global problems of at least 513 rows and 1 500 columns, whose forward
+ * pass keeps checkpoints and whose traceback recomputes the blocks it crosses -- 0.19 byte per cell. */
 int smx_set_trace_budget(smx_handle *h, int64_t bytes);
 int64_t smx_get_trace_budget(const smx_handle *h);
 

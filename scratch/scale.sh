@@ -12,6 +12,6 @@ try:
 except Exception as ex: print("N=$N $tag failed", ex); print(open("gpurun_out/scale_${tag}_n${N}_r02.err").read()[-1500:])
 PY
 }
-run weak --steps 3 --warmup 3
-run strong --steps 3 --warmup 3 --scaling strong
+run weak --steps 3 --warmup 2
+run strong --steps 3 --warmup 2 --scaling strong
 if [ "$2" == "c5" ]; then run c5 --config c5 --scaling strong --steps 1 --warmup 1; fi
