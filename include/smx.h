@@ -193,6 +193,23 @@ int smx_msa_run(smx_handle *h, const uint8_t *ref, int32_t ref_len, int32_t n_re
                 const int64_t *qry_off, const int32_t *qry_len, const uint32_t *cigar_rle, const int64_t *cigar_off, int64_t *n_cols);
 int smx_msa_fetch(smx_handle *h, uint8_t *ref_aligned, uint8_t *seq_aligned, int8_t *qs_aligned, uint8_t *cigar_aligned);
 
+/* ---- row N3, second half: the per-column Bayesian consensus --------------------------------------
+ * MyMSA.calculate_consensus_core (savemoney/modules/msa.py:1749-1812) calls, for every column of the multiple alignment,
+ * SequenceBasecallQscorePDF.calc_consensus_error_rate (cython_functions/alignment_functions.pyx:93-132): long double
+ * products over the reads that vote in the column (column letter not H / O).  This entry point returns that p_list for
+ * every column, with and without prior, bit-identical to the reference's x87 arithmetic (the product chains run on the
+ * device on a restated 80-bit multiplication, the seven remaining operations per value in the host's long double).
+ *   seq / qs / cig   [n_rows][n_cols] matrices as smx_msa_fetch delivers them, or all NULL = the result of the last
+ *                    smx_msa_run on this handle (still on the device)
+ *   P25[B*5 + c]     P_base_calling_given_true_refseq_dict["B_c"], bases in the order "ATCG-" (msa.py:655,699)
+ *   pdf[(B*5+c)*93 + k]  pdf_core["B_c"][k] (msa.py:705)
+ *   col_class[n_cols], pn_with / pn_without [n_classes][5]: P_N_dict_dict[ref letter] of msa.py:1813-1845 per column
+ *   p_with / p_without [n_cols][5], n_events[n_cols] (0: the reference emits "-" with q-score -1, msa.py:1793-1795)
+ * Returns -7 if a voting read holds a character outside ATCG- or a q-score above 92 (undefined behaviour in the reference). */
+int smx_consensus_run(smx_handle *h, const uint8_t *seq, const int8_t *qs, const uint8_t *cig, int32_t n_rows, int64_t n_cols,
+                      const double *P25, const double *pdf, const int32_t *col_class, const double *pn_with, const double *pn_without,
+                      int32_t n_classes, double *p_with, double *p_without, int32_t *n_events);
+
 /* ---- row N2: what consumes the score matrix and the CIGARs without per-result objects -------
  * smx_assign: msa.QueryAssignment (savemoney/modules/msa.py:31-64) on the device, one thread per read.
  *   score / status: [n_reads, 2 * n_refs] as smx_pipeline_fetch delivers them (status != 0 = empty MyResult());

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "smx_ops_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "smx_msa_run": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_int64)]),
     "smx_msa_fetch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "smx_consensus_run": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "smx_assign": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_double, c_void_p, c_void_p, c_void_p]),
     "smx_ir_format": (c_int64, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int64]),
 }

@@ -23,6 +23,7 @@
 #include "smx_traceback_ck.cuh"
 #include "smx_outputs.cuh"
 #include "smx_msa.cuh"
+#include "smx_consensus.cuh"
 
 namespace {
 
@@ -133,7 +134,7 @@ struct smx_handle {
     std::vector<uint8_t> ops_status;
     bool ops_valid = false;
     // smx_msa_run results (row N3): column matrices on the device until fetched
-    DevBuf d_msa_in, d_msa_work, d_msa_out;
+    DevBuf d_msa_in, d_msa_work, d_msa_out, d_cons;
     int64_t msa_cols = -1;
     int32_t msa_reads = 0;
 };
@@ -328,7 +329,7 @@ extern "C" void smx_destroy(smx_handle *h)
     cudaStreamSynchronize(h->stream);
     cudaStreamSynchronize(h->stream_hi);
     DevBuf *bufs[] = {&h->pool, &h->pool2, &h->pool_special, &h->d_probs, &h->d_order_cls, &h->d_order_all, &h->d_results, &h->d_trace, &h->d_boundary,
-                      &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_slots, &h->d_guard_err, &h->d_msa_in, &h->d_msa_work, &h->d_msa_out, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts,
+                      &h->d_runs, &h->d_dense, &h->d_dense_off, &h->d_tickets, &h->d_slots, &h->d_guard_err, &h->d_msa_in, &h->d_msa_work, &h->d_msa_out, &h->d_cons, &h->d_scan_pairs, &h->d_scan_tile_pair, &h->d_counts,
                       &h->d_sel_pairs, &h->d_sel_out, &h->d_regions, &h->d_chain_tasks, &h->d_chain_regions, &h->d_chain_traces,
                       &h->d_chain_out, &h->d_chain_scratch, &h->d_compact, &h->d_expand_items, &h->d_comp};
     smx_pipeline_free(h);
@@ -1306,6 +1307,78 @@ extern "C" int smx_msa_fetch(smx_handle *h, uint8_t *ref_aligned, uint8_t *seq_a
         if (qs_aligned) SMX_CUDA(h, cudaMemcpyAsync(qs_aligned, d + C + 2 * C * rows, C * rows, cudaMemcpyDeviceToHost, st));
     }
     SMX_CUDA(h, smx_sync(h, st));
+    return 0;
+}
+
+// Row N3, second half: the Bayesian consensus of MyMSA.calculate_consensus_core (msa.py:1749-1812) for every column of
+// a multiple alignment; see smx_consensus.cuh.  seq / qs / cig == NULL: the matrices of the last smx_msa_run, still on
+// the device.  P25[B * 5 + called] = P_base_calling_given_true_refseq_dict["B_called"], pdf[(B * 5 + called) * 93 + k] =
+// pdf_core["B_called"][k] (bases in the order "ATCG-"); pn_with / pn_without [n_classes][5] = P_N_dict of the column's
+// reference letter (col_class[c]) with and without prior.  p_with / p_without [n_cols][5] = p_list per column.
+extern "C" int smx_consensus_run(smx_handle *h, const uint8_t *seq, const int8_t *qs, const uint8_t *cig, int32_t n_rows, int64_t n_cols,
+                                 const double *P25, const double *pdf, const int32_t *col_class, const double *pn_with, const double *pn_without,
+                                 int32_t n_classes, double *p_with, double *p_without, int32_t *n_events)
+{
+    if (!h) return -1;
+    if (n_rows < 0 || n_cols < 0 || n_classes <= 0 || !P25 || !pdf || !pn_with || !pn_without || (n_cols > 0 && (!col_class || !p_with || !p_without || !n_events)))
+        return fail(h, -1, "smx_consensus_run: NULL or empty argument");
+    if ((seq == nullptr) != (qs == nullptr) || (seq == nullptr) != (cig == nullptr)) return fail(h, -1, "smx_consensus_run: pass all three matrices or none");
+    if (n_cols == 0) return 0;
+    for (int64_t c = 0; c < n_cols; ++c) if (col_class[c] < 0 || col_class[c] >= n_classes) return fail(h, -1, "smx_consensus_run: column %lld: class out of range", (long long)c);
+    SMX_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = h->stream_hi;
+    const size_t C = (size_t)n_cols, R = (size_t)n_rows;
+    const uint8_t *d_seq, *d_cig;
+    const int8_t *d_qs;
+    if (!seq) {
+        if (h->msa_cols != n_cols || h->msa_reads != n_rows) return fail(h, -1, "smx_consensus_run: no smx_msa_run of %d reads x %lld columns on this handle", n_rows, (long long)n_cols);
+        const uint8_t *d = (const uint8_t *)h->d_msa_out.p;   // layout of smx_msa_run: ref, seq, cig, qs
+        d_seq = d + C; d_cig = d_seq + C * R; d_qs = (const int8_t *)(d_cig + C * R);
+    }
+    // factor table and start values in native long double (smx_consensus_host.hpp)
+    const int NT = 25 * SMX_CONS_BASES * SMX_CONS_QIDX;
+    std::vector<uint64_t> tm, im;
+    std::vector<int32_t> te, ie;
+    smx_cons_build_table(P25, pdf, tm, te);
+    smx_cons_build_init(pn_with, pn_without, n_classes, im, ie);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t o_tm = 0, o_te = al(o_tm + 8 * (size_t)NT), o_im = al(o_te + 4 * (size_t)NT), o_ie = al(o_im + 8 * im.size()), o_cls = al(o_ie + 4 * ie.size()),
+                 o_om = al(o_cls + 4 * C), o_oe = al(o_om + 8 * 50 * C), o_ev = al(o_oe + 4 * 50 * C), o_err = al(o_ev + 4 * C),
+                 o_seq = al(o_err + 64), o_cig = al(o_seq + (seq ? C * R : 0)), o_qs = al(o_cig + (seq ? C * R : 0)), total = al(o_qs + (seq ? C * R : 0)) + 256;
+    if (int rc = ensure(h, h->d_cons, total)) return rc;
+    char *d = (char *)h->d_cons.p;
+    SMX_CUDA(h, cudaMemcpyAsync(d + o_tm, tm.data(), 8 * (size_t)NT, cudaMemcpyHostToDevice, st));
+    SMX_CUDA(h, cudaMemcpyAsync(d + o_te, te.data(), 4 * (size_t)NT, cudaMemcpyHostToDevice, st));
+    SMX_CUDA(h, cudaMemcpyAsync(d + o_im, im.data(), 8 * im.size(), cudaMemcpyHostToDevice, st));
+    SMX_CUDA(h, cudaMemcpyAsync(d + o_ie, ie.data(), 4 * ie.size(), cudaMemcpyHostToDevice, st));
+    SMX_CUDA(h, cudaMemcpyAsync(d + o_cls, col_class, 4 * C, cudaMemcpyHostToDevice, st));
+    SMX_CUDA(h, cudaMemsetAsync(d + o_err, 0, 64, st));
+    if (seq) {
+        if (R) {
+            SMX_CUDA(h, cudaMemcpyAsync(d + o_seq, seq, C * R, cudaMemcpyHostToDevice, st));
+            SMX_CUDA(h, cudaMemcpyAsync(d + o_cig, cig, C * R, cudaMemcpyHostToDevice, st));
+            SMX_CUDA(h, cudaMemcpyAsync(d + o_qs, qs, C * R, cudaMemcpyHostToDevice, st));
+        }
+        d_seq = (const uint8_t *)(d + o_seq); d_cig = (const uint8_t *)(d + o_cig); d_qs = (const int8_t *)(d + o_qs);
+    }
+    SmxConsArgs a;
+    a.seq = d_seq; a.qs = d_qs; a.cig = d_cig; a.rows = n_rows; a.cols = n_cols;
+    a.tab_m = (const uint64_t *)(d + o_tm); a.tab_e = (const int32_t *)(d + o_te);
+    a.col_class = (const int32_t *)(d + o_cls);
+    a.init_m = (const uint64_t *)(d + o_im); a.init_e = (const int32_t *)(d + o_ie); a.n_classes = n_classes;
+    a.out_m = (uint64_t *)(d + o_om); a.out_e = (int32_t *)(d + o_oe); a.n_events = (int32_t *)(d + o_ev); a.err = (int32_t *)(d + o_err);
+    smx_consensus_kernel<<<dim3((unsigned)((C + 127) / 128), 25), 128, 0, st>>>(a);
+    SMX_CUDA(h, cudaGetLastError());
+    std::vector<uint64_t> om(50 * C);
+    std::vector<int32_t> oe(50 * C);
+    int32_t err = 0;
+    SMX_CUDA(h, cudaMemcpyAsync(om.data(), d + o_om, 8 * 50 * C, cudaMemcpyDeviceToHost, st));
+    SMX_CUDA(h, cudaMemcpyAsync(oe.data(), d + o_oe, 4 * 50 * C, cudaMemcpyDeviceToHost, st));
+    SMX_CUDA(h, cudaMemcpyAsync(n_events, d + o_ev, 4 * C, cudaMemcpyDeviceToHost, st));
+    SMX_CUDA(h, cudaMemcpyAsync(&err, d + o_err, 4, cudaMemcpyDeviceToHost, st));
+    SMX_CUDA(h, smx_sync(h, st));
+    if (err) return fail(h, -7, "smx_consensus_run: a voting read holds a character outside ATCG- or a q-score above 92 (the reference reads out of bounds there, alignment_functions.pyx:113)");
+    smx_cons_finish(om.data(), oe.data(), C, p_with, p_without);
     return 0;
 }
 

@@ -10,7 +10,7 @@ MyMSAligner.execute, msa.py:629).  Here the same layout is computed column-paral
 
 The four fields hold exactly what the reference's MyMSA holds after generate_msa; they are rendered from the
 [n_reads, n_columns] byte matrices on first use (`*_matrix` gives the matrices themselves).  The Bayesian consensus
-(msa.py:1746-1812, long double) is not part of this row's first pass.
+(msa.py:1746-1812, long double) over those matrices is consensus.py (`MyMSA.calculate_consensus`).
 """
 from __future__ import annotations
 
@@ -53,6 +53,13 @@ class MyMSA:
         self.ref_seq_aligned_matrix, self.query_seq_matrix, self.q_scores_matrix, self.my_cigar_matrix = ref_aligned, seq, qs, cig
         self.param_dict = param_dict
         self._cache = {}
+
+    sbq_pdf = None   # class attribute as in the reference (set by MyMSA.set_sbq_pdf, msa.py:1738-1745): a consensus.SequenceBasecallQscorePDF
+
+    def calculate_consensus(self, engine=None):
+        """msa.py:1749-1754 on the device (consensus.py): fills with_prior_consensus_* / without_prior_consensus_*"""
+        from .consensus import calculate_consensus
+        return calculate_consensus(self, type(self).sbq_pdf, engine=engine)
 
     @property
     def n_columns(self):

@@ -38,8 +38,8 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     so = HERE / "liboracle.so"
-    src = HERE / "parasail_port.c"
-    if force or not so.exists() or (src.exists() and so.stat().st_mtime < src.stat().st_mtime):
+    srcs = [HERE / "parasail_port.c", HERE / "consensus_port.c"]
+    if force or not so.exists() or any(src.exists() and so.stat().st_mtime < src.stat().st_mtime for src in srcs):
         subprocess.check_call(["make", "-C", str(HERE), str(so)], stdout=subprocess.DEVNULL)
     return so
 
@@ -61,7 +61,25 @@ def lib():
         _lib.pp_matrix_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         _lib.pp_set_tie_rules.restype = None
         _lib.pp_set_tie_rules.argtypes = [ctypes.c_int] * 4
+        _lib.pp_consensus_error_rate.restype = ctypes.c_int
+        _lib.pp_consensus_error_rate.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_void_p, ctypes.c_void_p]
     return _lib
+
+
+def consensus_error_rate(P25: np.ndarray, pdf: np.ndarray, called: str, q_scores, PN5) -> list:
+    """SequenceBasecallQscorePDF.calc_consensus_error_rate (alignment_functions.pyx:93-132) for one column: p_list over the
+    bases "ATCG-".  P25 [25] and pdf [25, 93] float64 in the key order B_c with B, c over "ATCG-"."""
+    P25 = np.ascontiguousarray(P25, dtype=np.float64); pdf = np.ascontiguousarray(pdf, dtype=np.float64)
+    q = np.ascontiguousarray(q_scores, dtype=np.int32)
+    pn = np.ascontiguousarray(PN5, dtype=np.float64)
+    out = np.zeros(5, np.float64)
+    scratch = np.zeros(max(1, len(called)), np.longdouble)
+    rc = lib().pp_consensus_error_rate(P25.ctypes.data, pdf.ctypes.data, len(called), called.encode("ascii"), q.ctypes.data, pn.ctypes.data,
+                                       out.ctypes.data, scratch.ctypes.data)
+    if rc != 0:
+        raise ValueError("a character outside ATCG- or a q-score above 92 (the reference indexes out of bounds there)")
+    return [float(x) for x in out]
 
 
 def set_tie_rules(gap_prefers_extend: int = 1, h_order_diag_f_e: int = 1, sg_end_order: int = 0, sw_end_order: int = 1):
