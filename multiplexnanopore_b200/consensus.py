@@ -98,34 +98,47 @@ class SequenceBasecallQscorePDF:
         return P, pdf
 
 
+def select_sbq_pdf(q_score_distribution, candidates):
+    """MyMSA.set_sbq_pdf (msa.py:1738-1745): of the statistics tables on offer (SequenceBasecallQscorePDF objects or csv paths,
+    in the order of their minor versions) the one whose q-score distribution is closest (Jensen-Shannon) to the run's own
+    (`MyFastQ.get_q_score_distribution()`: counts of the q-scores -1 .. 41)"""
+    pdfs = [c if isinstance(c, SequenceBasecallQscorePDF) else SequenceBasecallQscorePDF(df_csv_path=c) for c in candidates]
+    js_scores = [pdf.calc_js_divergence(q_score_distribution) for pdf in pdfs]
+    return pdfs[int(np.argmin(js_scores))]
+
+
 def consensus_params(param_dict):
-    """msa.py:1813-1833: P_N_dict per reference letter, with and without prior (plain dicts keyed by letter)"""
-    ins_rate = param_dict["ins_rate"]
-    error_rate = param_dict["error_rate"]
-    len_bases = len(BASES)
-    assert len_bases == 5
-    with_prior = {
-        b_key1: {b_key2: (1 - error_rate) / len(b_val1) if b_key2 in b_val1 else error_rate / (len_bases - len(b_val1)) for b_key2 in BASES}
-        for b_val1, b_key1 in LETTER_CODE_DICT.items()
-    }
-    with_prior["-"] = {b_key2: ins_rate / 4 if b_key2 != "-" else 1 - ins_rate for b_key2 in BASES}
-    without_prior = {b_key1: {b_key2: 1 / len_bases for b_key2 in BASES} for b_key1 in "".join(LETTER_CODE_DICT.values()) + "-"}
+    """msa.py:1813-1833: P_N_dict per reference letter, with and without prior (plain dicts keyed by letter).
+    With prior: the bases a (possibly ambiguous) reference letter stands for share 1 - error_rate, the others -- the gap
+    included -- share error_rate; a gap column expects an insertion with ins_rate.  Without prior: uniform."""
+    ins_rate, error_rate = param_dict["ins_rate"], param_dict["error_rate"]
+    n = len(BASES)
+    assert n == 5
+    with_prior, without_prior = {}, {}
+    for stands_for, letter in LETTER_CODE_DICT.items():
+        inside, outside = (1 - error_rate) / len(stands_for), error_rate / (n - len(stands_for))
+        with_prior[letter] = {b: inside if b in stands_for else outside for b in BASES}
+        without_prior[letter] = {b: 1 / n for b in BASES}
+    with_prior["-"] = {b: 1 - ins_rate if b == "-" else ins_rate / 4 for b in BASES}
+    without_prior["-"] = {b: 1 / n for b in BASES}
     return with_prior, without_prior
 
 
 def mixed_bases(base_list):
-    """msa.py:1846-1857"""
+    """msa.py:1846-1857: one candidate -> itself; several -> the IUPAC letter of the bases among them (a gap among them is dropped)"""
     if len(base_list) == 1:
         return base_list[0]
-    elif "-" not in base_list:
-        pass
-    else:
-        base_list.remove("-")
-    letters = ""
-    for b in BASES[:-1]:
-        if b in base_list:
-            letters += b
-    return LETTER_CODE_DICT[letters]
+    present = set(base_list) - {"-"}
+    return LETTER_CODE_DICT["".join(b for b in BASES[:-1] if b in present)]
+
+
+def _column_letter(ref, call):
+    """msa.py:1799-1810: consensus CIGAR letter of a column from its reference character and the consensus call"""
+    if call == "-":
+        return "N" if ref == "-" else "D"
+    if ref == "-":
+        return "I"
+    return "=" if ref == call else "X"
 
 
 def consensus_error_rates(msa, sbq_pdf, param_dict=None, engine=None, device_resident=False):
@@ -167,13 +180,15 @@ def consensus_error_rates(msa, sbq_pdf, param_dict=None, engine=None, device_res
 
 
 def _consensus_core(ref_seq_aligned, p_rows, n_events):
-    """msa.py:1755-1812 after the p_list of every column is known"""
-    consensus_seq, consensus_q_scores, consensus_my_cigar = [], [], []
+    """msa.py:1755-1812 once the p_list of every column is known: the call is the candidate (or the mix of the candidates)
+    with the smallest error probability p, its q-score round(-10 log10 p) capped at 50 below p = 1e-5; a column nobody votes
+    in is a gap with q-score -1"""
+    calls, q_scores, letters = [], [], []
     for ref, p_row, ev in zip(ref_seq_aligned, p_rows, n_events):
         if ev > 0:
             p_list = [float(x) for x in p_row]
             p = min(p_list)
-            consensus_base_call = mixed_bases([b for b, tmp_p in zip(BASES, p_list) if tmp_p == p])
+            call = mixed_bases([b for b, tmp_p in zip(BASES, p_list) if tmp_p == p])
             if p >= 10 ** (-5):
                 q_score = np.round(-10 * np.log10(p)).astype(int)
             elif p < 0:
@@ -181,23 +196,9 @@ def _consensus_core(ref_seq_aligned, p_rows, n_events):
             else:
                 q_score = 50
         else:
-            consensus_base_call = "-"
-            q_score = -1
-        consensus_seq.append(consensus_base_call)
-        consensus_q_scores.append(q_score)
-        if ref == consensus_base_call != "-":
-            consensus_my_cigar.append("=")
-        elif ref == "-" != consensus_base_call:
-            consensus_my_cigar.append("I")
-        elif ref != consensus_base_call == "-":
-            consensus_my_cigar.append("D")
-        elif "-" != ref != consensus_base_call != "-":
-            consensus_my_cigar.append("X")
-        elif ref == consensus_base_call == "-":
-            consensus_my_cigar.append("N")
-        else:
-            raise Exception(f"error: {ref} {consensus_base_call}")
-    return "".join(consensus_seq), consensus_q_scores, "".join(consensus_my_cigar)
+            call, q_score = "-", -1
+        calls.append(call); q_scores.append(q_score); letters.append(_column_letter(ref, call))
+    return "".join(calls), q_scores, "".join(letters)
 
 
 def calculate_consensus(msa, sbq_pdf, param_dict=None, engine=None, device_resident=False):

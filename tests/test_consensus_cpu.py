@@ -143,3 +143,26 @@ def test_host_code_of_the_entry_point_around_a_cpu_replay_of_the_kernel(harness)
                                     tabs[0][0].ctypes.data, tabs[0][1].ctypes.data, np.zeros(1, np.int32).ctypes.data, np.full((1, 5), 0.2).ctypes.data,
                                     np.full((1, 5), 0.2).ctypes.data, 1, np.zeros((1, 5)).ctypes.data, np.zeros((1, 5)).ctypes.data, np.zeros(1, np.int32).ctypes.data)
     assert rc == -7
+
+
+def test_statistics_table_file_and_selection(tmp_path):
+    """the csv reader (same format as the reference's NanoporeStats_*.csv) gives the tables the constructor-from-counts gives,
+    and select_sbq_pdf (MyMSA.set_sbq_pdf, msa.py:1738-1745) picks the table whose q-score distribution is closest"""
+    from multiplexnanopore_b200 import consensus as cs
+    g = gold()
+    paths = []
+    for k, t in enumerate(g["tables"]):
+        p = tmp_path / f"NanoporeStats_0.{k}.csv"
+        with open(p, "w") as f:
+            f.write("# file_version: 0.0.%d\n" % k)
+            f.write("\t" + "\t".join(t["columns"]) + "\n")
+            for idx, row in zip(range(-1, 42), t["counts"]):
+                f.write(str(idx) + "\t" + "\t".join(str(x) for x in row) + "\n")
+        paths.append(p)
+    for p, t in zip(paths, g["tables"]):
+        a, b = cs.SequenceBasecallQscorePDF(df_csv_path=p), cs.SequenceBasecallQscorePDF(columns=t["columns"], counts=t["counts"])
+        assert a.NanoporeStats_PDF_version.startswith("0.0.") and np.array_equal(a.tables()[0], b.tables()[0]) and np.array_equal(a.tables()[1], b.tables()[1])
+        assert abs(sum(a.pdf_core["A_A"]) - 1.0) < 1e-12 and len(a.pdf_core["A_A"]) == 93
+    pdfs = [cs.SequenceBasecallQscorePDF(df_csv_path=p) for p in paths]
+    for k, pdf in enumerate(pdfs):
+        assert cs.select_sbq_pdf(pdf.q_score_distribution, paths).NanoporeStats_PDF_version == f"0.0.{k}"
