@@ -320,131 +320,64 @@ inline int64_t aligned_offset_runs(const Runs &v, int64_t off, uint32_t mask)
     return a;
 }
 
-// Suffix sums over a run array: columns, I/S columns and D/H columns of runs[i..).  The fixed-point iterations of
-// get_aligned_ref_seq_offset / get_aligned_query_seq_offset ask for "how many I/S (D/H) columns among the last `a`
-// columns" about a dozen times per pair-strand; scanning the tail each time was most of the stitch stage (12 ns per run
-// and pair-strand).  Round 1 kept the three sums for EVERY run (24 bytes written per run: the heaviest pass of the
-// stage); now one checkpoint per 64 runs: a question is a binary search over the checkpoints plus at most 64 runs.
-struct TailSums {
-    static constexpr size_t B = 64;
-    std::vector<int64_t> ck;  // 3 per checkpoint c: columns, I/S columns, D/H columns of runs[c * B ..); last checkpoint = (0, 0, 0)
-    const Runs *v = nullptr;
-    size_t n = 0, n_ck = 0;
-    int64_t total[3] = {0, 0, 0};
-    static inline void add(uint32_t run, int64_t (&acc)[3])
-    {
-        const int64_t len = run >> 4;
-        const uint32_t op = run & 15u;
-        acc[0] += len;
-        acc[1] += (op == 1u || op == 4u) ? len : 0;
-        acc[2] += (op == 2u || op == 5u) ? len : 0;
-    }
-    void build(const Runs &runs)
-    {
-        v = &runs;
-        n = runs.size();
-        n_ck = (n + B - 1) / B + 1;
-        ck.resize(3 * n_ck);
-        int64_t acc[3] = {0, 0, 0};
-        size_t c = n_ck - 1;
-        ck[3 * c] = 0; ck[3 * c + 1] = 0; ck[3 * c + 2] = 0;
-        for (size_t i = n; i-- > 0;) {
-            add(runs[i], acc);
-            if (i % B == 0) { c = i / B; ck[3 * c] = acc[0]; ck[3 * c + 1] = acc[1]; ck[3 * c + 2] = acc[2]; }
-        }
-        total[0] = acc[0]; total[1] = acc[1]; total[2] = acc[2];
-    }
-    int64_t cols0() const { return total[0]; }
-    // smallest run index i whose suffix runs[i..) holds at most `limit` columns (strict: fewer than `limit`), with the sums of that suffix
-    size_t first_suffix_within(int64_t limit, bool strict, int64_t (&sum)[3]) const
-    {
-        auto ok = [&](int64_t c) { return strict ? c < limit : c <= limit; };
-        size_t lo = 0, hi = n_ck - 1;   // smallest checkpoint whose suffix is within the limit (the last one always is: 0 columns)
-        while (lo < hi) {
-            const size_t mid = (lo + hi) >> 1;
-            if (ok(ck[3 * mid])) hi = mid; else lo = mid + 1;
-        }
-        size_t i = std::min(lo * B, n);
-        sum[0] = ck[3 * lo]; sum[1] = ck[3 * lo + 1]; sum[2] = ck[3 * lo + 2];
-        const size_t floor_i = lo == 0 ? 0 : (lo - 1) * B;
-        while (i > floor_i) {   // extend backwards run by run inside the block before the checkpoint
-            int64_t t[3] = {sum[0], sum[1], sum[2]};
-            add((*v)[i - 1], t);
-            if (!ok(t[0])) break;
-            sum[0] = t[0]; sum[1] = t[1]; sum[2] = t[2];
-            --i;
-        }
-        return i;
-    }
-    // columns among the last `a` columns that are I/S (which = 0) or D/H (which = 1); a beyond the length clamps
-    int64_t count(int64_t a, int which) const
-    {
-        if (a <= 0) return 0;
-        if (a >= total[0]) return total[1 + which];
-        int64_t sum[3];
-        const size_t lo = first_suffix_within(a, false, sum);   // runs lo.. lie inside the tail entirely
-        int64_t cnt = sum[1 + which];
-        if (lo > 0) {  // the run before contributes its last a - cols[lo] columns
-            const uint32_t op = (*v)[lo - 1] & 15u;
-            const bool hit = which ? (op == 2u || op == 5u) : (op == 1u || op == 4u);
-            if (hit) cnt += a - sum[0];
-        }
-        return cnt;
-    }
-    int64_t aligned_offset(int64_t off, int which) const
-    {
-        if (off == 0) return 0;
-        int64_t a = off, prev = 0, cnt = count(a, which);
-        while (off != a - cnt) {
-            a += cnt - prev;
-            prev = cnt;
-            cnt = count(a, which);
-        }
-        return a;
-    }
-};
-
-// set_ref_seq_offset_as_0 on runs: rotates in place, returns new_query_seq_offset
+// set_ref_seq_offset_as_0 on runs: rotates in place, returns new_query_seq_offset.
+// The reference asks its fixed-point questions about tails of the column string ("the shortest tail that holds ref_off
+// reference letters", "... q_off query letters", "how many D / H columns lie in those tails"); all of them are answered by ONE
+// backward scan over the runs that stops as soon as both tails are found, and the scan also leaves the run the cut falls
+// into.  The suffix-sum checkpoints of the previous version cost a full pass plus a dozen searches with unpredictable branches
+// on the op codes: 6.0 against 2.9 us per 1 200-run pair-strand (scratch/bench_rotate.cpp).
 inline int64_t rotate_to_ref0_runs(Runs &v, int64_t ref_off, int64_t q_off)
 {
     if (ref_off == 0 && q_off == 0) return 0;
-    thread_local TailSums ts;
-    ts.build(v);
-    const int64_t a_r = ts.aligned_offset(ref_off, 0);
-    const int64_t a_q = ts.aligned_offset(q_off, 1);
+    // tail = the last t columns; c0 / c1 = its I/S resp. D/H columns.  a_r = smallest t with t - c0 == ref_off, a_q = smallest
+    // t with t - c1 == q_off (get_aligned_*_seq_offset); dh_r / dh_q = D/H columns among the last a_r resp. a_q columns
+    // (op codes: I 1, D 2, S 4, H 5, = 7, X 8).  The loop body has no data-dependent branch: the two "found" tests flip once.
+    static const int64_t kRef[16] = {0, 0, 1, 0, 0, 1, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0};   // the column holds a reference letter (not I / S)
+    static const int64_t kQry[16] = {0, 1, 0, 0, 1, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0};   // ... a query letter (not D / H)
+    int64_t t = 0, nr = 0, nq = 0;   // tail length, its reference letters (t - c0) and query letters (t - c1)
+    int64_t a_r = ref_off == 0 ? 0 : -1, a_q = q_off == 0 ? 0 : -1, dh_r = 0, dh_q = 0;
+    size_t idx = v.size();   // run the cut falls into (or the first run of the tail), `part` leading columns of it stay in front
+    int64_t part = 0;
+    for (size_t i = v.size(); i-- > 0;) {
+        const int64_t len = v[i] >> 4;
+        const uint32_t op = v[i] & 15u;
+        const int64_t nr2 = nr + len * kRef[op], nq2 = nq + len * kQry[op];
+        if (a_r < 0 && nr2 >= ref_off) {   // a run of reference letters reaches the offset: the tail takes `need` of its columns
+            const int64_t need = ref_off - nr;
+            a_r = t + need; dh_r = (t - nq) + (kQry[op] ? 0 : need); idx = i; part = len - need;
+            if (a_q >= 0) break;
+        }
+        if (a_q < 0 && nq2 >= q_off) {     // a run of query letters (none of them D / H) reaches the offset
+            a_q = t + (q_off - nq); dh_q = t - nq;
+            if (a_r >= 0) break;
+        }
+        nr = nr2; nq = nq2; t += len;
+    }
+    const int64_t c1 = t - nq;
+    if (a_r < 0) { a_r = t; dh_r = c1; idx = 0; part = 0; }   // an offset beyond the sequence (callers never pass one): the whole string
+    if (a_q < 0) { a_q = t; dh_q = c1; }
     const int64_t diff = a_q - a_r;
     int64_t new_off;
-    if (a_q > a_r) new_off = diff - (ts.count(a_q, 1) - ts.count(a_r, 1));
-    else if (a_q != 0) new_off = diff + (ts.count(a_r, 1) - ts.count(a_q, 1));
-    else if (a_r != 0) new_off = diff + ts.count(a_r, 1);
+    if (a_q > a_r) new_off = diff - (dh_q - dh_r);
+    else if (a_q != 0) new_off = diff + (dh_r - dh_q);
+    else if (a_r != 0) new_off = diff + dh_r;
     else new_off = 0;
-    if (a_r > 0) {
-        const int64_t n = ts.cols0();
-        const int64_t head = a_r >= n ? 0 : n - a_r;  // columns that move to the back
-        // v is maximal, so after cutting at column `head` only the wrap-around junction (old last run, old first
-        // run) can merge; everything else moves as blocks
-        // idx = leading runs that lie before the cut entirely: one before the smallest i whose suffix holds fewer than n - head columns
-        int64_t sum[3];
-        const size_t lo = ts.first_suffix_within(n - head, true, sum);
-        const size_t idx = lo > 0 ? lo - 1 : 0;
-        const int64_t cols_idx = lo > 0 ? sum[0] + (int64_t)(v[idx] >> 4) : sum[0];
-        const int64_t acc = n - cols_idx;
-        const int64_t part = head - acc;  // leading columns of v[idx] that still lie before the cut (they move to the back)
-        if (idx > 0 || part > 0) {
-            thread_local Runs tl_rot;
-            Runs &t = tl_rot;
-            t.clear();
-            t.reserve(v.size() + 2);
-            size_t start = idx;
-            if (part > 0) { t.push_back((uint32_t)(((int64_t)(v[idx] >> 4) - part) << 4) | (v[idx] & 15u)); start = idx + 1; }
-            t.insert(t.end(), v.begin() + (std::ptrdiff_t)start, v.end());
-            if (idx > 0) {
-                push_run(t, v[0] & 15u, (int64_t)(v[0] >> 4));
-                t.insert(t.end(), v.begin() + 1, v.begin() + (std::ptrdiff_t)idx);
-            }
-            if (part > 0) push_run(t, v[idx] & 15u, part);
-            v.swap(t);   // the old array becomes the next call's scratch
+    // v is maximal, so after cutting only the wrap-around junction (old last run, old first run) can merge; everything else
+    // moves as blocks: [tail of v[idx]] v[idx+1 ..] + v[0] v[1 .. idx-1] [head of v[idx]]
+    if (a_r > 0 && (idx > 0 || part > 0)) {
+        thread_local Runs tl_rot;
+        Runs &r = tl_rot;
+        r.clear();
+        r.reserve(v.size() + 2);
+        size_t start = idx;
+        if (part > 0) { r.push_back((uint32_t)(((int64_t)(v[idx] >> 4) - part) << 4) | (v[idx] & 15u)); start = idx + 1; }
+        r.insert(r.end(), v.begin() + (std::ptrdiff_t)start, v.end());
+        if (idx > 0) {
+            push_run(r, v[0] & 15u, (int64_t)(v[0] >> 4));
+            r.insert(r.end(), v.begin() + 1, v.begin() + (std::ptrdiff_t)idx);
         }
+        if (part > 0) push_run(r, v[idx] & 15u, part);
+        v.swap(r);   // the old array becomes the next call's scratch
     }
     return new_off;
 }
