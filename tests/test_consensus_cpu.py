@@ -166,3 +166,44 @@ def test_statistics_table_file_and_selection(tmp_path):
     pdfs = [cs.SequenceBasecallQscorePDF(df_csv_path=p) for p in paths]
     for k, pdf in enumerate(pdfs):
         assert cs.select_sbq_pdf(pdf.q_score_distribution, paths).NanoporeStats_PDF_version == f"0.0.{k}"
+
+
+def test_zero_probabilities_infinities_and_nans_follow_the_fpu(harness):
+    """q-scores 0 and 42..92 hit zero entries of pdf_core (msa.py:683-687 smooths the rows 1..41 only; :705 pads with zeros):
+    factors 0 / x, x / 0 and 0 / 0.  The CPU replay of the entry point (restated multiplication with its zero / infinity /
+    NaN classes) must still equal the oracle's native long double, NaN for NaN."""
+    import math
+    from multiplexnanopore_b200 import consensus as cs
+    harness.smx_test_consensus.restype = ctypes.c_int
+    harness.smx_test_consensus.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_longlong] + [ctypes.c_void_p] * 5 + [ctypes.c_int] + [ctypes.c_void_p] * 3
+    t = gold()["tables"][1]
+    P, pdf = cs.SequenceBasecallQscorePDF(columns=t["columns"], counts=t["counts"]).tables()
+    with_prior, without_prior = cs.consensus_params(dict(error_rate=1e-3, ins_rate=1e-4))
+    rng = np.random.default_rng(77)
+    R, C = 12, 400
+    seq = rng.choice(np.frombuffer(b"ATCG-", np.uint8), size=(R, C), p=[0.23, 0.23, 0.23, 0.23, 0.08])
+    qs = rng.choice(np.array([-1, 0, 0, 5, 20, 41, 42, 60, 92], np.int8), size=(R, C))
+    qs[seq == ord("-")] = -1
+    cig = rng.choice(np.frombuffer(b"==XDHO", np.uint8), size=(R, C))
+    ref = rng.choice(np.frombuffer(b"ATCG-N", np.uint8), size=C)
+    letters = sorted(set(ref.tobytes().decode()))
+    col_class = np.array([letters.index(chr(x)) for x in ref], np.int32)
+    pn_w = np.array([[with_prior[ch][b] for b in cs.BASES] for ch in letters], np.float64)
+    pn_wo = np.array([[without_prior[ch][b] for b in cs.BASES] for ch in letters], np.float64)
+    p_w = np.zeros((C, 5)); p_wo = np.zeros((C, 5)); n_ev = np.zeros(C, np.int32)
+    rc = harness.smx_test_consensus(seq.ctypes.data, qs.ctypes.data, cig.ctypes.data, R, C, P.ctypes.data, pdf.ctypes.data, col_class.ctypes.data,
+                                    pn_w.ctypes.data, pn_wo.ctypes.data, len(letters), p_w.ctypes.data, p_wo.ctypes.data, n_ev.ctypes.data)
+    assert rc == 0
+    same = lambda a, b: all((math.isnan(x) and math.isnan(y)) or x == y for x, y in zip(a, b))
+    special = 0
+    for c in range(C):
+        votes = [(chr(seq[r, c]), int(qs[r, c])) for r in range(R) if cig[r, c] not in (ord("H"), ord("O"))]
+        assert n_ev[c] == len(votes)
+        if not votes:
+            continue
+        called, q = "".join(v[0] for v in votes), [v[1] for v in votes]
+        a = orc.consensus_error_rate(P, pdf, called, q, [with_prior[chr(ref[c])][b] for b in cs.BASES])
+        b = orc.consensus_error_rate(P, pdf, called, q, [without_prior[chr(ref[c])][b] for b in cs.BASES])
+        assert same(a, [float(x) for x in p_w[c]]) and same(b, [float(x) for x in p_wo[c]]), c
+        special += any(math.isnan(x) or math.isinf(x) for x in a)
+    assert special > 50, "the columns must reach the NaN / infinity paths"
